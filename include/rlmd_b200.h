@@ -1,0 +1,146 @@
+/*
+ * rlmd_b200 - C ABI of the B200-native engine for rlmd's multiplicative
+ * Monte-Carlo hot path (leverage sweeps, batched multiplicative env step,
+ * replay-buffer n-step sampling).
+ *
+ * The reference (majidsina/rlmd) is pure Python and has NO plugin / FFI layer
+ * (SURVEY.md section 8b): its boundary for this path is three sets of Python
+ * signatures.  Each entry point below names the reference interface it sits
+ * behind (file:line in the reference tree); rlmd_b200/{lev_exp,envs,
+ * replay_torch}.py are the same-named Python shims that bind them with ctypes
+ * (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the library never allocates or frees caller-visible memory;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - every call returns 0 or a negative B200_E* code; b200_last_error()
+ *     returns the message of the last failing call on the calling thread;
+ *   - no CPU fallback exists: without a CUDA device every compute entry point
+ *     returns B200_ECUDA.
+ */
+#ifndef RLMD_B200_H
+#define RLMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_EINVAL (-1)  /* bad argument (message says which) */
+#define B200_ECUDA (-2)   /* CUDA runtime / driver error */
+#define B200_ELIMIT (-3)  /* size outside what the kernels support */
+
+const char* b200_last_error(void);
+int b200_version(void);
+/* sm_count / cc_major / cc_minor of the current device */
+int b200_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ------------------------------------------------------------------ *
+ * Leverage sweep (K1)
+ *
+ * Sits behind lev/lev_exp.py: coin_fixed_final_lev :56, coin_smart_lev :128,
+ * dice_* :508/:586, gbm_* :935/:1008, dice_sh_* :1121/:1209 - the per-leverage
+ * loop `gambles = where(...); value = value_0 * prod / chain` (:83-87,
+ * :167-175 and siblings) for the whole grid in one launch.
+ * ------------------------------------------------------------------ */
+enum {
+  B200_LEV_DISCRETE = 0, /* coin / dice / dice_sh: factor table m[G][K]     */
+  B200_LEV_GBM = 1       /* factor exp(l*x), x fp32 log-returns, lev[G]      */
+};
+enum {
+  B200_SRC_STREAM = 0, /* pre-drawn outcomes [N,ld]: uint8 codes or fp32 x  */
+  B200_SRC_PHILOX = 1  /* outcomes drawn on device, Philox4x32-10           */
+};
+enum {
+  B200_MODE_CHAIN = 1, /* exact fp32 sequential product ((V0*m0)*m1)*...:
+                          bit-identical to *_smart_lev's data_T (discrete)   */
+  B200_MODE_LOG = 2    /* log-domain: integer outcome counts (discrete) or
+                          fp64 sum of x (GBM); fp64 log-wealth               */
+};
+
+#define B200_MAX_GRID 64
+#define B200_MAX_OUTCOMES 4
+
+typedef struct b200_lev_desc {
+  int64_t n_investors;     /* N: rows handled by this call (local shard)     */
+  int64_t ld_outcomes;     /* row stride of `outcomes` in ELEMENTS (>= H)    */
+  int64_t investor_offset; /* global id of row 0 (Philox counters, sharding) */
+  uint64_t seed;           /* Philox key                                     */
+  int32_t horizon;         /* H                                              */
+  int32_t n_grid;          /* G <= B200_MAX_GRID                             */
+  int32_t n_outcomes;      /* K in 2..4 (discrete); ignored for GBM          */
+  int32_t kind;            /* B200_LEV_*                                     */
+  int32_t source;          /* B200_SRC_*                                     */
+  int32_t mode;            /* B200_MODE_*                                    */
+  float value_0;           /* V0                                             */
+  float log_mean;          /* GBM Philox: mean of x  (mu - sigma^2/2)        */
+  float sigma;             /* GBM Philox: std of x                           */
+  int32_t variant;         /* CHAIN kernel variant: 0 = library default,
+                              1 FSEL, 2 predicated FMUL2, 3 LDS table (all
+                              bit-identical; exposed for benchmarking)        */
+  uint32_t thresholds[B200_MAX_OUTCOMES]; /* discrete Philox: outcome =
+                              #{k : draw >= thresholds[k]}, k < K-1, draw a
+                              uniform uint32; thresholds ascending            */
+} b200_lev_desc;
+
+/*
+ * outcomes : STREAM: uint8 [N,ld] (discrete, codes < K) or float [N,ld] (GBM);
+ *            PHILOX: NULL.
+ * factors_host : HOST pointer (the table is tiny and travels as a kernel
+ *            parameter).  Discrete: float [G,K] row-major, computed by the
+ *            caller with the reference's own fp32 expressions; GBM: float lev[G].
+ * data_T   : float [G,N] wealth after step H-1, or NULL.
+ *            CHAIN: the fp32 chain.  LOG: fl32(exp(log_w)) with the reference
+ *            dtype's saturation (inf once the running wealth left fp32 range,
+ *            0 once it underflowed: GBM tracks the running extremes).
+ * log_w    : double [G,N] log wealth (LOG mode), or NULL.
+ * counts   : int32 [N,K] occurrences of each outcome (discrete LOG), or NULL.
+ */
+int b200_lev_sweep(const b200_lev_desc* desc, const void* outcomes,
+                   const float* factors_host, float* data_T, double* log_w,
+                   int32_t* counts, void* stream);
+
+/* Materialises the outcomes a PHILOX sweep with `desc` consumes into
+ * out[N,ld] (uint8 codes or float x): lets a streamed run and the CPU oracle
+ * see the identical pre-drawn array. */
+int b200_lev_draw(const b200_lev_desc* desc, void* out, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * Row statistics (the reference's summary-statistic block)
+ *
+ * Sits behind the block inlined 13x in lev/lev_exp.py (e.g. :89-104,
+ * :177-192): sort(descending); top = s[:K]; adj = s[K:]; std_mean
+ * (population), lower median, MAD about the mean - for `rows` independent
+ * vectors of length n in one call.  Exact order statistics by radix select on
+ * the fp32 bit pattern (torch.sort order, NaN greatest).
+ *
+ * stats[r][12] (double), reference row order (lev/lev_exp.py:194-209):
+ *   mean, mean_top, mean_adj, mad, mad_top, mad_adj,
+ *   std, std_top, std_adj, med, med_top, med_adj.
+ * ------------------------------------------------------------------ */
+/* bytes of device workspace b200_rowstats needs for `rows` rows */
+int64_t b200_rowstats_workspace_bytes(int64_t rows);
+
+/* values: float [rows, ld] (row r at values + r*ld), n valid entries per row.
+ * n_total / top describe the GLOBAL vector when the rows are investor shards
+ * (multi-GPU): single-GPU callers pass n_total = n.
+ * phase = -1 runs every pass back to back (single GPU).  phase = 0..5 runs
+ * one pass; between passes a multi-GPU caller all-reduces (SUM) the
+ * workspace's exchange region (see b200_rowstats_exchange) across ranks. */
+int b200_rowstats(const float* values, int64_t rows, int64_t n, int64_t ld,
+                  int64_t n_total, int64_t top, void* workspace, double* stats,
+                  int32_t phase, void* stream);
+
+/* Per-row regions of the workspace (viewed as [rows, out[4]] 8-byte words) that
+ * must be summed across ranks after `phase`: out[0..1] = offset,count of the
+ * int64 words, out[2..3] = offset,count of the double words, out[4] = words per
+ * row. */
+int b200_rowstats_exchange(int32_t phase, int64_t out[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLMD_B200_H */

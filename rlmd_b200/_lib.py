@@ -1,0 +1,101 @@
+"""
+ctypes binding of librlmd_b200.so (include/rlmd_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises
+at import, and every compute entry point fails loudly without a CUDA device.
+Build it with `python -c "import __graft_entry__ as g; g.build()"` or `make`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librlmd_b200.so")
+
+B200_OK, B200_EINVAL, B200_ECUDA, B200_ELIMIT = 0, -1, -2, -3
+LEV_DISCRETE, LEV_GBM = 0, 1
+SRC_STREAM, SRC_PHILOX = 0, 1
+MODE_CHAIN, MODE_LOG = 1, 2
+MAX_GRID, MAX_OUTCOMES = 64, 4
+
+
+class LevDesc(C.Structure):
+    _fields_ = [
+        ("n_investors", C.c_int64),
+        ("ld_outcomes", C.c_int64),
+        ("investor_offset", C.c_int64),
+        ("seed", C.c_uint64),
+        ("horizon", C.c_int32),
+        ("n_grid", C.c_int32),
+        ("n_outcomes", C.c_int32),
+        ("kind", C.c_int32),
+        ("source", C.c_int32),
+        ("mode", C.c_int32),
+        ("value_0", C.c_float),
+        ("log_mean", C.c_float),
+        ("sigma", C.c_float),
+        ("variant", C.c_int32),
+        ("thresholds", C.c_uint32 * MAX_OUTCOMES),
+    ]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rlmd_b200 error {code}: {msg}")
+        self.code = code
+
+
+if not os.path.isfile(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build the CUDA library first (make, or __graft_entry__.build()); "
+        "rlmd_b200 has no CPU fallback"
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+_vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+_SIGNATURES = {
+    "b200_last_error": (C.c_char_p, []),
+    "b200_version": (C.c_int, []),
+    "b200_device_info": (C.c_int, [C.POINTER(_i32)] * 3),
+    "b200_lev_sweep": (C.c_int, [C.POINTER(LevDesc), _vp, C.POINTER(C.c_float), _vp, _vp, _vp, _vp]),
+    "b200_lev_draw": (C.c_int, [C.POINTER(LevDesc), _vp, _vp]),
+    "b200_rowstats_workspace_bytes": (_i64, [_i64]),
+    "b200_rowstats": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
+    "b200_rowstats_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),
+}
+# extended below as entry points are added; tests/test_cabi.py checks that every
+# symbol declared in include/rlmd_b200.h is listed here and exported.
+EXPORTS = _SIGNATURES
+
+
+def _bind():
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B200Error(rc, lib.b200_last_error().decode("utf-8", "replace"))
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise B200Error(B200_ECUDA, "no CUDA device: rlmd_b200 has no CPU fallback")
+
+
+def stream_ptr():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return C.c_void_p(0 if t is None else t.data_ptr())

@@ -1,0 +1,135 @@
+// Shared device/host helpers for the rlmd_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/rlmd_b200.h"
+
+namespace b200 {
+
+// ----------------------------------------------------------------- errors
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define B200_CUDA(expr)                                   \
+  do {                                                    \
+    int _rc = ::b200::check_cuda((expr), #expr);          \
+    if (_rc != 0) return _rc;                             \
+  } while (0)
+
+#define B200_REQUIRE(cond, ...)                                     \
+  do {                                                              \
+    if (!(cond)) return ::b200::set_error(B200_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+int sm_count();
+
+// ------------------------------------------------------------ Philox4x32-10
+// Counter-based generator (Salmon et al., SC'11).  Words are consumed as
+//   counter = (investor_id lo, investor_id hi, block index, stream tag)
+//   key     = (seed lo, seed hi)
+// so a draw depends only on (seed, global investor id, time block): results
+// are independent of the GPU count and of the launch geometry.
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                           uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += W0;
+    k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+enum : uint32_t {
+  PHILOX_TAG_LEV = 0x4C455600u,   // 'LEV'
+  PHILOX_TAG_ENV = 0x454E5600u,   // 'ENV'
+  PHILOX_TAG_REPLAY = 0x52504C00u // 'RPL'
+};
+
+// Box-Muller on two uniform words: u1 in (0,1], u2 in [0,1).
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float two_m32 = 2.3283064365386963e-10f;  // 2^-32
+  float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 24 bits, never 0
+  float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;
+  (void)two_m32;
+  float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// -------------------------------------------------------------- reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block; result valid in thread 0.  `scratch` holds >= 32 T.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  T r = (threadIdx.x < nw) ? scratch[threadIdx.x] : T(0);
+  if (wid == 0) r = warp_sum(r);
+  return r;
+}
+
+// Order-preserving map fp32 -> uint32 in torch.sort order (NaN greatest).
+__host__ __device__ __forceinline__ uint32_t float_key(float f) {
+  uint32_t b;
+#ifdef __CUDA_ARCH__
+  b = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } cv; cv.f = f; b = cv.u;
+#endif
+  if ((b & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;  // any NaN
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key_float(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  if (k == 0xffffffffu) b = 0x7fc00000u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  union { float f; uint32_t u; } cv; cv.u = b; return cv.f;
+#endif
+}
+
+}  // namespace b200

@@ -1,0 +1,234 @@
+"""
+Engine-level calls (thin ctypes wrappers; torch tensors are only buffers).
+
+Every function here launches CUDA kernels through the C ABI on the current
+torch stream and fails loudly without a GPU - there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LevDesc, check, lib, ptr, require_cuda, stream_ptr
+
+STAT_NAMES = (
+    "mean", "mean_top", "mean_adj", "mad", "mad_top", "mad_adj",
+    "std", "std_top", "std_adj", "med", "med_top", "med_adj",
+)
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def device_info() -> dict:
+    require_cuda()
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib.b200_device_info(C.byref(a), C.byref(b), C.byref(c)))
+    return {"sm_count": a.value, "cc": (b.value, c.value)}
+
+
+# ----------------------------------------------------------------- outcomes
+def encode_codes(outcomes, device="cuda") -> torch.Tensor:
+    """
+    Reference-format outcomes ([N,H] fp32 {0,1} for the coin, int64 {0,1,2} for
+    the dice; lev/coin_flip.py:160-161, lev/dice_roll.py:147-148) -> the engine
+    format: uint8 codes [N, ld] on the GPU with ld = H rounded up to 16 so that
+    the TMA path applies.  Returns a view [N,H] of the padded buffer.
+    """
+    require_cuda()
+    t = torch.as_tensor(outcomes)
+    n, h = t.shape
+    ld = _round_up(h, 16)
+    buf = torch.zeros((n, ld), dtype=torch.uint8, device=device)
+    buf[:, :h].copy_(t.to(device=device, non_blocking=True))
+    return buf[:, :h]
+
+
+def encode_returns(x, device="cuda") -> torch.Tensor:
+    """GBM log-returns -> fp32 [N, ld] on the GPU, ld a multiple of 4 (16 bytes)."""
+    require_cuda()
+    t = torch.as_tensor(x)
+    n, h = t.shape
+    ld = _round_up(h, 4)
+    buf = torch.zeros((n, ld), dtype=torch.float32, device=device)
+    buf[:, :h].copy_(t.to(device=device, non_blocking=True))
+    return buf[:, :h]
+
+
+def philox_thresholds(probs: Sequence[float]) -> list:
+    """Cumulative probabilities -> uint32 thresholds: code = #{k: u >= thr[k]}."""
+    thr, acc = [], 0.0
+    for p in probs[:-1]:
+        acc += float(p)
+        thr.append(min(int(math.floor(acc * 4294967296.0)), 0xFFFFFFFF))
+    return thr
+
+
+# -------------------------------------------------------------------- sweep
+def lev_sweep(
+    kind: str,
+    factors: np.ndarray,
+    value_0: float,
+    *,
+    outcomes: Optional[torch.Tensor] = None,
+    n_investors: Optional[int] = None,
+    horizon: Optional[int] = None,
+    mode: str = "chain",
+    want_data_T: bool = True,
+    want_log_w: bool = False,
+    want_counts: bool = False,
+    seed: int = 0,
+    investor_offset: int = 0,
+    probs: Optional[Sequence[float]] = None,
+    log_mean: float = 0.0,
+    sigma: float = 0.0,
+    variant: int = 0,
+    out_data_T: Optional[torch.Tensor] = None,
+    device=None,
+) -> dict:
+    """
+    One launch over the whole leverage grid (b200_lev_sweep).
+
+    kind      "discrete" (factors [G,K] fp32) or "gbm" (factors = lev[G] fp32)
+    outcomes  CUDA tensor [N,H] uint8 (discrete) / float32 (gbm), row stride
+              arbitrary (unit inner stride); None -> Philox draws on device
+    mode      "chain" (exact fp32 product; discrete only) or "log"
+    returns   {"data_T": [G,N] f32, "log_w": [G,N] f64, "counts": [N,K] i32}
+    """
+    require_cuda()
+    f = np.ascontiguousarray(factors, dtype=np.float32)
+    d = LevDesc()
+    if kind == "discrete":
+        d.kind = _lib.LEV_DISCRETE
+        g, k = f.shape
+        d.n_outcomes = k
+    elif kind == "gbm":
+        d.kind = _lib.LEV_GBM
+        g, k = f.shape[0], 0
+    else:
+        raise ValueError("kind must be 'discrete' or 'gbm'")
+    d.n_grid = g
+    d.mode = {"chain": _lib.MODE_CHAIN, "log": _lib.MODE_LOG}[mode]
+    d.value_0 = float(value_0)
+    d.variant = int(variant)
+    d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    d.investor_offset = int(investor_offset)
+    d.log_mean, d.sigma = float(log_mean), float(sigma)
+    if outcomes is not None:
+        if not outcomes.is_cuda:
+            raise ValueError("outcomes must live on the GPU (see encode_codes / encode_returns)")
+        want = torch.uint8 if kind == "discrete" else torch.float32
+        if outcomes.dtype != want or outcomes.dim() != 2 or outcomes.stride(1) != 1:
+            raise ValueError(f"outcomes must be a [N,H] {want} tensor with unit inner stride")
+        n, h = outcomes.shape
+        d.source = _lib.SRC_STREAM
+        d.ld_outcomes = outcomes.stride(0) if n > 1 else max(outcomes.stride(0), h)
+        dev = outcomes.device
+    else:
+        if n_investors is None or horizon is None:
+            raise ValueError("Philox mode needs n_investors and horizon")
+        n, h = int(n_investors), int(horizon)
+        d.source = _lib.SRC_PHILOX
+        d.ld_outcomes = h
+        dev = torch.device(device or "cuda")
+        if kind == "discrete":
+            thr = philox_thresholds(probs)
+            for i, v in enumerate(thr):
+                d.thresholds[i] = v
+    d.n_investors, d.horizon = n, h
+
+    res = {}
+    with torch.cuda.device(dev):
+        data_T = log_w = counts = None
+        if want_data_T:
+            data_T = out_data_T if out_data_T is not None else torch.empty((g, n), dtype=torch.float32, device=dev)
+            assert data_T.shape == (g, n) and data_T.is_contiguous() and data_T.dtype == torch.float32
+        if want_log_w:
+            log_w = torch.empty((g, n), dtype=torch.float64, device=dev)
+        if want_counts:
+            counts = torch.empty((n, k), dtype=torch.int32, device=dev)
+        check(lib.b200_lev_sweep(C.byref(d), ptr(outcomes), f.ctypes.data_as(C.POINTER(C.c_float)),
+                                 ptr(data_T), ptr(log_w), ptr(counts), stream_ptr()))
+    res["data_T"], res["log_w"], res["counts"] = data_T, log_w, counts
+    return res
+
+
+def lev_draw(kind: str, n_investors: int, horizon: int, *, seed: int = 0, investor_offset: int = 0,
+             probs=None, log_mean: float = 0.0, sigma: float = 0.0, device="cuda") -> torch.Tensor:
+    """The outcome array a Philox sweep with the same arguments consumes."""
+    require_cuda()
+    d = LevDesc()
+    d.n_investors, d.horizon = int(n_investors), int(horizon)
+    d.n_grid, d.mode, d.source = 1, _lib.MODE_LOG, _lib.SRC_PHILOX
+    d.seed, d.investor_offset = int(seed) & 0xFFFFFFFFFFFFFFFF, int(investor_offset)
+    if kind == "discrete":
+        d.kind, d.n_outcomes = _lib.LEV_DISCRETE, len(probs)
+        for i, v in enumerate(philox_thresholds(probs)):
+            d.thresholds[i] = v
+        ld = _round_up(horizon, 16)
+        out = torch.zeros((n_investors, ld), dtype=torch.uint8, device=device)
+    else:
+        d.kind, d.log_mean, d.sigma = _lib.LEV_GBM, float(log_mean), float(sigma)
+        ld = _round_up(horizon, 4)
+        out = torch.zeros((n_investors, ld), dtype=torch.float32, device=device)
+    d.ld_outcomes = ld
+    with torch.cuda.device(out.device):
+        check(lib.b200_lev_draw(C.byref(d), ptr(out), stream_ptr()))
+    return out[:, :horizon]
+
+
+# ----------------------------------------------------------------- rowstats
+def rowstats_workspace(rows: int, device) -> torch.Tensor:
+    nbytes = lib.b200_rowstats_workspace_bytes(rows)
+    return torch.empty((rows, nbytes // 8 // max(rows, 1)), dtype=torch.int64, device=device)
+
+
+def rowstats(values: torch.Tensor, top: int, *, n_total: Optional[int] = None, group=None,
+             workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """
+    The reference's 12 summary statistics for every row of `values` [rows, n]
+    (fp32, CUDA, unit inner stride) -> float64 [rows, 12] (STAT_NAMES order).
+
+    With `group` (a torch.distributed process group) the rows are investor
+    shards of a global vector of n_total entries: histograms and partial sums are
+    all-reduced between passes, every rank returns the global statistics.
+    """
+    require_cuda()
+    if values.dim() != 2 or values.dtype != torch.float32 or not values.is_cuda or values.stride(1) != 1:
+        raise ValueError("values must be a [rows,n] float32 CUDA tensor with unit inner stride")
+    rows, n = values.shape
+    ld = values.stride(0) if rows > 1 else max(values.stride(0), n)
+    n_total = n if n_total is None else int(n_total)
+    dev = values.device
+    stats = torch.empty((rows, 12), dtype=torch.float64, device=dev)
+    if rows == 0:
+        return stats
+    with torch.cuda.device(dev):
+        ws = workspace if workspace is not None else rowstats_workspace(rows, dev)
+        if group is None:
+            check(lib.b200_rowstats(ptr(values), rows, n, ld, n_total, int(top), ptr(ws), ptr(stats), -1, stream_ptr()))
+            return stats
+        import torch.distributed as dist
+
+        ex = (C.c_int64 * 5)()
+        wsf = ws.view(torch.float64)
+        for phase in range(6):
+            check(lib.b200_rowstats(ptr(values), rows, n, ld, n_total, int(top), ptr(ws), ptr(stats), phase,
+                                    stream_ptr()))
+            check(lib.b200_rowstats_exchange(phase, ex))
+            io, ic, do, dc, _ = list(ex)
+            if ic:
+                part = ws[:, io:io + ic].contiguous()
+                dist.all_reduce(part, group=group)
+                ws[:, io:io + ic] = part
+            if dc:
+                part = wsf[:, do:do + dc].contiguous()
+                dist.all_reduce(part, group=group)
+                wsf[:, do:do + dc] = part
+    return stats

@@ -1,0 +1,158 @@
+"""
+Drop-in for the reference's `lev/lev_exp.py`: the same function names,
+positional signatures, return types, printed text and output layouts, with the
+per-leverage / per-time-step Python loops replaced by CUDA launches
+(rlmd_b200.engine -> librlmd_b200.so).
+
+    sys.modules["lev.lev_exp"] = rlmd_b200.lev_exp
+
+Reference behaviour kept on the host, verbatim in meaning:
+  * `param_range` - the grid with its truncation quirks (lev/lev_exp.py:29-53);
+  * the grid becomes an fp32 tensor and is negated iff -down_r > up_r
+    (:80-81 and siblings; never for GBM :961,1042);
+  * factors are evaluated left to right in fp32 on 0-dim operands
+    (`1 + lev * up_r`, `1 + lev * r + (1 - lev) * sh`; :85, :541-543, :1160-1166).
+The sweeps run in CHAIN mode (exact fp32 sequential product), so `data_T` of
+the coin / dice / dice_sh functions is bit-identical to the reference's.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+import torch as T
+
+from . import engine
+
+_F32 = np.float32
+
+
+# ------------------------------------------------------------------- grid
+def param_range(low: float, high: float, increment: float) -> list:
+    """List of grid values from `low` to `high` in steps of `increment`.
+
+    Python-double arithmetic with the reference's integer truncations
+    (lev/lev_exp.py:29-53): int(low/incr) .. int(high/incr + 1), the fractional
+    offset of `low` added back, an exact 0 dropped unless it is the only value.
+    """
+    k_lo = int(low / increment)
+    k_hi = int(high / increment + 1)
+    offset = low / increment - k_lo
+    values = []
+    for k in range(k_lo, k_hi):
+        values.append((k + offset) * increment)
+    if 0 in values and len(values) != 1:
+        values.remove(0)
+    return values
+
+
+def _grid(lev_low, lev_high, lev_incr, up_r=None, down_r=None) -> np.ndarray:
+    g = np.asarray(param_range(lev_low, lev_high, lev_incr), dtype=_F32)
+    if up_r is not None and -down_r > up_r:
+        g = -g
+    return g
+
+
+def _lin(lev: np.ndarray, r: float) -> np.ndarray:
+    """fl32(1 + fl32(lev * fl32(r)))"""
+    return (_F32(1) + lev * _F32(r)).astype(_F32)
+
+
+def coin_factor_table(lev: np.ndarray, up_r: float, down_r: float) -> np.ndarray:
+    """[G,2]: column = outcome value (0 = down, 1 = up), lev/lev_exp.py:85."""
+    return np.stack([_lin(lev, down_r), _lin(lev, up_r)], axis=1)
+
+
+def dice_factor_table(lev, up_r, down_r, mid_r) -> np.ndarray:
+    """[G,3]: code 0 up, 1 down, 2 mid (lev/lev_exp.py:541-543)."""
+    return np.stack([_lin(lev, up_r), _lin(lev, down_r), _lin(lev, mid_r)], axis=1)
+
+
+def dice_sh_factor_table(lev, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r) -> np.ndarray:
+    """[G,3]: (1 + l r) + (1 - l) sh in fp32 (lev/lev_exp.py:1160-1166)."""
+    one_minus = (_F32(1) - lev).astype(_F32)
+    cols = []
+    for r, sh in ((up_r, sh_up_r), (down_r, sh_down_r), (mid_r, sh_mid_r)):
+        cols.append((_lin(lev, r) + (one_minus * _F32(sh)).astype(_F32)).astype(_F32))
+    return np.stack(cols, axis=1)
+
+
+def grid2d_factor_table(a, b, returns, sh_returns) -> np.ndarray:
+    """Engine-only 2-D grid (leverage x insurance fraction): m = (1 + a r) + b sh."""
+    a = np.asarray(a, dtype=_F32)
+    b = np.asarray(b, dtype=_F32)
+    cols = [(_lin(a, r) + (b * _F32(s)).astype(_F32)).astype(_F32) for r, s in zip(returns, sh_returns)]
+    return np.stack(cols, axis=1)
+
+
+# -------------------------------------------------------------- plumbing
+def _as_int(x) -> int:
+    return int(x.item()) if isinstance(x, T.Tensor) else int(x)
+
+
+def _as_float(x) -> float:
+    return float(x.item()) if isinstance(x, T.Tensor) else float(x)
+
+
+def _codes(outcomes) -> T.Tensor:
+    if isinstance(outcomes, T.Tensor) and outcomes.is_cuda and outcomes.dtype == T.uint8:
+        return outcomes  # already in the engine format
+    return engine.encode_codes(outcomes)
+
+
+def _returns(outcomes) -> T.Tensor:
+    if isinstance(outcomes, T.Tensor) and outcomes.is_cuda and outcomes.dtype == T.float32 \
+            and outcomes.stride(1) == 1 and outcomes.stride(0) % 4 == 0:
+        return outcomes
+    return engine.encode_returns(outcomes)
+
+
+_FINAL_FMT = """       lev {:1.0f}%:
+                 avg mean/med/mad/std:  $ {:1.2e} / {:1.2e} / {:1.1e} / {:1.1e}
+                 top mean/med/mad/std:  $ {:1.2e} / {:1.2e} / {:1.1e} / {:1.1e}
+                 adj mean/med/mad/std:  $ {:1.2e} / {:1.2e} / {:1.1e} / {:1.1e}"""
+
+
+def _print_final(lev: np.ndarray, stats: np.ndarray) -> None:
+    """The reference's per-leverage report (lev/lev_exp.py:106-125)."""
+    for l, s in zip(lev, stats.astype(_F32)):
+        mean, mean_top, mean_adj, mad, mad_top, mad_adj, std, std_top, std_adj, med, med_top, med_adj = s
+        print(_FINAL_FMT.format(float(l) * 100, mean, med, mad, std, mean_top, med_top, mad_top, std_top,
+                                mean_adj, med_adj, mad_adj, std_adj))
+
+
+def _final(kind, outcomes, table, lev, top, value_0, mode="chain"):
+    res = engine.lev_sweep(kind, table, _as_float(value_0), outcomes=outcomes, mode=mode)
+    stats = engine.rowstats(res["data_T"], int(top))
+    return res["data_T"], stats.cpu().numpy()
+
+
+# ----------------------------------------------------- fixed final leverage
+def coin_fixed_final_lev(device, outcomes, top, value_0, up_r, down_r, lev_low, lev_high, lev_incr):
+    """lev/lev_exp.py:56-125 - prints the final-time statistics per leverage."""
+    lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
+    _, stats = _final("discrete", _codes(outcomes), coin_factor_table(lev, up_r, down_r), lev, top, value_0)
+    _print_final(lev, stats)
+
+
+def dice_fixed_final_lev(device, outcomes, top, value_0, up_r, down_r, mid_r, lev_low, lev_high, lev_incr):
+    """lev/lev_exp.py:508-583."""
+    lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
+    _, stats = _final("discrete", _codes(outcomes), dice_factor_table(lev, up_r, down_r, mid_r), lev, top, value_0)
+    _print_final(lev, stats)
+
+
+def dice_sh_fixed_final_lev(device, outcomes, top, value_0, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r,
+                            lev_low, lev_high, lev_incr):
+    """lev/lev_exp.py:1121-1206."""
+    lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
+    table = dice_sh_factor_table(lev, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r)
+    _, stats = _final("discrete", _codes(outcomes), table, lev, top, value_0)
+    _print_final(lev, stats)
+
+
+def gbm_fixed_final_lev(device, outcomes, top, value_0, lev_low, lev_high, lev_incr):
+    """lev/lev_exp.py:935-1005 (no sign flip of the grid)."""
+    lev = _grid(lev_low, lev_high, lev_incr)
+    _, stats = _final("gbm", _returns(outcomes), lev, lev, top, value_0, mode="log")
+    _print_final(lev, stats)

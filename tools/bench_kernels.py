@@ -1,0 +1,111 @@
+"""
+Kernel-level timings on one B200 (CUDA events on the launching stream, L2
+flushed by inputs much larger than L2).  Writes JSON lines to stdout.
+
+    python tools/bench_kernels.py [--n 1000000] [--h 10000]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rlmd_b200 import engine, lev_exp  # noqa: E402
+
+
+def timeit(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return min(ts), float(np.median(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--h", type=int, default=10_000)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    n, h = a.n, a.h
+    peaks = {}
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peaks = json.load(open(p))
+    hbm = peaks.get("hbm_gbs", 6650.0)
+
+    def emit(name, best, med, steps, bytes_per_step, **kw):
+        rec = dict(kernel=name, n=n, h=h, best_s=best, median_s=med, investor_steps_per_s=steps / best,
+                   algorithmic_GBps=steps * bytes_per_step / best / 1e9,
+                   hbm_frac=steps * bytes_per_step / best / 1e9 / hbm, **kw)
+        print(json.dumps(rec), flush=True)
+
+    dice = engine.lev_draw("discrete", n, h, seed=420, probs=(1 / 6, 1 / 6, 2 / 3))
+    coin = None
+    lev10 = np.asarray(lev_exp.param_range(0.1, 1.0, 0.1), np.float32)
+    lev20 = np.asarray(lev_exp.param_range(0.05, 1.0, 0.05), np.float32)
+    out10 = torch.empty((10, n), dtype=torch.float32, device="cuda")
+    out20 = torch.empty((20, n), dtype=torch.float32, device="cuda")
+    steps = n * h
+    if a.only in ("", "chain"):
+        for g, lev, out in ((10, lev10, out10), (20, lev20, out20)):
+            f = lev_exp.dice_factor_table(lev, 0.5, -0.5, 0.05)
+            for v in (1, 2, 3):
+                b, m = timeit(lambda: engine.lev_sweep("discrete", f, 100.0, outcomes=dice, mode="chain",
+                                                        variant=v, out_data_T=out))
+                emit(f"chain_dice_G{g}_v{v}", b, m, steps, 1, G=g, path_steps_per_s=steps * g / b)
+        coin = engine.lev_draw("discrete", n, h, seed=421, probs=(0.5, 0.5))
+        f = lev_exp.coin_factor_table(lev10, 0.5, -0.4)
+        for v in (1, 2, 3):
+            b, m = timeit(lambda: engine.lev_sweep("discrete", f, 100.0, outcomes=coin, mode="chain", variant=v,
+                                                    out_data_T=out10))
+            emit(f"chain_coin_G10_v{v}", b, m, steps, 1, G=10, path_steps_per_s=steps * 10 / b)
+        del coin
+    if a.only in ("", "log"):
+        f = lev_exp.dice_factor_table(lev10, 0.5, -0.5, 0.05)
+        b, m = timeit(lambda: engine.lev_sweep("discrete", f, 100.0, outcomes=dice, mode="log", out_data_T=out10))
+        emit("log_dice_G10", b, m, steps, 1, G=10)
+    if a.only in ("", "stats"):
+        b, m = timeit(lambda: engine.rowstats(out10, max(1, n // 10000)))
+        print(json.dumps(dict(kernel="rowstats_10rows", n=n, best_s=b, median_s=m,
+                              GBps_5pass=5 * 10 * n * 4 / b / 1e9)), flush=True)
+    if a.only in ("", "philox"):
+        f = lev_exp.dice_factor_table(lev10, 0.5, -0.5, 0.05)
+        for v in (1, 2, 3):
+            b, m = timeit(lambda: engine.lev_sweep("discrete", f, 100.0, n_investors=n, horizon=h, seed=1,
+                                                    probs=(1 / 6, 1 / 6, 2 / 3), mode="chain", variant=v,
+                                                    out_data_T=out10), warm=1, reps=3)
+            emit(f"chain_dice_philox_G10_v{v}", b, m, steps, 0, G=10, path_steps_per_s=steps * 10 / b)
+    del dice
+    if a.only in ("", "gbm"):
+        levg = np.asarray(lev_exp.param_range(-1.0, 1.0, 0.2), np.float32)
+        ng = n // 4
+        x = engine.lev_draw("gbm", ng, h, seed=3, log_mean=0.05 - 0.1, sigma=0.2 ** 0.5)
+        outg = torch.empty((10, ng), dtype=torch.float32, device="cuda")
+        b, m = timeit(lambda: engine.lev_sweep("gbm", levg, 100.0, outcomes=x, mode="log", out_data_T=outg))
+        rec_steps = ng * h
+        print(json.dumps(dict(kernel="gbm_stream_G10", n=ng, h=h, best_s=b, median_s=m,
+                              investor_steps_per_s=rec_steps / b, algorithmic_GBps=rec_steps * 4 / b / 1e9,
+                              hbm_frac=rec_steps * 4 / b / 1e9 / hbm)), flush=True)
+        del x
+        npx = 12_500_000 if n >= 1_000_000 else n
+        outp = torch.empty((10, npx), dtype=torch.float32, device="cuda")
+        b, m = timeit(lambda: engine.lev_sweep("gbm", levg, 100.0, n_investors=npx, horizon=h, seed=3,
+                                                log_mean=0.05 - 0.1, sigma=0.2 ** 0.5, mode="log",
+                                                out_data_T=outp), warm=1, reps=3)
+        print(json.dumps(dict(kernel="gbm_philox_G10", n=npx, h=h, best_s=b, median_s=m,
+                              investor_steps_per_s=npx * h / b)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
