@@ -8,7 +8,7 @@ LIB := rlmd_b200/librlmd_b200.so
 
 all: $(LIB)
 
-build/%.o: rlmd_b200/csrc/%.cu rlmd_b200/csrc/common.cuh include/rlmd_b200.h
+build/%.o: rlmd_b200/csrc/%.cu $(wildcard rlmd_b200/csrc/*.cuh) include/rlmd_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 

@@ -79,7 +79,7 @@ typedef struct b200_lev_desc {
   float log_mean;          /* GBM Philox: mean of x  (mu - sigma^2/2)        */
   float sigma;             /* GBM Philox: std of x                           */
   int32_t variant;         /* CHAIN kernel variant: 0 = library default,
-                              1 FSEL, 2 predicated FMUL2, 3 LDS table (all
+                              1 FSEL, 2 LDS table (both
                               bit-identical; exposed for benchmarking)        */
   uint32_t thresholds[B200_MAX_OUTCOMES]; /* discrete Philox: outcome =
                               #{k : draw >= thresholds[k]}, k < K-1, draw a
@@ -102,6 +102,23 @@ typedef struct b200_lev_desc {
 int b200_lev_sweep(const b200_lev_desc* desc, const void* outcomes,
                    const float* factors_host, float* data_T, double* log_w,
                    int32_t* counts, void* stream);
+
+/*
+ * Per-step series (K2): steps [t_begin, t_end) of the sweep with the wealth
+ * after EVERY step written out, for the per-step statistics of *_smart_lev
+ * (lev/lev_exp.py:167-212 and siblings: `for lev: for t: value_t = ...; sort;
+ * std_mean; median`).  The caller walks the horizon in chunks, runs
+ * b200_rowstats over the [G * chunk] rows of `dump` and scatters the 12
+ * statistics into data[G,13,H-1]; after the last chunk `state` holds data_T.
+ *
+ * state : discrete (CHAIN): float [G,N] wealth, in/out (ignored as input when
+ *         t_begin == 0); GBM: double [3,N] = running sum of x, its max, its min.
+ * dump  : float [G, t_end - t_begin, N] or NULL (advance the state only).
+ * t_begin must be a multiple of 4 (discrete Philox) / 32 (GBM).
+ */
+int b200_lev_chunk(const b200_lev_desc* desc, const void* outcomes,
+                   const float* factors_host, int32_t t_begin, int32_t t_end,
+                   void* state, float* dump, void* stream);
 
 /* Materialises the outcomes a PHILOX sweep with `desc` consumes into
  * out[N,ld] (uint8 codes or float x): lets a streamed run and the CPU oracle

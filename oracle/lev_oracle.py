@@ -186,11 +186,16 @@ def lower_median(v: np.ndarray) -> float:
 def group_stats(v: np.ndarray):
     """(mean, mad, std, med) of one group, fp64 accumulation, population std."""
     v64 = v.astype(np.float64)
+    med = float("nan") if np.isnan(v).any() else float(lower_median(v))
+    if not np.isfinite(v64).all():
+        # torch.std_mean runs Welford's update: one inf (then inf - inf) makes the
+        # mean, hence std and MAD, nan (seen in tests/golden/lev_coin_overflow.npz)
+        return float("nan"), float("nan"), float("nan"), med
     with np.errstate(over="ignore", invalid="ignore"):
         mean = v64.mean()
         mad = np.abs(v64 - mean).mean()
-        std = math.sqrt(((v64 - mean) ** 2).mean()) if np.isfinite(mean) else float("nan")
-    return mean, mad, std, float(lower_median(v))
+        std = math.sqrt(((v64 - mean) ** 2).mean())
+    return mean, mad, std, med
 
 
 def summary_stats(v: np.ndarray, top: int) -> np.ndarray:

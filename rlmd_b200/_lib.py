@@ -59,6 +59,7 @@ _SIGNATURES = {
     "b200_device_info": (C.c_int, [C.POINTER(_i32)] * 3),
     "b200_lev_sweep": (C.c_int, [C.POINTER(LevDesc), _vp, C.POINTER(C.c_float), _vp, _vp, _vp, _vp]),
     "b200_lev_draw": (C.c_int, [C.POINTER(LevDesc), _vp, _vp]),
+    "b200_lev_chunk": (C.c_int, [C.POINTER(LevDesc), _vp, C.POINTER(C.c_float), _i32, _i32, _vp, _vp, _vp]),
     "b200_rowstats_workspace_bytes": (_i64, [_i64]),
     "b200_rowstats": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "b200_rowstats_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),

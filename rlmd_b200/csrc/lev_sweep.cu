@@ -1,316 +1,23 @@
-// K1: leverage sweep, final-time wealth for the whole grid in one launch.
+// K1: leverage sweep entry points (b200_lev_sweep / b200_lev_chunk / b200_lev_draw)
+// and the kernels that do not depend on the grid-tile templates.
 //
-// Reference: lev/lev_exp.py - the per-leverage loop of *_fixed_final_lev
-// (:83-87, :539-545, :963-967, :1158-1168) and the sequential chain of
-// *_smart_lev (:167-175, :629-640, :1048-1055, :1258-1273).
-//
-// CHAIN mode (discrete): one thread per investor, G wealth registers, the exact
-//   fp32 product ((V0*m_0)*m_1)*... in time order.  Outcome bytes [N,ld] are
-//   staged through shared memory in [128 investors x 128 steps] tiles by TMA
-//   (cp.async.bulk.tensor.2d, 128-byte swizzle => the per-thread row reads are
-//   16-byte LDS without bank conflicts) behind a ring of mbarriers.  Rows whose
-//   stride or base is not 16-byte aligned take a cooperative plain-load path
-//   into the same swizzled layout.
 // LOG mode (discrete): wealth depends on the outcomes only through their
 //   counts, so one warp sweeps one investor row with coalesced 16-byte loads and
 //   counts codes with dp4a; HBM-bound, G-independent.
 // LOG mode (GBM): running sum of x with its running extremes (to reproduce the
 //   reference dtype's overflow/underflow saturation), thread per investor over
 //   TMA-staged fp32 tiles, or Philox + Box-Muller draws in registers.
-#include <cuda.h>
-
-#include <cmath>
-#include <cstring>
-
-#include "common.cuh"
+// CHAIN mode kernels live in lev_kernels.cuh / lev_chain_k*.cu.
+#include "lev_kernels.cuh"
 
 namespace b200 {
 
-constexpr int TILE_ROWS = 128;   // investors per block
-constexpr int TILE_BYTES = 128;  // bytes of one investor's row per tile (swizzle span)
-constexpr int STAGES = 4;
-constexpr int TILE_SMEM = TILE_ROWS * TILE_BYTES;  // 16 KB
-
-struct FactorTable {
-  float m[B200_MAX_OUTCOMES][32];  // [k][g] for one grid tile of <= 32 points
-};
 struct LogFactorTable {
   double lm[B200_MAX_OUTCOMES][B200_MAX_GRID];  // log m[k][g]
 };
 struct LevGrid {
   float lev[B200_MAX_GRID];
 };
-
-// ------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-// 16-byte chunk `c` of tile row `r` under the 128-byte swizzle.
-__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * TILE_BYTES + ((c ^ (r & 7)) << 4)); }
-
-// ------------------------------------------------------- one chain step
-// Three bit-identical ways to apply w[g] *= m[code][g] for the whole grid tile
-// (each is one IEEE fp32 multiply per path-step; they differ in how the factor
-// is selected, i.e. in which pipes they load - see DESIGN.md "chain variants"):
-//   V_FSEL : per g, (K-1) FSEL from constant-bank factors + 1 FMUL
-//   V_PRED2: K divergent arms of packed FMUL2 (mul.rn.f32x2) by constant-bank factors
-//   V_LDS  : factor rows m[code][*] fetched from a shared-memory table with
-//            LDS.128 (broadcast across lanes that saw the same code) + FMUL2
-enum { V_FSEL = 0, V_PRED2 = 1, V_LDS = 2 };
-
-template <int GT>
-struct GridTile {
-  static constexpr int PAD = (GT + 3) & ~3;                    // floats per table row, multiple of 4
-  static constexpr int STRIDE = (PAD % 16 == 0) ? PAD + 4 : PAD;  // rows of different codes on disjoint banks
-};
-
-template <int GT, int K, int V>
-struct ChainState {
-  float w[GT];
-  __device__ __forceinline__ void init(float v0) {
-#pragma unroll
-    for (int g = 0; g < GT; ++g) w[g] = v0;
-  }
-};
-
-template <int GT, int K, int V>
-__device__ __forceinline__ void chain_step(float (&w)[GT], const FactorTable& f, const float* __restrict__ tab,
-                                           uint32_t code) {
-  if (V == V_LDS) {
-    constexpr int S = GridTile<GT>::STRIDE;
-    const float4* __restrict__ row = reinterpret_cast<const float4*>(tab + code * S);
-#pragma unroll
-    for (int c = 0; c < GridTile<GT>::PAD / 4; ++c) {
-      const float4 m = row[c];
-      const int g = 4 * c;
-      if (g + 1 < GT) {
-        const float2 r = __fmul2_rn(make_float2(w[g], w[g + 1]), make_float2(m.x, m.y));
-        w[g] = r.x; w[g + 1] = r.y;
-      } else if (g < GT) {
-        w[g] = __fmul_rn(w[g], m.x);
-      }
-      if (g + 3 < GT) {
-        const float2 r = __fmul2_rn(make_float2(w[g + 2], w[g + 3]), make_float2(m.z, m.w));
-        w[g + 2] = r.x; w[g + 3] = r.y;
-      } else if (g + 2 < GT) {
-        w[g + 2] = __fmul_rn(w[g + 2], m.z);
-      }
-    }
-  } else if (V == V_PRED2) {
-    // divergent branches: each arm is straight-line packed multiplies by
-    // constant-bank factors; lanes that saw another code sit the arm out
-    static_assert(GT % 2 == 0, "packed variant needs an even grid tile");
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (code == (uint32_t)k) {
-#pragma unroll
-        for (int g = 0; g < GT; g += 2) {
-          const float2 r = __fmul2_rn(make_float2(w[g], w[g + 1]), make_float2(f.m[k][g], f.m[k][g + 1]));
-          w[g] = r.x; w[g + 1] = r.y;
-        }
-      }
-    }
-  } else {
-    const bool is1 = code == 1, is2 = code == 2, is3 = code == 3;
-#pragma unroll
-    for (int g = 0; g < GT; ++g) {
-      float m = f.m[0][g];
-      m = (K == 2 ? code != 0 : is1) ? f.m[1][g] : m;
-      if (K >= 3) m = is2 ? f.m[2][g] : m;
-      if (K >= 4) m = is3 ? f.m[3][g] : m;
-      w[g] = __fmul_rn(w[g], m);
-    }
-  }
-}
-
-template <int GT, int K, int V>
-__device__ __forceinline__ void chain_word(float (&w)[GT], const FactorTable& f, const float* __restrict__ tab,
-                                           uint32_t word) {
-#pragma unroll
-  for (int b = 0; b < 4; ++b) chain_step<GT, K, V>(w, f, tab, (word >> (8 * b)) & 0xffu);
-}
-
-template <int GT, int K>
-__device__ __forceinline__ void fill_table(float* tab, const FactorTable& f) {
-  constexpr int S = GridTile<GT>::STRIDE;
-  for (int i = threadIdx.x; i < K * S; i += blockDim.x) {
-    const int k = i / S, g = i - k * S;
-    tab[i] = g < GT ? f.m[k][g] : 1.0f;
-  }
-}
-
-// --------------------------------------------- CHAIN, discrete, streamed
-// USE_TMA: tiles arrive by cp.async.bulk.tensor; otherwise all threads copy.
-template <int GT, int K, int V, bool USE_TMA>
-__global__ void __launch_bounds__(TILE_ROWS)
-chain_discrete_stream_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ outcomes,
-                             int64_t ld, const __grid_constant__ FactorTable f, int32_t H, int64_t N,
-                             int32_t G, float V0, float* __restrict__ data_T, int64_t ldT) {
-  extern __shared__ __align__(1024) uint8_t tiles[];
-  __shared__ __align__(8) uint64_t full[STAGES];
-  __shared__ __align__(16) float tab[V == V_LDS ? K * GridTile<GT>::STRIDE : 4];
-
-  const int tid = threadIdx.x;
-  const int64_t row0 = (int64_t)blockIdx.x * TILE_ROWS;
-  const int ntiles = (H + TILE_BYTES - 1) / TILE_BYTES;
-
-  if (V == V_LDS) fill_table<GT, K>(tab, f);
-  if (USE_TMA) {
-    if (tid == 0) {
-      for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
-      fence_barrier_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const int pre = ntiles < STAGES ? ntiles : STAGES;
-      for (int s = 0; s < pre; ++s) {
-        mbar_expect_tx(&full[s], TILE_SMEM);
-        tma_load_2d(tiles + s * TILE_SMEM, &tmap, &full[s], s * TILE_BYTES, (int)row0);
-      }
-    }
-  } else {
-    __syncthreads();
-  }
-
-  float w[GT];
-#pragma unroll
-  for (int g = 0; g < GT; ++g) w[g] = V0;
-
-  for (int kt = 0; kt < ntiles; ++kt) {
-    const int s = USE_TMA ? kt % STAGES : 0;
-    uint8_t* tile = tiles + s * TILE_SMEM;
-    if (USE_TMA) {
-      mbar_wait(&full[s], (uint32_t)((kt / STAGES) & 1));
-    } else {
-      // cooperative copy: consecutive threads read consecutive bytes of a row
-      __syncthreads();
-      const int t0 = kt * TILE_BYTES;
-      for (int idx = tid; idx < TILE_ROWS * TILE_BYTES; idx += TILE_ROWS) {
-        const int r = idx >> 7, b = idx & 127;
-        const int64_t row = row0 + r;
-        uint8_t v = 0;
-        if (row < N && t0 + b < H) v = outcomes[row * ld + t0 + b];
-        tile[swz(r, b >> 4) + (b & 15)] = v;
-      }
-      __syncthreads();
-    }
-    const int steps = min(TILE_BYTES, H - kt * TILE_BYTES);
-    if (steps == TILE_BYTES) {
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        const uint4 q = *reinterpret_cast<const uint4*>(tile + swz(tid, c));
-        chain_word<GT, K, V>(w, f, tab, q.x);
-        chain_word<GT, K, V>(w, f, tab, q.y);
-        chain_word<GT, K, V>(w, f, tab, q.z);
-        chain_word<GT, K, V>(w, f, tab, q.w);
-      }
-    } else {
-#pragma unroll 1
-      for (int t = 0; t < steps; ++t) {
-        const uint32_t code = tile[swz(tid, t >> 4) + (t & 15)];
-        chain_step<GT, K, V>(w, f, tab, code);
-      }
-    }
-    if (USE_TMA) {
-      __syncthreads();  // every thread is done with stage s
-      if (tid == 0 && kt + STAGES < ntiles) {
-        mbar_expect_tx(&full[s], TILE_SMEM);
-        tma_load_2d(tile, &tmap, &full[s], (kt + STAGES) * TILE_BYTES, (int)row0);
-      }
-    }
-  }
-
-  const int64_t row = row0 + tid;
-  if (row < N) {
-#pragma unroll
-    for (int g = 0; g < GT; ++g)
-      if (g < G) data_T[(int64_t)g * ldT + row] = w[g];
-  }
-}
-
-// ------------------------------------------------- Philox outcome draws
-// Four consecutive time steps share one Philox block: counter =
-// (investor lo, investor hi, t/4, TAG), key = seed.  Code = #{k: u >= thr[k]}.
-struct Thresholds {
-  uint32_t t[B200_MAX_OUTCOMES];
-};
-template <int K>
-__device__ __forceinline__ uint32_t draw_code(uint32_t u, const Thresholds& th) {
-  uint32_t c = (u >= th.t[0]);
-  if (K >= 3) c += (u >= th.t[1]);
-  if (K >= 4) c += (u >= th.t[2]);
-  return c;
-}
-
-template <int GT, int K, int V>
-__global__ void __launch_bounds__(128)
-chain_discrete_philox_kernel(const __grid_constant__ FactorTable f, const __grid_constant__ Thresholds th,
-                             uint64_t seed, int64_t investor_offset, int32_t H, int64_t N, int32_t G, float V0,
-                             float* __restrict__ data_T, int64_t ldT) {
-  __shared__ __align__(16) float tab[V == V_LDS ? K * GridTile<GT>::STRIDE : 4];
-  if (V == V_LDS) {
-    fill_table<GT, K>(tab, f);
-    __syncthreads();
-  }
-  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= N) return;
-  const uint64_t id = (uint64_t)(row + investor_offset);
-  const uint32_t c0 = (uint32_t)id, c1 = (uint32_t)(id >> 32);
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  float w[GT];
-#pragma unroll
-  for (int g = 0; g < GT; ++g) w[g] = V0;
-  const int nblk = H >> 2;
-#pragma unroll 2
-  for (int j = 0; j < nblk; ++j) {
-    const Philox4 r = philox4x32_10(c0, c1, (uint32_t)j, PHILOX_TAG_LEV, k0, k1);
-    chain_step<GT, K, V>(w, f, tab, draw_code<K>(r.x, th));
-    chain_step<GT, K, V>(w, f, tab, draw_code<K>(r.y, th));
-    chain_step<GT, K, V>(w, f, tab, draw_code<K>(r.z, th));
-    chain_step<GT, K, V>(w, f, tab, draw_code<K>(r.w, th));
-  }
-  if (H & 3) {
-    const Philox4 r = philox4x32_10(c0, c1, (uint32_t)nblk, PHILOX_TAG_LEV, k0, k1);
-    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
-    for (int t = 0; t < (H & 3); ++t) chain_step<GT, K, V>(w, f, tab, draw_code<K>(u[t], th));
-  }
-#pragma unroll
-  for (int g = 0; g < GT; ++g)
-    if (g < G) data_T[(int64_t)g * ldT + row] = w[g];
-}
 
 template <int K>
 __global__ void __launch_bounds__(128)
@@ -589,11 +296,57 @@ draw_gbm_kernel(uint64_t seed, int64_t investor_offset, float log_mean, float si
   }
 }
 
-// ------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// ------------------------------------------------ GBM series chunk
+// Steps [t_begin, t_end) (t_begin a multiple of 32 so that the fp32 partial sums
+// fold exactly where the final-time kernels fold them) with the wealth after
+// every step dumped: dump[(g*tc + t-t_begin)*N + row].  state = double [3,N].
+__device__ __forceinline__ float gbm_wealth(double l, double S, double Smax, double Smin, double logV0) {
+  const double LOG_FLT_MAX = 88.72283905206835;
+  const double LOG_FLT_ZERO = -103.97207708399179;
+  const double hi = logV0 + (l >= 0 ? l * Smax : l * Smin);
+  const double lo = logV0 + (l >= 0 ? l * Smin : l * Smax);
+  if (hi > LOG_FLT_MAX) return __int_as_float(0x7f800000);
+  if (lo < LOG_FLT_ZERO) return 0.0f;
+  return (float)exp(logV0 + l * S);
+}
 
+template <bool PHILOX>
+__global__ void __launch_bounds__(128)
+gbm_chunk_kernel(const float* __restrict__ x, int64_t ld, const __grid_constant__ LevGrid lv, uint64_t seed,
+                 int64_t investor_offset, float log_mean, float sigma, int32_t t_begin, int32_t t_end, int64_t N,
+                 int32_t G, double logV0, double* __restrict__ state, float* __restrict__ dump) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  GbmAcc acc;
+  if (t_begin > 0) { acc.S = state[row]; acc.Smax = state[N + row]; acc.Smin = state[2 * N + row]; }
+  const int64_t tc = t_end - t_begin;
+  const uint64_t id = (uint64_t)(row + investor_offset);
+  float xb[4];
+  for (int t = t_begin; t < t_end; ++t) {
+    float xt;
+    if (PHILOX) {
+      if ((t & 3) == 0 || t == t_begin)
+        gbm_draw4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)(t >> 2), (uint32_t)seed, (uint32_t)(seed >> 32),
+                  log_mean, sigma, xb);
+      xt = xb[t & 3];
+    } else {
+      xt = __ldg(x + row * ld + t);
+    }
+    acc.step(xt);
+    if (dump != nullptr) {
+      const double S = acc.S + (double)acc.p;
+      const double Smax = fmax(acc.Smax, acc.S + (double)acc.pmax);
+      const double Smin = fmin(acc.Smin, acc.S + (double)acc.pmin);
+      for (int g = 0; g < G; ++g)
+        __stcs(dump + ((int64_t)g * tc + (t - t_begin)) * N + row, gbm_wealth((double)lv.lev[g], S, Smax, Smin, logV0));
+    }
+    if ((t & 31) == 31) acc.fold();
+  }
+  acc.fold();
+  state[row] = acc.S; state[N + row] = acc.Smax; state[2 * N + row] = acc.Smin;
+}
+
+// ------------------------------------------------------------ host side
 static EncodeTiledFn encode_tiled_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
@@ -610,9 +363,8 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// [N rows, row_bytes] byte view with 128-byte x 128-row boxes, 128B swizzle.
-static int make_row_tile_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t row_elems,
-                             int64_t ld_elems, int elem_bytes) {
+int make_row_tile_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t row_elems, int64_t ld_elems,
+                      int elem_bytes) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return set_error(B200_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   const cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)n_rows};
@@ -627,78 +379,38 @@ static int make_row_tile_map(CUtensorMap* map, const void* base, int64_t n_rows,
   return 0;
 }
 
-// 1 = V_FSEL, 2 = V_PRED2, 3 = V_LDS; chosen from the B200 measurements in profiles/
-static int default_chain_variant() { return 1; }
-
-static bool tma_ok(const void* base, int64_t ld_bytes, int64_t n_rows) {
-  return ((uintptr_t)base % 16 == 0) && (ld_bytes % 16 == 0) && n_rows < (int64_t)1 << 31;
-}
-
-template <int GT, int K, int V>
-static int launch_chain_discrete(const b200_lev_desc& d, const uint8_t* outcomes, const FactorTable& f, int g_cnt,
-                                 float* data_T, cudaStream_t st) {
-  const int64_t N = d.n_investors;
-  if (d.source == B200_SRC_PHILOX) {
-    Thresholds th;
-    for (int k = 0; k < B200_MAX_OUTCOMES; ++k) th.t[k] = d.thresholds[k];
-    const unsigned blocks = (unsigned)((N + 127) / 128);
-    chain_discrete_philox_kernel<GT, K, V><<<blocks, 128, 0, st>>>(f, th, d.seed, d.investor_offset, d.horizon, N,
-                                                                   g_cnt, d.value_0, data_T, N);
-    return check_cuda(cudaGetLastError(), "chain_discrete_philox launch");
-  }
-  const unsigned blocks = (unsigned)((N + TILE_ROWS - 1) / TILE_ROWS);
-  CUtensorMap map;
-  memset(&map, 0, sizeof(map));
-  if (tma_ok(outcomes, d.ld_outcomes, N)) {
-    int rc = make_row_tile_map(&map, outcomes, N, d.horizon, d.ld_outcomes, 1);
-    if (rc) return rc;
-    auto kern = chain_discrete_stream_kernel<GT, K, V, true>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * TILE_SMEM));
-    kern<<<blocks, TILE_ROWS, STAGES * TILE_SMEM, st>>>(map, outcomes, d.ld_outcomes, f, d.horizon, N, g_cnt,
-                                                        d.value_0, data_T, N);
-  } else {
-    chain_discrete_stream_kernel<GT, K, V_FSEL, false><<<blocks, TILE_ROWS, TILE_SMEM, st>>>(
-        map, outcomes, d.ld_outcomes, f, d.horizon, N, g_cnt, d.value_0, data_T, N);
-  }
-  return check_cuda(cudaGetLastError(), "chain_discrete_stream launch");
-}
-
-template <int K, int V>
-static int dispatch_chain_gt(const b200_lev_desc& d, const uint8_t* outcomes, const FactorTable& f, int g_cnt,
-                             float* data_T, cudaStream_t st) {
-  if (g_cnt <= 4) return launch_chain_discrete<4, K, V>(d, outcomes, f, g_cnt, data_T, st);
-  if (g_cnt <= 10) return launch_chain_discrete<10, K, V>(d, outcomes, f, g_cnt, data_T, st);
-  if (g_cnt <= 20) return launch_chain_discrete<20, K, V>(d, outcomes, f, g_cnt, data_T, st);
-  return launch_chain_discrete<32, K, V>(d, outcomes, f, g_cnt, data_T, st);
-}
-
-template <int K>
-static int dispatch_chain_variant(const b200_lev_desc& d, const uint8_t* outcomes, const FactorTable& f, int g_cnt,
-                                  float* data_T, cudaStream_t st) {
-  int v = d.variant;
-  if (v == 0) v = default_chain_variant();
-  switch (v) {
-    case 2: return dispatch_chain_gt<K, V_PRED2>(d, outcomes, f, g_cnt, data_T, st);
-    case 3: return dispatch_chain_gt<K, V_LDS>(d, outcomes, f, g_cnt, data_T, st);
-    default: return dispatch_chain_gt<K, V_FSEL>(d, outcomes, f, g_cnt, data_T, st);
-  }
-}
-
+// Steps [t_begin, t_end) of the discrete CHAIN for the whole grid, in tiles of
+// <= 32 grid points; each tile re-streams (or re-draws) the outcomes.
+// state / dump are laid out for the FULL grid: [G, N] and [G, t_end-t_begin, N].
 static int run_chain_discrete(const b200_lev_desc& d, const uint8_t* outcomes, const float* factors_host,
-                              float* data_T, cudaStream_t st) {
-  // grid tiles of <= 32 points; each tile re-streams (or re-draws) the outcomes
+                              int t_begin, int t_end, const float* state_in, float* state_out, float* dump,
+                              cudaStream_t st) {
+  const int64_t N = d.n_investors;
+  const int64_t tc = t_end - t_begin;
   for (int g0 = 0; g0 < d.n_grid; g0 += 32) {
     const int g_cnt = d.n_grid - g0 < 32 ? d.n_grid - g0 : 32;
-    FactorTable f;
+    ChainLaunch a;
+    a.d = &d;
+    a.outcomes = outcomes;
     for (int k = 0; k < B200_MAX_OUTCOMES; ++k)
       for (int g = 0; g < 32; ++g)
-        f.m[k][g] = (g < g_cnt && k < d.n_outcomes) ? factors_host[(int64_t)(g0 + g) * d.n_outcomes + k] : 1.0f;
-    float* out = data_T + (int64_t)g0 * d.n_investors;
+        a.f.m[k][g] = (g < g_cnt && k < d.n_outcomes) ? factors_host[(int64_t)(g0 + g) * d.n_outcomes + k] : 1.0f;
+    a.p.t_begin = t_begin;
+    a.p.t_end = t_end;
+    a.p.G = g_cnt;
+    a.p.V0 = d.value_0;
+    a.p.N = N;
+    a.p.ldT = N;
+    a.p.state_in = state_in ? state_in + (int64_t)g0 * N : nullptr;
+    a.p.state_out = state_out + (int64_t)g0 * N;
+    a.p.dump = dump ? dump + (int64_t)g0 * tc * N : nullptr;
+    a.variant = d.variant;
+    a.st = st;
     int rc;
     switch (d.n_outcomes) {
-      case 2: rc = dispatch_chain_variant<2>(d, outcomes, f, g_cnt, out, st); break;
-      case 3: rc = dispatch_chain_variant<3>(d, outcomes, f, g_cnt, out, st); break;
-      default: rc = dispatch_chain_variant<4>(d, outcomes, f, g_cnt, out, st); break;
+      case 2: rc = chain_discrete_launch<2>(a); break;
+      case 3: rc = chain_discrete_launch<3>(a); break;
+      default: rc = chain_discrete_launch<4>(a); break;
     }
     if (rc) return rc;
   }
@@ -776,7 +488,7 @@ static int validate(const b200_lev_desc* d) {
   B200_REQUIRE(d->n_grid >= 1 && d->n_grid <= B200_MAX_GRID, "lev: n_grid must be in 1..%d", B200_MAX_GRID);
   B200_REQUIRE(d->kind == B200_LEV_DISCRETE || d->kind == B200_LEV_GBM, "lev: unknown kind %d", d->kind);
   B200_REQUIRE(d->source == B200_SRC_STREAM || d->source == B200_SRC_PHILOX, "lev: unknown source %d", d->source);
-  B200_REQUIRE(d->variant >= 0 && d->variant <= 3, "lev: variant must be 0 (auto) .. 3");
+  B200_REQUIRE(d->variant >= 0 && d->variant <= 2, "lev: variant must be 0 (auto), 1 (FSEL) or 2 (LDS)");
   if (d->kind == B200_LEV_DISCRETE) {
     B200_REQUIRE(d->n_outcomes >= 2 && d->n_outcomes <= B200_MAX_OUTCOMES, "lev: n_outcomes must be in 2..%d",
                  B200_MAX_OUTCOMES);
@@ -809,7 +521,7 @@ extern "C" int b200_lev_sweep(const b200_lev_desc* desc, const void* outcomes, c
   if (d.kind == B200_LEV_DISCRETE) {
     if (d.mode == B200_MODE_CHAIN) {
       B200_REQUIRE(data_T != nullptr, "lev_sweep: CHAIN mode needs data_T");
-      return run_chain_discrete(d, (const uint8_t*)outcomes, host_f, data_T, st);
+      return run_chain_discrete(d, (const uint8_t*)outcomes, host_f, 0, d.horizon, nullptr, data_T, nullptr, st);
     }
     if (d.mode == B200_MODE_LOG) {
       B200_REQUIRE(d.source == B200_SRC_STREAM, "lev_sweep: discrete LOG mode takes streamed outcomes");
@@ -849,4 +561,37 @@ extern "C" int b200_lev_draw(const b200_lev_desc* desc, void* out, void* stream)
     }
   }
   return check_cuda(cudaGetLastError(), "lev_draw launch");
+}
+
+extern "C" int b200_lev_chunk(const b200_lev_desc* desc, const void* outcomes, const float* factors, int32_t t_begin,
+                              int32_t t_end, void* state, float* dump, void* stream) {
+  int rc = validate(desc);
+  if (rc) return rc;
+  const b200_lev_desc& d = *desc;
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_REQUIRE(factors != nullptr && state != nullptr, "lev_chunk: factors/state is NULL");
+  B200_REQUIRE(0 <= t_begin && t_begin < t_end && t_end <= d.horizon, "lev_chunk: need 0 <= t_begin < t_end <= horizon");
+  B200_REQUIRE(d.source == B200_SRC_PHILOX || outcomes != nullptr || d.n_investors == 0,
+               "lev_chunk: outcomes is NULL for a streamed sweep");
+  if (d.n_investors == 0) return 0;
+  if (d.kind == B200_LEV_DISCRETE) {
+    B200_REQUIRE(d.mode == B200_MODE_CHAIN, "lev_chunk: discrete chunks run in CHAIN mode");
+    B200_REQUIRE(d.source != B200_SRC_PHILOX || (t_begin & 3) == 0, "lev_chunk: Philox chunks start at a multiple of 4");
+    float* stf = (float*)state;
+    return run_chain_discrete(d, (const uint8_t*)outcomes, factors, t_begin, t_end, t_begin > 0 ? stf : nullptr, stf,
+                              dump, st);
+  }
+  B200_REQUIRE((t_begin & 31) == 0, "lev_chunk: GBM chunks start at a multiple of 32");
+  LevGrid lv;
+  for (int g = 0; g < B200_MAX_GRID; ++g) lv.lev[g] = g < d.n_grid ? factors[g] : 0.f;
+  const double logV0 = log((double)d.value_0);
+  const unsigned blocks = (unsigned)((d.n_investors + 127) / 128);
+  if (d.source == B200_SRC_PHILOX)
+    gbm_chunk_kernel<true><<<blocks, 128, 0, st>>>(nullptr, 0, lv, d.seed, d.investor_offset, d.log_mean, d.sigma,
+                                                   t_begin, t_end, d.n_investors, d.n_grid, logV0, (double*)state, dump);
+  else
+    gbm_chunk_kernel<false><<<blocks, 128, 0, st>>>((const float*)outcomes, d.ld_outcomes, lv, d.seed,
+                                                    d.investor_offset, d.log_mean, d.sigma, t_begin, t_end,
+                                                    d.n_investors, d.n_grid, logV0, (double*)state, dump);
+  return check_cuda(cudaGetLastError(), "gbm_chunk launch");
 }

@@ -54,7 +54,9 @@ struct RowWS {
   double mean_all, mean_top, mean_adj;
   double value[NT];         // selected values (as double)
   long long ties_top, ties_adj;
-  long long pad_r[4];
+  long long nonfinite[3];   // all / top / adj group holds +-inf or NaN (torch.std_mean -> nan)
+  long long has_nan[3];     // all / top / adj group holds a NaN (torch.median -> nan)
+  long long pad_r[2];
 };
 static_assert(sizeof(RowWS) % 8 == 0, "8-byte words");
 
@@ -221,7 +223,18 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) w->mean_all = w->sum_all / (double)n;
+    if (threadIdx.x == 0) {
+      w->mean_all = w->sum_all / (double)n;
+      // key bins that can only hold non-finite values: 3 = -inf, 2044 = +inf, 2047 = NaN
+      const long long ninf = w->hist1[3], pinf = w->hist1[2044], nan = w->hist1[2047];
+      const long long hi = pinf + nan;  // sort to the top
+      w->nonfinite[0] = (hi + ninf) > 0;
+      w->nonfinite[1] = hi > 0 || ninf > n - K;
+      w->nonfinite[2] = hi > K || ninf > 0;
+      w->has_nan[0] = nan > 0;
+      w->has_nan[1] = nan > 0;
+      w->has_nan[2] = nan > K;
+    }
   } else if (STEP == 1) {
     for (int j = 0; j < NT; ++j) {
       find_bin(w->hist2[j], L2_BINS, w->rank[j], &bin_s, &rem_s, scratch);
@@ -267,6 +280,13 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
       s[6] = sqrt(w->sqdev_all / (double)n); s[7] = sqrt(sq_top / (double)K);
       s[8] = sqrt(sq_adj / (double)(n - K));
       s[9] = w->value[0]; s[10] = w->value[2]; s[11] = w->value[3];
+      // torch semantics: Welford's std_mean turns any non-finite member into
+      // nan mean/std (hence nan MAD); median propagates NaN
+      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      for (int j = 0; j < 3; ++j) {
+        if (w->nonfinite[j]) { s[0 + j] = qnan; s[3 + j] = qnan; s[6 + j] = qnan; }
+        if (w->has_nan[j]) s[9 + j] = qnan;
+      }
     }
   }
 }

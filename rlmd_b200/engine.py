@@ -103,45 +103,8 @@ def lev_sweep(
     """
     require_cuda()
     f = np.ascontiguousarray(factors, dtype=np.float32)
-    d = LevDesc()
-    if kind == "discrete":
-        d.kind = _lib.LEV_DISCRETE
-        g, k = f.shape
-        d.n_outcomes = k
-    elif kind == "gbm":
-        d.kind = _lib.LEV_GBM
-        g, k = f.shape[0], 0
-    else:
-        raise ValueError("kind must be 'discrete' or 'gbm'")
-    d.n_grid = g
-    d.mode = {"chain": _lib.MODE_CHAIN, "log": _lib.MODE_LOG}[mode]
-    d.value_0 = float(value_0)
-    d.variant = int(variant)
-    d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    d.investor_offset = int(investor_offset)
-    d.log_mean, d.sigma = float(log_mean), float(sigma)
-    if outcomes is not None:
-        if not outcomes.is_cuda:
-            raise ValueError("outcomes must live on the GPU (see encode_codes / encode_returns)")
-        want = torch.uint8 if kind == "discrete" else torch.float32
-        if outcomes.dtype != want or outcomes.dim() != 2 or outcomes.stride(1) != 1:
-            raise ValueError(f"outcomes must be a [N,H] {want} tensor with unit inner stride")
-        n, h = outcomes.shape
-        d.source = _lib.SRC_STREAM
-        d.ld_outcomes = outcomes.stride(0) if n > 1 else max(outcomes.stride(0), h)
-        dev = outcomes.device
-    else:
-        if n_investors is None or horizon is None:
-            raise ValueError("Philox mode needs n_investors and horizon")
-        n, h = int(n_investors), int(horizon)
-        d.source = _lib.SRC_PHILOX
-        d.ld_outcomes = h
-        dev = torch.device(device or "cuda")
-        if kind == "discrete":
-            thr = philox_thresholds(probs)
-            for i, v in enumerate(thr):
-                d.thresholds[i] = v
-    d.n_investors, d.horizon = n, h
+    d, g, k, n, h, dev = _fill_desc(kind, f, value_0, outcomes, n_investors, horizon, mode, seed, investor_offset,
+                                    probs, log_mean, sigma, variant, device)
 
     res = {}
     with torch.cuda.device(dev):
@@ -181,6 +144,118 @@ def lev_draw(kind: str, n_investors: int, horizon: int, *, seed: int = 0, invest
     with torch.cuda.device(out.device):
         check(lib.b200_lev_draw(C.byref(d), ptr(out), stream_ptr()))
     return out[:, :horizon]
+
+
+def _fill_desc(kind, f, value_0, outcomes, n_investors, horizon, mode, seed, investor_offset, probs, log_mean,
+               sigma, variant, device):
+    d = LevDesc()
+    if kind == "discrete":
+        d.kind = _lib.LEV_DISCRETE
+        g, k = f.shape
+        d.n_outcomes = k
+    elif kind == "gbm":
+        d.kind = _lib.LEV_GBM
+        g, k = f.shape[0], 0
+    else:
+        raise ValueError("kind must be 'discrete' or 'gbm'")
+    d.n_grid = g
+    d.mode = {"chain": _lib.MODE_CHAIN, "log": _lib.MODE_LOG}[mode]
+    d.value_0 = float(value_0)
+    d.variant = int(variant)
+    d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    d.investor_offset = int(investor_offset)
+    d.log_mean, d.sigma = float(log_mean), float(sigma)
+    if outcomes is not None:
+        if not outcomes.is_cuda:
+            raise ValueError("outcomes must live on the GPU (see encode_codes / encode_returns)")
+        want = torch.uint8 if kind == "discrete" else torch.float32
+        if outcomes.dtype != want or outcomes.dim() != 2 or outcomes.stride(1) != 1:
+            raise ValueError(f"outcomes must be a [N,H] {want} tensor with unit inner stride")
+        n, h = outcomes.shape
+        d.source = _lib.SRC_STREAM
+        d.ld_outcomes = outcomes.stride(0) if n > 1 else max(outcomes.stride(0), h)
+        dev = outcomes.device
+    else:
+        if n_investors is None or horizon is None:
+            raise ValueError("Philox mode needs n_investors and horizon")
+        n, h = int(n_investors), int(horizon)
+        d.source = _lib.SRC_PHILOX
+        d.ld_outcomes = h
+        dev = torch.device(device or "cuda")
+        if kind == "discrete":
+            for i, v in enumerate(philox_thresholds(probs)):
+                d.thresholds[i] = v
+    d.n_investors, d.horizon = n, h
+    return d, g, k, n, h, dev
+
+
+def lev_series(
+    kind: str,
+    factors: np.ndarray,
+    lev_row: np.ndarray,
+    value_0: float,
+    top: int,
+    *,
+    outcomes: Optional[torch.Tensor] = None,
+    n_investors: Optional[int] = None,
+    horizon: Optional[int] = None,
+    seed: int = 0,
+    investor_offset: int = 0,
+    probs: Optional[Sequence[float]] = None,
+    log_mean: float = 0.0,
+    sigma: float = 0.0,
+    variant: int = 0,
+    chunk_steps: Optional[int] = None,
+    chunk_bytes: int = 2 << 30,
+    n_total: Optional[int] = None,
+    group=None,
+    device=None,
+):
+    """
+    Per-step statistics of the whole grid (the *_smart_lev contract):
+    returns data [G,13,H-1] fp32 (rows: the 12 statistics in the reference's
+    order, then the leverage) and data_T [G,N] fp32 (wealth after step H-1).
+
+    The horizon is walked in chunks: b200_lev_chunk dumps the wealth after every
+    step of the chunk to a [G*steps, N] buffer, b200_rowstats reduces every row,
+    and the statistics are scattered into `data` (step t -> column t-1).
+    With `group`, the rows are investor shards and the statistics are global.
+    """
+    require_cuda()
+    f = np.ascontiguousarray(factors, dtype=np.float32)
+    mode = "chain" if kind == "discrete" else "log"
+    d, g, k, n, h, dev = _fill_desc(kind, f, value_0, outcomes, n_investors, horizon, mode, seed, investor_offset,
+                                    probs, log_mean, sigma, variant, device)
+    n_total = n if n_total is None else int(n_total)
+    fptr = f.ctypes.data_as(C.POINTER(C.c_float))
+    with torch.cuda.device(dev):
+        data = torch.zeros((g, 13, max(h - 1, 0)), dtype=torch.float32, device=dev)
+        if h > 1:
+            data[:, 12, :] = torch.as_tensor(np.asarray(lev_row, dtype=np.float32), device=dev)[:, None]
+        if kind == "discrete":
+            state = torch.empty((g, n), dtype=torch.float32, device=dev)
+        else:
+            state = torch.empty((3, n), dtype=torch.float64, device=dev)
+        if chunk_steps is None:
+            chunk_steps = max(32, min(h, chunk_bytes // max(4 * g * max(n, 1), 1), 2048 // g))
+        tc_max = max(32, (int(chunk_steps) // 32) * 32)
+        tc_max = min(tc_max, (h + 31) // 32 * 32)
+        chunk = torch.empty((g * tc_max * max(n, 1),), dtype=torch.float32, device=dev)
+        ws = rowstats_workspace(g * tc_max, dev)
+        last = None
+        for t0 in range(0, h, tc_max):
+            t1 = min(h, t0 + tc_max)
+            tc = t1 - t0
+            dump = chunk[: g * tc * n].view(g * tc, n)
+            check(lib.b200_lev_chunk(C.byref(d), ptr(outcomes), fptr, t0, t1, ptr(state), ptr(dump), stream_ptr()))
+            if n > 0:
+                st = rowstats(dump, top, n_total=n_total, group=group, workspace=ws[: g * tc]).view(g, tc, 12)
+                lo = max(t0, 1)
+                if t1 > lo:
+                    data[:, :12, lo - 1:t1 - 1] = st[:, lo - t0:, :].permute(0, 2, 1).to(torch.float32)
+            last = dump.view(g, tc, n)[:, tc - 1, :]
+        data_T = state if kind == "discrete" else last.clone()
+    return data, data_T
 
 
 # ----------------------------------------------------------------- rowstats

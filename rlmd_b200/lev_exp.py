@@ -17,7 +17,7 @@ the coin / dice / dice_sh functions is bit-identical to the reference's.
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Tuple  # noqa: F401
 
 import numpy as np
 import torch as T
@@ -113,12 +113,15 @@ _FINAL_FMT = """       lev {:1.0f}%:
                  adj mean/med/mad/std:  $ {:1.2e} / {:1.2e} / {:1.1e} / {:1.1e}"""
 
 
-def _print_final(lev: np.ndarray, stats: np.ndarray) -> None:
-    """The reference's per-leverage report (lev/lev_exp.py:106-125)."""
+def _print_final(lev: np.ndarray, stats: np.ndarray, smart: bool = False) -> None:
+    """The reference's per-leverage report (lev/lev_exp.py:106-125).
+
+    The *_smart_lev variants print med_top in the "adj" line (:214-233); kept.
+    """
     for l, s in zip(lev, stats.astype(_F32)):
         mean, mean_top, mean_adj, mad, mad_top, mad_adj, std, std_top, std_adj, med, med_top, med_adj = s
         print(_FINAL_FMT.format(float(l) * 100, mean, med, mad, std, mean_top, med_top, mad_top, std_top,
-                                mean_adj, med_adj, mad_adj, std_adj))
+                                mean_adj, med_top if smart else med_adj, mad_adj, std_adj))
 
 
 def _final(kind, outcomes, table, lev, top, value_0, mode="chain"):
@@ -156,3 +159,48 @@ def gbm_fixed_final_lev(device, outcomes, top, value_0, lev_low, lev_high, lev_i
     lev = _grid(lev_low, lev_high, lev_incr)
     _, stats = _final("gbm", _returns(outcomes), lev, lev, top, value_0, mode="log")
     _print_final(lev, stats)
+
+
+# ------------------------------------------------------------ smart leverage
+def _series(kind, outcomes, table, lev, investors, horizon, top, value_0) -> Tuple[T.Tensor, T.Tensor]:
+    n, h = outcomes.shape
+    if (investors is not None and _as_int(investors) != n) or (horizon is not None and _as_int(horizon) != h):
+        raise ValueError("investors/horizon do not match the shape of outcomes")
+    return engine.lev_series(kind, table, lev, _as_float(value_0), int(top), outcomes=outcomes)
+
+
+def coin_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, down_r, lev_low, lev_high, lev_incr):
+    """lev/lev_exp.py:128-237 -> (data [L,13,H-1], data_T [L,N]), fp32 on the GPU."""
+    lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
+    data, data_T = _series("discrete", _codes(outcomes), coin_factor_table(lev, up_r, down_r), lev, investors,
+                           horizon, top, value_0)
+    _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
+    return data, data_T
+
+
+def dice_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, down_r, mid_r, lev_low, lev_high,
+                   lev_incr):
+    """lev/lev_exp.py:586-701."""
+    lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
+    data, data_T = _series("discrete", _codes(outcomes), dice_factor_table(lev, up_r, down_r, mid_r), lev, investors,
+                           horizon, top, value_0)
+    _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
+    return data, data_T
+
+
+def dice_sh_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, down_r, mid_r, sh_up_r, sh_down_r,
+                      sh_mid_r, lev_low, lev_high, lev_incr):
+    """lev/lev_exp.py:1209-1334."""
+    lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
+    table = dice_sh_factor_table(lev, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r)
+    data, data_T = _series("discrete", _codes(outcomes), table, lev, investors, horizon, top, value_0)
+    _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
+    return data, data_T
+
+
+def gbm_smart_lev(device, outcomes, investors, horizon, top, value_0, lev_low, lev_high, lev_incr):
+    """lev/lev_exp.py:1008-1118."""
+    lev = _grid(lev_low, lev_high, lev_incr)
+    data, data_T = _series("gbm", _returns(outcomes), lev, lev, investors, horizon, top, value_0)
+    _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
+    return data, data_T

@@ -41,7 +41,10 @@ LEV_CASES = [
     # long horizon: fp32 underflow towards denormals / zero at full leverage
     dict(name="coin_long", kind="coin", n=513, h=3000, top=1, v0=1e2, seed=7,
          up_r=0.5, down_r=-0.4, p=(0.5,), grid=(0.2, 1.0, 0.2), stride=250),
-    # GBM overflow to inf in fp32
+    # fp32 overflow to inf for part of the investors (torch.std_mean -> nan there)
+    dict(name="coin_overflow", kind="coin", n=400, h=1000, top=3, v0=1e2, seed=9,
+         up_r=0.5, down_r=-0.4, p=(0.7,), grid=(0.2, 1.0, 0.4), stride=37),
+    # GBM underflow to zero in fp32
     dict(name="gbm_overflow", kind="gbm", n=300, h=4000, top=1, v0=1e2, seed=8,
          mu=0.05, sigma=math.sqrt(0.2), grid=(0.2, 2.0, 0.6), stride=500),
 ]

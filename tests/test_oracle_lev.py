@@ -83,6 +83,12 @@ def test_smart_lev_matches_reference(case):
         assert_stats_close(data[:, :9], gold["data"][:, :9])
     elif case["name"] != "gbm_overflow":
         assert_stats_close(data[:, :12], gold["data"][:, :12], rtol=5e-5)
+    else:
+        # deep in the denormal range the fp32 chain has lost its relative accuracy:
+        # compare where the reference is still normal, and the zero pattern elsewhere
+        normal = np.abs(gold["data"][:, :12]) > 1e-30
+        assert_stats_close(np.where(normal, data[:, :12], 0), np.where(normal, gold["data"][:, :12], 0), rtol=2e-4)
+        assert np.array_equal(gold["data"][:, 9:12] == 0, data[:, 9:12] == 0)
 
 
 def test_param_range_truth_table():
