@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""
+bench.py - headline benchmark of the leverage-sweep hot path (contract in the
+task prompt; BASELINE.json metric "investor-steps/sec (leverage sweep)").
+
+Workload (BASELINE.json configs[1]): lev/dice_roll.py's trinary die-roll sweep,
+1e6 investors x 1e4 steps per GPU, the script's final-time grid
+param_range(0.05, 1.00, 0.05) = 20 leverages, top = 100.  One "step" is one
+pass of the `dice_fixed_final_lev` hot path over one synthetic outcome array:
+    sweep (log-domain count kernel) -> data_T[20, N] -> 12 summary statistics
+    per leverage (exact order statistics by radix select).
+With N GPUs (one process per GPU, torchrun) every rank owns its own 1e6
+investors (weak scaling); the only cross-GPU traffic is the all-reduce of the
+per-leverage partial sums and radix histograms inside the statistics.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line.  `--impl reference` times the reference's own CPU
+implementation of the same path (torch-CPU port, all host threads) on a bounded
+sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_INVESTORS = 1_000_000
+HORIZON = 10_000
+TOP = 100
+GRID = (0.05, 1.00, 0.05)
+RETURNS = (0.5, -0.5, 0.05)
+PROBS = (1 / 6, 1 / 6, 2 / 3)
+V0 = 100.0
+METRIC = "investor-steps/sec (leverage sweep)"
+UNIT = "investor-steps/s"
+WORKLOAD = "lev/dice_roll.py dice_fixed_final_lev: 1e6 investors x 1e4 steps per GPU, 20 leverages, top 100"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------ CPU arm
+def cpu_reference_step(n_s, h, threads=None):
+    """One pass of the torch-CPU port over a fresh [n_s, h] int64 outcome array."""
+    import torch
+
+    from oracle import lev_ref_port as port
+
+    if threads:
+        torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(420)
+    u = torch.rand((n_s, h), generator=gen)
+    outcomes = torch.where(u < PROBS[0], 0, torch.where(u < PROBS[0] + PROBS[1], 1, 2)).to(torch.int64)
+    del u
+    top = max(1, int(n_s * 1e-4))
+    t0 = time.perf_counter()
+    rows, levs = port.fixed_final("dice", outcomes, top, V0, RETURNS, GRID)
+    dt = time.perf_counter() - t0
+    assert len(rows) == 20
+    return dt
+
+
+def run_reference(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = torch.get_num_threads()
+    h = HORIZON
+    # size the per-step sample so that the whole K+W run ends within ~2.5 minutes
+    probe = cpu_reference_step(200, h)
+    rate = 200 / probe  # investors per second at this horizon and grid
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_s = int(max(200, min(args.ref_sample, rate * budget)))
+    for _ in range(args.warmup):
+        cpu_reference_step(n_s, h)
+    ts = [cpu_reference_step(n_s, h) for _ in range(args.steps)]
+    total = sum(ts)
+    value = n_s * h * args.steps / total
+    sample = f"{n_s} investors x {h} steps per step (of the 1e6 x 1e4 workload), 20 leverages, torch-CPU ops"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------- clock sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {
+                0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown",
+            }
+            for bit, name in names.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop.is_set():
+            self.sample()
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=1)
+        import statistics
+
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from rlmd_b200 import engine, lev_exp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (rlmd_b200 has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    peaks, peak_kind = load_peaks()
+
+    n, h = args.investors, HORIZON
+    lev = np.asarray(lev_exp.param_range(*GRID), dtype=np.float32)
+    table = lev_exp.dice_factor_table(lev, *RETURNS)
+    g = table.shape[0]
+    top_total = TOP * world
+    n_total = n * world
+
+    # synthetic outcomes of this rank's investors, resident in HBM (10 GB >> 126 MB L2:
+    # every step streams the whole array from DRAM again)
+    outcomes = engine.lev_draw("discrete", n, h, seed=420, investor_offset=rank * n, probs=PROBS, device=dev)
+    data_T = torch.empty((g, n), dtype=torch.float32, device=dev)
+    ws = engine.rowstats_workspace(g, dev)
+    stats_holder = {}
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def step(i=None):
+        if i is not None:
+            ev[i][0].record()
+        engine.lev_sweep("discrete", table, V0, outcomes=outcomes, mode="log", out_data_T=data_T)
+        if i is not None:
+            ev[i][1].record()
+        stats_holder["s"] = engine.rowstats(data_T, top_total, n_total=n_total, group=group, workspace=ws)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step(i)
+    t_end.record()
+    sampler.sample()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    elapsed = t_start.elapsed_time(t_end) * 1e-3
+    sweep_s = sum(a.elapsed_time(b) for a, b in ev) * 1e-3 / args.steps
+    if world > 1:
+        t = torch.tensor([elapsed, sweep_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed, sweep_s = float(t[0]), float(t[1])
+    value = n_total * h * args.steps / elapsed
+    launches_per_step = 1 + 10  # sweep + 5 statistic passes + 5 row-resolve kernels
+
+    # ---- end to end: pinned host outcomes -> H2D (overlapped with the sweep) -> statistics -> host
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n, h), dtype=torch.uint8, pin_memory=True)
+        host.copy_(outcomes)
+        torch.cuda.synchronize()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        kw = dict(mode="log", device=dev, group=group, n_total=n_total)
+        engine.lev_final_host("discrete", table, V0, top_total, host, **kw)  # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            st = engine.lev_final_host("discrete", table, V0, top_total, host, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        e2e = {
+            "value": n_total * h * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * h,
+            "d2h_bytes_per_step": int(st.nbytes), "steps": e2e_steps,
+            "note": "per-rank pinned uint8 outcomes copied H2D in 256 MiB row chunks overlapped with the sweep; "
+                    "statistics read back to the host every step",
+        }
+        del host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = n * h * 1.0 / sweep_s / 1e9  # 1 byte per investor-step, per GPU, per launch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("log_discrete_stream_kernel", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "kernel": "log_discrete_stream_kernel<3>", "achieved": achieved, "peak": hbm_peak,
+        "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+        "algorithmic_bytes_per_launch": n * h, "avg_launch_ms": sweep_s * 1e3,
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        n_s = args.cpu_sample
+        dt = cpu_reference_step(n_s, h)
+        cpu = {
+            "value": n_s * h / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_s} investors x {h} steps, 20 leverages: torch-CPU port of dice_fixed_final_lev "
+                      f"(oracle/lev_ref_port.py), {dt:.1f} s",
+        }
+
+    stats = stats_holder["s"].cpu().numpy()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8 codes, int32 counts, f64 log-wealth",
+        "data": "synthetic (on-device Philox4x32-10 die rolls, seed 420)",
+        "config": {
+            "workload": WORKLOAD, "investors_per_gpu": n, "horizon": h, "leverages": g, "top": top_total,
+            "mode": "log-domain final sweep + exact row statistics", "sharding": f"investors x{world}",
+            "l2": "inputs (10 GB per GPU) exceed the 126 MB L2; no explicit flush",
+        },
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        "path_steps_per_s": value * g,
+        "check": {"median_wealth_lev0": float(stats[0, 9]), "mean_wealth_lev0": float(stats[0, 0])},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--investors", type=int, default=N_INVESTORS, help="investors per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=10_000, help="investors in the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=4_000, help="investors per step of --impl reference")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -68,6 +68,9 @@ typedef struct b200_lev_desc {
   int64_t n_investors;     /* N: rows handled by this call (local shard)     */
   int64_t ld_outcomes;     /* row stride of `outcomes` in ELEMENTS (>= H)    */
   int64_t investor_offset; /* global id of row 0 (Philox counters, sharding) */
+  int64_t ld_out;          /* row stride of data_T / log_w in elements; 0 = N
+                              (lets a caller fill a column block of a wider
+                              [G, N_total] array: host-pipelined / sharded runs) */
   uint64_t seed;           /* Philox key                                     */
   int32_t horizon;         /* H                                              */
   int32_t n_grid;          /* G <= B200_MAX_GRID                             */

@@ -23,6 +23,7 @@ class LevDesc(C.Structure):
         ("n_investors", C.c_int64),
         ("ld_outcomes", C.c_int64),
         ("investor_offset", C.c_int64),
+        ("ld_out", C.c_int64),
         ("seed", C.c_uint64),
         ("horizon", C.c_int32),
         ("n_grid", C.c_int32),

@@ -19,6 +19,8 @@ struct LevGrid {
   float lev[B200_MAX_GRID];
 };
 
+static int64_t out_ld(const b200_lev_desc& d) { return d.ld_out > 0 ? d.ld_out : d.n_investors; }
+
 template <int K>
 __global__ void __launch_bounds__(128)
 draw_discrete_kernel(const __grid_constant__ Thresholds th, uint64_t seed, int64_t investor_offset, int32_t H,
@@ -384,7 +386,7 @@ int make_row_tile_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_
 // state / dump are laid out for the FULL grid: [G, N] and [G, t_end-t_begin, N].
 static int run_chain_discrete(const b200_lev_desc& d, const uint8_t* outcomes, const float* factors_host,
                               int t_begin, int t_end, const float* state_in, float* state_out, float* dump,
-                              cudaStream_t st) {
+                              int64_t ldT, cudaStream_t st) {
   const int64_t N = d.n_investors;
   const int64_t tc = t_end - t_begin;
   for (int g0 = 0; g0 < d.n_grid; g0 += 32) {
@@ -400,10 +402,10 @@ static int run_chain_discrete(const b200_lev_desc& d, const uint8_t* outcomes, c
     a.p.G = g_cnt;
     a.p.V0 = d.value_0;
     a.p.N = N;
-    a.p.ldT = N;
-    a.p.state_in = state_in ? state_in + (int64_t)g0 * N : nullptr;
-    a.p.state_out = state_out + (int64_t)g0 * N;
-    a.p.dump = dump ? dump + (int64_t)g0 * tc * N : nullptr;
+    a.p.ldT = ldT;
+    a.p.state_in = state_in ? state_in + (int64_t)g0 * ldT : nullptr;
+    a.p.state_out = state_out + (int64_t)g0 * ldT;
+    a.p.dump = dump ? dump + (int64_t)g0 * tc * ldT : nullptr;
     a.variant = d.variant;
     a.st = st;
     int rc;
@@ -438,15 +440,15 @@ static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, con
   switch (d.n_outcomes) {
     case 2:
       log_discrete_stream_kernel<2><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(
-          outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, logV0, data_T, log_w, counts, N);
+          outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, logV0, data_T, log_w, counts, out_ld(d));
       break;
     case 3:
       log_discrete_stream_kernel<3><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(
-          outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, logV0, data_T, log_w, counts, N);
+          outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, logV0, data_T, log_w, counts, out_ld(d));
       break;
     default:
       log_discrete_stream_kernel<4><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(
-          outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, logV0, data_T, log_w, counts, N);
+          outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, logV0, data_T, log_w, counts, out_ld(d));
       break;
   }
   return check_cuda(cudaGetLastError(), "log_discrete_stream launch");
@@ -461,7 +463,7 @@ static int run_log_gbm(const b200_lev_desc& d, const float* x, const float* lev_
   if (d.source == B200_SRC_PHILOX) {
     const unsigned blocks = (unsigned)((N + 127) / 128);
     log_gbm_philox_kernel<<<blocks, 128, 0, st>>>(lv, d.seed, d.investor_offset, d.log_mean, d.sigma, d.horizon, N,
-                                                  d.n_grid, logV0, data_T, log_w, N);
+                                                  d.n_grid, logV0, data_T, log_w, out_ld(d));
     return check_cuda(cudaGetLastError(), "log_gbm_philox launch");
   }
   const unsigned blocks = (unsigned)((N + TILE_ROWS - 1) / TILE_ROWS);
@@ -473,10 +475,10 @@ static int run_log_gbm(const b200_lev_desc& d, const float* x, const float* lev_
     auto kern = log_gbm_stream_kernel<true>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * TILE_SMEM));
     kern<<<blocks, TILE_ROWS, STAGES * TILE_SMEM, st>>>(map, x, d.ld_outcomes, lv, d.horizon, N, d.n_grid, logV0,
-                                                        data_T, log_w, N);
+                                                        data_T, log_w, out_ld(d));
   } else {
     log_gbm_stream_kernel<false><<<blocks, TILE_ROWS, TILE_SMEM, st>>>(map, x, d.ld_outcomes, lv, d.horizon, N,
-                                                                       d.n_grid, logV0, data_T, log_w, N);
+                                                                       d.n_grid, logV0, data_T, log_w, out_ld(d));
   }
   return check_cuda(cudaGetLastError(), "log_gbm_stream launch");
 }
@@ -485,6 +487,7 @@ static int validate(const b200_lev_desc* d) {
   B200_REQUIRE(d != nullptr, "lev: desc is NULL");
   B200_REQUIRE(d->n_investors >= 0 && d->n_investors < ((int64_t)1 << 40), "lev: n_investors out of range");
   B200_REQUIRE(d->horizon >= 1, "lev: horizon must be >= 1");
+  B200_REQUIRE(d->ld_out == 0 || d->ld_out >= d->n_investors, "lev: ld_out < n_investors");
   B200_REQUIRE(d->n_grid >= 1 && d->n_grid <= B200_MAX_GRID, "lev: n_grid must be in 1..%d", B200_MAX_GRID);
   B200_REQUIRE(d->kind == B200_LEV_DISCRETE || d->kind == B200_LEV_GBM, "lev: unknown kind %d", d->kind);
   B200_REQUIRE(d->source == B200_SRC_STREAM || d->source == B200_SRC_PHILOX, "lev: unknown source %d", d->source);
@@ -521,7 +524,7 @@ extern "C" int b200_lev_sweep(const b200_lev_desc* desc, const void* outcomes, c
   if (d.kind == B200_LEV_DISCRETE) {
     if (d.mode == B200_MODE_CHAIN) {
       B200_REQUIRE(data_T != nullptr, "lev_sweep: CHAIN mode needs data_T");
-      return run_chain_discrete(d, (const uint8_t*)outcomes, host_f, 0, d.horizon, nullptr, data_T, nullptr, st);
+      return run_chain_discrete(d, (const uint8_t*)outcomes, host_f, 0, d.horizon, nullptr, data_T, nullptr, out_ld(d), st);
     }
     if (d.mode == B200_MODE_LOG) {
       B200_REQUIRE(d.source == B200_SRC_STREAM, "lev_sweep: discrete LOG mode takes streamed outcomes");
@@ -579,7 +582,7 @@ extern "C" int b200_lev_chunk(const b200_lev_desc* desc, const void* outcomes, c
     B200_REQUIRE(d.source != B200_SRC_PHILOX || (t_begin & 3) == 0, "lev_chunk: Philox chunks start at a multiple of 4");
     float* stf = (float*)state;
     return run_chain_discrete(d, (const uint8_t*)outcomes, factors, t_begin, t_end, t_begin > 0 ? stf : nullptr, stf,
-                              dump, st);
+                              dump, d.n_investors, st);
   }
   B200_REQUIRE((t_begin & 31) == 0, "lev_chunk: GBM chunks start at a multiple of 32");
   LevGrid lv;

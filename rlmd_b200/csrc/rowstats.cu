@@ -261,8 +261,9 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
       const long long tt = K - w->cnt_gt;  // ties that belong to the top group
       w->ties_top = tt;
       w->ties_adj = n_eq - tt;
-      w->mean_top = (w->sum_gt + (double)tt * thr) / (double)K;
-      w->mean_adj = (w->sum_lt + (double)(n_eq - tt) * thr) / (double)(n - K);
+      // a tie share of zero must not contribute 0 * inf
+      w->mean_top = (w->sum_gt + (tt > 0 ? (double)tt * thr : 0.0)) / (double)K;
+      w->mean_adj = (w->sum_lt + (n_eq - tt > 0 ? (double)(n_eq - tt) * thr : 0.0)) / (double)(n - K);
     }
   } else {
     if (threadIdx.x == 0) {

@@ -111,7 +111,12 @@ def lev_sweep(
         data_T = log_w = counts = None
         if want_data_T:
             data_T = out_data_T if out_data_T is not None else torch.empty((g, n), dtype=torch.float32, device=dev)
-            assert data_T.shape == (g, n) and data_T.is_contiguous() and data_T.dtype == torch.float32
+            if tuple(data_T.shape) != (g, n) or data_T.dtype != torch.float32 or (n > 1 and data_T.stride(1) != 1):
+                raise ValueError("out_data_T must be a float32 [G,N] tensor with unit inner stride")
+            if g > 1 and n > 0:
+                d.ld_out = data_T.stride(0)
+            if want_log_w and d.ld_out not in (0, n):
+                raise ValueError("log_w and a strided out_data_T cannot be combined")
         if want_log_w:
             log_w = torch.empty((g, n), dtype=torch.float64, device=dev)
         if want_counts:
@@ -256,6 +261,54 @@ def lev_series(
             last = dump.view(g, tc, n)[:, tc - 1, :]
         data_T = state if kind == "discrete" else last.clone()
     return data, data_T
+
+
+def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, outcomes_host: torch.Tensor, *,
+                   mode: str = "log", chunk_rows: Optional[int] = None, variant: int = 0, device="cuda",
+                   return_data_T: bool = False, group=None, n_total: Optional[int] = None):
+    """
+    The *_fixed_final_lev hot path for outcomes that live in HOST memory
+    (pinned for overlap): investor rows are independent, so the array is walked
+    in row chunks through two device staging buffers - the H2D copy of chunk i+1
+    overlaps the sweep of chunk i - and the statistics come back to the host.
+    Returns float64 [G,12] numpy (and data_T on the device when asked).
+    """
+    require_cuda()
+    if outcomes_host.is_cuda or outcomes_host.dim() != 2:
+        raise ValueError("outcomes_host must be a 2-D host tensor")
+    want = torch.uint8 if kind == "discrete" else torch.float32
+    if outcomes_host.dtype != want:
+        raise ValueError(f"outcomes_host must be {want}")
+    f = np.ascontiguousarray(factors, dtype=np.float32)
+    g = f.shape[0]
+    n, h = outcomes_host.shape
+    dev = torch.device(device)
+    ld = _round_up(h, 16 if kind == "discrete" else 4)
+    if chunk_rows is None:
+        chunk_rows = max(1024, (256 << 20) // (ld * outcomes_host.element_size()))
+    chunk_rows = min(chunk_rows, max(n, 1))
+    with torch.cuda.device(dev):
+        data_T = torch.empty((g, n), dtype=torch.float32, device=dev)
+        bufs = [torch.empty((chunk_rows, ld), dtype=want, device=dev) for _ in range(2)]
+        comp = torch.cuda.current_stream()
+        copy = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        copy.wait_stream(comp)
+        for i, r0 in enumerate(range(0, n, chunk_rows)):
+            rows = min(chunk_rows, n - r0)
+            b = bufs[i & 1]
+            if i >= 2:
+                copy.wait_event(done[i & 1])
+            with torch.cuda.stream(copy):
+                b[:rows, :h].copy_(outcomes_host[r0:r0 + rows], non_blocking=True)
+                ready[i & 1].record(copy)
+            comp.wait_event(ready[i & 1])
+            lev_sweep(kind, f, value_0, outcomes=b[:rows, :h], mode=mode, variant=variant,
+                      out_data_T=data_T[:, r0:r0 + rows])
+            done[i & 1].record(comp)
+        stats = rowstats(data_T, top, n_total=n_total, group=group).cpu().numpy() if n > 0 else np.zeros((g, 12))
+    return (stats, data_T) if return_data_T else stats
 
 
 # ----------------------------------------------------------------- rowstats

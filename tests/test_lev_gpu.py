@@ -28,7 +28,7 @@ def eng():
     return engine
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("case", DISCRETE, ids=lambda c: c["name"])
 def test_chain_data_T_bit_exact_vs_reference(eng, case, variant):
     oc, f, lev, _ = oracle_inputs(case)
