@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -142,12 +142,12 @@ class ClockSampler(threading.Thread):
             pass
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             self.sample()
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=1)
         import statistics
 
