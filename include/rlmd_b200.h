@@ -160,6 +160,55 @@ int b200_rowstats(const float* values, int64_t rows, int64_t n, int64_t ld,
  * row. */
 int b200_rowstats_exchange(int32_t phase, int64_t out[5]);
 
+/* ------------------------------------------------------------------ *
+ * Batched multiplicative environment step (K4)
+ *
+ * Sits behind the gym.Env classes of envs/coin_flip_envs.py (Coin_Inv{A,B,C}
+ * :150-233,:290-379,:436-538), envs/dice_roll_envs.py, envs/gbm_envs.py
+ * (:147-212,:304-323,:449-474) and envs/dice_roll_sh_envs.py (:160-235,
+ * :290-365,:420-502,:557-645): `step(action) -> (next_state, reward,
+ * [done, learn_done], risk)` and `reset()`, for n_envs independent copies in
+ * lock-step; the done flags are tools/env_resources.py:26-137.  All fp64.
+ * ------------------------------------------------------------------ */
+enum { B200_ENV_COIN = 0, B200_ENV_DICE = 1, B200_ENV_GBM = 2, B200_ENV_DICE_SH = 3 };
+enum { B200_INV_A = 0, B200_INV_B = 1, B200_INV_C = 2, B200_INV_INSURED = 3 };
+#define B200_ENV_MAX_GAMBLES 8
+
+typedef struct b200_env_desc {
+  int32_t family;      /* B200_ENV_*                                          */
+  int32_t investor;    /* B200_INV_* (INSURED: dice_sh only)                  */
+  int32_t n_gambles;   /* simultaneous identical gambles (dice_sh: 1)         */
+  int32_t stop_abs;    /* 1: stop-loss = |a0| (Coin_InvB, coin_flip_envs.py:308),
+                          0: (a0 + eps1) / 2 (every other class)               */
+  double max_value, initial_value, min_value;      /* 1e18, 1e4, 100            */
+  double max_abs_action, min_reward, min_return;   /* eps1, eps2, eps3          */
+  double max_return, min_weight, lev_factor;       /* 1e10, eps4, eta           */
+  double returns[3];     /* coin: (up, down, -); dice: (up, down, mid)          */
+  double probs[3];
+  double sh_returns[3];  /* safe haven (up, down, mid), already clamped         */
+  double i_lev_factor, sh_lev_factor;
+  double log_mean, vol;  /* GBM: r ~ N(log_mean, vol)                           */
+  uint64_t seed;         /* Philox key when returns are drawn on the device     */
+} b200_env_desc;
+
+/* state / action / risk vector lengths of the class `desc` describes */
+int b200_menv_dims(const b200_env_desc* desc, int32_t* state_dim,
+                   int32_t* action_dim, int32_t* risk_dim);
+
+/* wealth [E], time [E] (per-env step counter, starts at 1), state [E,S] or NULL;
+ * mask [E] bytes or NULL (= reset every env). */
+int b200_menv_reset(const b200_env_desc* desc, int64_t n_envs, double* wealth,
+                    int32_t* time, double* state, const uint8_t* mask, void* stream);
+
+/* action [E,A]; returns_in [E,n_gambles] injected returns (dice_sh: the die
+ * return, [E]) or NULL = draw on the device (Philox, `draw_index` must differ
+ * for every call); next_state [E,S], reward [E], done [E,2] bytes
+ * (done, learn_done), risk [E,R].  wealth / time are updated in place. */
+int b200_menv_step(const b200_env_desc* desc, int64_t n_envs, double* wealth,
+                   int32_t* time, const double* action, const double* returns_in,
+                   uint64_t draw_index, double* next_state, double* reward,
+                   uint8_t* done, double* risk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,37 @@ class LevDesc(C.Structure):
     ]
 
 
+ENV_COIN, ENV_DICE, ENV_GBM, ENV_DICE_SH = 0, 1, 2, 3
+INV_A, INV_B, INV_C, INV_INSURED = 0, 1, 2, 3
+ENV_MAX_GAMBLES = 8
+
+
+class EnvDesc(C.Structure):
+    _fields_ = [
+        ("family", C.c_int32),
+        ("investor", C.c_int32),
+        ("n_gambles", C.c_int32),
+        ("stop_abs", C.c_int32),
+        ("max_value", C.c_double),
+        ("initial_value", C.c_double),
+        ("min_value", C.c_double),
+        ("max_abs_action", C.c_double),
+        ("min_reward", C.c_double),
+        ("min_return", C.c_double),
+        ("max_return", C.c_double),
+        ("min_weight", C.c_double),
+        ("lev_factor", C.c_double),
+        ("returns", C.c_double * 3),
+        ("probs", C.c_double * 3),
+        ("sh_returns", C.c_double * 3),
+        ("i_lev_factor", C.c_double),
+        ("sh_lev_factor", C.c_double),
+        ("log_mean", C.c_double),
+        ("vol", C.c_double),
+        ("seed", C.c_uint64),
+    ]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"rlmd_b200 error {code}: {msg}")
@@ -61,6 +92,9 @@ _SIGNATURES = {
     "b200_lev_sweep": (C.c_int, [C.POINTER(LevDesc), _vp, C.POINTER(C.c_float), _vp, _vp, _vp, _vp]),
     "b200_lev_draw": (C.c_int, [C.POINTER(LevDesc), _vp, _vp]),
     "b200_lev_chunk": (C.c_int, [C.POINTER(LevDesc), _vp, C.POINTER(C.c_float), _i32, _i32, _vp, _vp, _vp]),
+    "b200_menv_dims": (C.c_int, [C.POINTER(EnvDesc)] + [C.POINTER(_i32)] * 3),
+    "b200_menv_reset": (C.c_int, [C.POINTER(EnvDesc), _i64, _vp, _vp, _vp, _vp, _vp]),
+    "b200_menv_step": (C.c_int, [C.POINTER(EnvDesc), _i64, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "b200_rowstats_workspace_bytes": (_i64, [_i64]),
     "b200_rowstats": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "b200_rowstats_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),

@@ -1,0 +1,68 @@
+"""
+Fixture generators that drive the UNMODIFIED reference env / replay classes with
+injected random draws (see gen_golden.py for how to run).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import ref_shim  # noqa: E402
+import golden_io  # noqa: E402
+
+
+class _Feeder:
+    """Stands in for np.random.choice / np.random.normal: hands out pre-drawn returns."""
+
+    def __init__(self):
+        self.queue = []
+
+    def choice(self, a, p=None, size=None):
+        v = self.queue.pop(0)
+        assert len(v) == int(size)
+        assert all(x in list(a) for x in v)
+        return np.array(v, dtype=np.float64)
+
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        v = self.queue.pop(0)
+        assert len(v) == int(size)
+        return np.array(v, dtype=np.float64)
+
+
+def gen_env():
+    for name, module, cls, family, investor, n_g in golden_io.ENV_CASES:
+        mod = ref_shim.load(module)
+        with ref_shim.reference_cwd():
+            env = getattr(mod, cls)() if family == "dice_sh" else getattr(mod, cls)(n_g)
+        a_dim = env.action_space.shape[0]
+        n_draw = 1 if family == "dice_sh" else n_g
+        actions, draws = golden_io.env_inputs(name, a_dim, n_draw, family)
+        rets = golden_io.env_returns(family, draws)
+        feeder = _Feeder()
+        old_choice, old_normal = np.random.choice, np.random.normal
+        np.random.choice, np.random.normal = feeder.choice, feeder.normal
+        states, rewards, dones, risks, resets = [], [], [], [], []
+        try:
+            state0 = np.array(env.reset(), dtype=np.float64)
+            for t in range(golden_io.ENV_STEPS):
+                feeder.queue.append(list(rets[t]))
+                ns, rew, done, risk = env.step(actions[t].copy())
+                states.append(np.array(ns, dtype=np.float64).copy())
+                rewards.append(float(rew))
+                dones.append([bool(done[0]), bool(done[1])])
+                risks.append(np.array(risk, dtype=np.float64).copy())
+                resets.append(bool(done[0]))
+                if done[0]:
+                    env.reset()
+        finally:
+            np.random.choice, np.random.normal = old_choice, old_normal
+        out = os.path.join(HERE, f"env_{name}.npz")
+        np.savez_compressed(out, actions=actions, returns=rets, state0=state0, states=np.array(states),
+                            rewards=np.array(rewards), dones=np.array(dones), risks=np.array(risks),
+                            resets=np.array(resets))
+        print("wrote", out, np.array(states).shape, "episodes:", int(np.sum(resets)))

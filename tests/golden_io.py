@@ -90,3 +90,55 @@ def lev_case(name: str) -> dict:
         if c["name"] == name:
             return c
     raise KeyError(name)
+
+
+# ---------------------------------------------------------------------- envs
+# (fixture name, reference module, class, family, investor, n_gambles)
+ENV_CASES = [
+    ("coin_A1", "envs.coin_flip_envs", "Coin_InvA", "coin", "A", 1),
+    ("coin_A3", "envs.coin_flip_envs", "Coin_InvA", "coin", "A", 3),
+    ("coin_B1", "envs.coin_flip_envs", "Coin_InvB", "coin", "B", 1),
+    ("coin_B2", "envs.coin_flip_envs", "Coin_InvB", "coin", "B", 2),
+    ("coin_C1", "envs.coin_flip_envs", "Coin_InvC", "coin", "C", 1),
+    ("coin_C3", "envs.coin_flip_envs", "Coin_InvC", "coin", "C", 3),
+    ("dice_A1", "envs.dice_roll_envs", "Dice_InvA", "dice", "A", 1),
+    ("dice_B2", "envs.dice_roll_envs", "Dice_InvB", "dice", "B", 2),
+    ("dice_C1", "envs.dice_roll_envs", "Dice_InvC", "dice", "C", 1),
+    ("gbm_A1", "envs.gbm_envs", "GBM_InvA", "gbm", "A", 1),
+    ("gbm_A2", "envs.gbm_envs", "GBM_InvA", "gbm", "A", 2),
+    ("gbm_B2", "envs.gbm_envs", "GBM_InvB", "gbm", "B", 2),
+    ("gbm_C1", "envs.gbm_envs", "GBM_InvC", "gbm", "C", 1),
+    ("dicesh_A", "envs.dice_roll_sh_envs", "Dice_SH_InvA", "dice_sh", "A", 1),
+    ("dicesh_B", "envs.dice_roll_sh_envs", "Dice_SH_InvB", "dice_sh", "B", 1),
+    ("dicesh_C", "envs.dice_roll_sh_envs", "Dice_SH_InvC", "dice_sh", "C", 1),
+]
+ENV_STEPS = 600
+
+
+def env_inputs(name: str, action_dim: int, n_draws: int, family: str):
+    """Seeded actions [T,A] and raw draws [T,n]: uniform(0,1) for the discrete families,
+    standard normals for GBM (turned into returns by `env_returns`)."""
+    seed = 1000 + sum(ord(ch) for ch in name)
+    rs = np.random.RandomState(seed)
+    actions = rs.uniform(-0.99, 0.99, size=(ENV_STEPS, action_dim))
+    # saturated / degenerate actions exercise the exact-equality done flags
+    for t in range(7, ENV_STEPS, 41):
+        actions[t, -1] = 0.99
+    for t in range(19, ENV_STEPS, 53):
+        actions[t, :] = -0.99
+    for t in range(29, ENV_STEPS, 67):
+        actions[t, :] = 1e-7
+    for t in range(3, ENV_STEPS, 5):
+        actions[t] = np.abs(actions[t]) * 0.3    # calm stretches so episodes get long
+    draws = rs.standard_normal((ENV_STEPS, n_draws)) if family == "gbm" else rs.random_sample((ENV_STEPS, n_draws))
+    return actions, draws
+
+
+def env_returns(family: str, draws: np.ndarray) -> np.ndarray:
+    """Raw draws -> the return values the env would have sampled."""
+    if family == "coin":
+        return np.where(draws < 0.5, 0.5, -0.4)
+    if family in ("dice", "dice_sh"):
+        return np.where(draws < 1 / 6, 0.5, np.where(draws < 2 / 6, -0.5, 0.05))
+    drift, vol = 0.0540025395205692, 0.1897916175617430
+    return (drift - vol ** 2 / 2) + vol * draws
