@@ -209,6 +209,80 @@ int b200_menv_step(const b200_env_desc* desc, int64_t n_envs, double* wealth,
                    uint64_t draw_index, double* next_state, double* reward,
                    uint8_t* done, double* risk, void* stream);
 
+/* ------------------------------------------------------------------ *
+ * Replay buffer (K5 gather / n-step return, K6 append)
+ *
+ * Sits behind tools/replay_torch.py ReplayBufferTorch (and its NumPy twin
+ * tools/replay.py ReplayBuffer): __init__ :57-115, store_exp :167-197 with
+ * _episode_history :117-165, sample_exp :360-412 with _construct_history
+ * :199-247 and the multi-step return :273-358.  The caller owns every buffer
+ * (the Python shim keeps them as the same-named torch tensors).
+ * ------------------------------------------------------------------ */
+#define B200_REPLAY_MAX_STEPS 64
+
+typedef struct b200_replay_desc {
+  int64_t mem_size;           /* slots (tools/replay_torch.py:79-82), < 2^31    */
+  int32_t state_dim;          /* sum(input_dims)                                 */
+  int32_t action_dim;         /* num_actions                                     */
+  float* state_memory;        /* [mem_size, state_dim]                           */
+  float* action_memory;       /* [mem_size, action_dim]                          */
+  float* reward_memory;       /* [mem_size]                                      */
+  float* next_state_memory;   /* [mem_size, state_dim]                           */
+  uint8_t* terminal_memory;   /* [mem_size] 0/1                                  */
+  int32_t* episode_start;     /* [mem_size] first slot of the slot's episode     */
+  int64_t* header;            /* [8]: mem_idx, finished episodes, first / last
+                                 terminal slot, first slot of the running episode */
+} b200_replay_desc;
+
+/* zeroes the header, the terminal flags and episode_start (the reference's
+ * T.empty leaves terminal_memory uninitialised, :98-100; its first-episode
+ * branch :147 only works when that memory happens to be zero) */
+int b200_replay_reset(const b200_replay_desc* desc, void* stream);
+
+/* Appends `count` transitions in order, as `count` calls of store_exp would
+ * (slot = (position + k) % mem_size; reward = fl32(max(reward, reward_floor)),
+ * :189) and maintains episode_start / the header (_episode_history :117-165).
+ * state [count,S], action [count,A], reward [count], next_state [count,S]:
+ * double when is_f64 (the envs' dtype) else float; done [count] bytes.
+ * position = mem_idx before the call, or -1 = take it from the device header
+ * (no host round trip).  The multi-step bookkeeping assumes the append-only
+ * regime the reference asserts (buffer >= n_cumsteps). */
+int b200_replay_store(const b200_replay_desc* desc, const void* state, const void* action,
+                      const void* reward, const void* next_state, const uint8_t* done,
+                      int64_t count, int32_t is_f64, int64_t position, double reward_floor,
+                      void* stream);
+
+/* One transition from HOST memory - store_exp(state, action, reward,
+ * next_state, done) as the training loop calls it (:167): the row travels as
+ * a kernel parameter, so the call is one launch and no copy.
+ * B200_ELIMIT when 2*state_dim + action_dim + 1 > 480. */
+int b200_replay_store_host(const b200_replay_desc* desc, const double* state_host,
+                           const double* action_host, double reward,
+                           const double* next_state_host, int32_t done, int64_t position,
+                           double reward_floor, void* stream);
+
+/* n_batches mini-batches of `batch` samples in one call (sample_exp :360-412
+ * is n_batches = 1).
+ * idx      : int64 [n_batches*batch] slots to sample (the reference's `batch`,
+ *            :383 - the parity path), or NULL = draw `batch` DISTINCT uniform
+ *            slots per mini-batch on the device (Philox4x32-10 keyed by seed /
+ *            draw_index, rejection of duplicates in a shared-memory set;
+ *            batch <= 8192) and report them in out_idx.
+ * filled   : min(mem_idx, mem_size) (:382), or -1 = from the device header.
+ * multi_steps n in 1..64; gamma_pow_host: HOST float[n], fl32(gamma**t).
+ * additive : 1 = sum of discounted rewards (dynamics "A"), 0 = product.
+ * outputs  : out_state [.,S] (n = 1: state_memory[idx]; n > 1: the history's
+ *            next_state at its first used step, :309), out_action [.,A],
+ *            out_reward [.], out_next_state [.,S] = next_state_memory[idx],
+ *            out_done [.] bytes, out_eff [.] int64 effective length (:336-345).
+ *            A slot outside [0, filled) yields zeros and out_eff = 0. */
+int b200_replay_sample(const b200_replay_desc* desc, const int64_t* idx, int64_t n_batches,
+                       int32_t batch, int64_t filled, int32_t multi_steps,
+                       const float* gamma_pow_host, int32_t additive, uint64_t seed,
+                       uint64_t draw_index, int64_t* out_idx, float* out_state,
+                       float* out_action, float* out_reward, float* out_next_state,
+                       uint8_t* out_done, int64_t* out_eff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

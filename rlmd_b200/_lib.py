@@ -70,6 +70,24 @@ class EnvDesc(C.Structure):
     ]
 
 
+REPLAY_MAX_STEPS = 64
+
+
+class ReplayDesc(C.Structure):
+    _fields_ = [
+        ("mem_size", C.c_int64),
+        ("state_dim", C.c_int32),
+        ("action_dim", C.c_int32),
+        ("state_memory", C.c_void_p),
+        ("action_memory", C.c_void_p),
+        ("reward_memory", C.c_void_p),
+        ("next_state_memory", C.c_void_p),
+        ("terminal_memory", C.c_void_p),
+        ("episode_start", C.c_void_p),
+        ("header", C.c_void_p),
+    ]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"rlmd_b200 error {code}: {msg}")
@@ -95,6 +113,12 @@ _SIGNATURES = {
     "b200_menv_dims": (C.c_int, [C.POINTER(EnvDesc)] + [C.POINTER(_i32)] * 3),
     "b200_menv_reset": (C.c_int, [C.POINTER(EnvDesc), _i64, _vp, _vp, _vp, _vp, _vp]),
     "b200_menv_step": (C.c_int, [C.POINTER(EnvDesc), _i64, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "b200_replay_reset": (C.c_int, [C.POINTER(ReplayDesc), _vp]),
+    "b200_replay_store": (C.c_int, [C.POINTER(ReplayDesc), _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, C.c_double, _vp]),
+    "b200_replay_store_host": (C.c_int, [C.POINTER(ReplayDesc), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.c_double, C.POINTER(C.c_double), _i32, _i64, C.c_double, _vp]),
+    "b200_replay_sample": (C.c_int, [C.POINTER(ReplayDesc), _vp, _i64, _i32, _i64, _i32, C.POINTER(C.c_float), _i32,
+                                     C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_rowstats_workspace_bytes": (_i64, [_i64]),
     "b200_rowstats": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "b200_rowstats_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),

@@ -1,0 +1,458 @@
+// K5 / K6: replay buffer - batched append with episode bookkeeping, unique
+// index draws and the (multi-step) gather.
+//
+// Reference: tools/replay_torch.py (ReplayBufferTorch) - store_exp :167-197 with
+// _episode_history :117-165; sample_exp :360-412 with _construct_history
+// :199-247 and the n-step return :273-310, :336-345.  tools/replay.py is the
+// same algorithm on NumPy fp64.
+//
+// The reference keeps, per finished episode, Python slices of the memories and
+// searches them per sample.  Here the history of a sampled slot follows in
+// O(1) from one int32 per slot (first slot of its episode) and a five-word
+// header kept in device memory (restated and tested against
+// the list bookkeeping in oracle/replay_oracle.py):
+//   finished episode j >= 1 : start = episode_start[i], len = i - start + 1 (+1
+//                             unless slot i is terminal: the history carries
+//                             one FUTURE step)
+//   first episode / nothing finished yet : start = 0, len = i + 1
+//   episode still running   : the reference falls back to the prefix of
+//                             episode 0: start = 0, len = min(i - e_last + 1, e_0 + 1)
+//   eff = min(len, n);  R = sum / prod_{t < eff-1} fl32(gamma^t) * r[first + t],
+//   first = start + len - eff;  s0 = next_state[first], a0 = action[first].
+// Everything a sample needs is on the device, so store -> sample sequences run
+// without a host round trip (and can be captured in a CUDA graph).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace b200 {
+
+enum { H_MEM_IDX = 0, H_EPISODES = 1, H_E0 = 2, H_ELAST = 3, H_RUN_START = 4 };
+
+constexpr int STORE_HOST_MAX_WORDS = 480;  // doubles travelling as a kernel parameter
+
+struct HostRow {
+  double v[STORE_HOST_MAX_WORDS];
+};
+
+// ------------------------------------------------------------------ store
+template <typename T>
+__device__ __forceinline__ float to_reward(T r, double floor_) {
+  const double x = (double)r;
+  return (float)(x > floor_ ? x : floor_);  // max(reward, r_abs_zero) in double, then fp32 (:189)
+}
+
+// rows: flattened copy / conversion of state, action, next_state
+template <typename T>
+__global__ void __launch_bounds__(256)
+replay_store_rows_kernel(const b200_replay_desc d, const T* __restrict__ state, const T* __restrict__ action,
+                         const T* __restrict__ next_state, int64_t count, int64_t position) {
+  const int S = d.state_dim, A = d.action_dim, W = 2 * S + A;
+  const int64_t pos = position >= 0 ? position : d.header[H_MEM_IDX];
+  const int64_t total = count * W;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = e / W;
+    const int c = (int)(e - k * W);
+    const int64_t slot = (pos + k) % d.mem_size;
+    if (c < S) d.state_memory[slot * S + c] = (float)state[k * S + c];
+    else if (c < S + A) d.action_memory[slot * A + (c - S)] = (float)action[k * A + (c - S)];
+    else d.next_state_memory[slot * S + (c - S - A)] = (float)next_state[k * S + (c - S - A)];
+  }
+}
+
+// scalars: reward, terminal flag and the first slot of the episode of every new
+// slot = max(run_start before this call, 1 + last terminal slot before it in
+// this call).  One 1024-wide tile per block: an inclusive max-scan inside the
+// tile, and a backward search over the earlier `done` bytes for the tile prefix.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+replay_store_index_kernel(const b200_replay_desc d, const T* __restrict__ reward,
+                          const uint8_t* __restrict__ done, int64_t count, int64_t position,
+                          double reward_floor) {
+  __shared__ long long warp_max[32];
+  __shared__ long long tile_prefix;
+  const int64_t pos = position >= 0 ? position : d.header[H_MEM_IDX];
+  const int64_t tile0 = (int64_t)blockIdx.x * 1024;
+  const int64_t k = tile0 + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  // boundary carried by the transitions before this tile
+  if (threadIdx.x == 0) tile_prefix = -1;
+  __syncthreads();
+  for (int64_t hi = tile0; hi > 0; hi -= 1024) {
+    const int64_t j = hi - 1 - threadIdx.x;
+    long long cand = (j >= 0 && done[j]) ? (long long)(pos + j + 1) : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand = max(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    if (lane == 0 && cand >= 0) atomicMax(&tile_prefix, cand);
+    __syncthreads();
+    if (tile_prefix >= 0) break;
+    __syncthreads();
+  }
+  __syncthreads();
+  long long carry = tile_prefix >= 0 ? tile_prefix : (long long)d.header[H_RUN_START];
+
+  // exclusive max-scan of (pos + k + 1 where done) inside the tile
+  const bool mine = k < count;
+  const bool dn = mine && done[k] != 0;
+  long long v = dn ? (long long)(pos + k + 1) : -1;
+  long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long up = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = max(inc, up);
+  }
+  if (lane == 31) warp_max[wid] = inc;
+  __syncthreads();
+  long long before = carry;
+  for (int w = 0; w < wid; ++w) before = max(before, warp_max[w]);
+  long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) excl = -1;
+  const long long start = max(before, excl);
+
+  if (mine) {
+    const int64_t slot = (pos + k) % d.mem_size;
+    d.reward_memory[slot] = to_reward(reward[k], reward_floor);
+    d.terminal_memory[slot] = dn ? 1 : 0;
+    d.episode_start[slot] = (int32_t)start;
+  }
+}
+
+// header: finished-episode count, first / last terminal slot, write position
+__global__ void __launch_bounds__(1024)
+replay_commit_kernel(const b200_replay_desc d, const uint8_t* __restrict__ done, int64_t count, int64_t position) {
+  __shared__ long long s_cnt[32], s_first[32], s_last[32];
+  long long cnt = 0, first = (1ll << 62), last = -1;
+  for (int64_t k = threadIdx.x; k < count; k += blockDim.x) {
+    if (done[k]) {
+      ++cnt;
+      first = min(first, (long long)k);
+      last = max(last, (long long)k);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s_cnt[wid] = cnt; s_first[wid] = first; s_last[wid] = last; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      cnt += s_cnt[w];
+      first = min(first, s_first[w]);
+      last = max(last, s_last[w]);
+    }
+    int64_t* h = d.header;
+    const int64_t pos = position >= 0 ? position : h[H_MEM_IDX];
+    if (cnt > 0) {
+      if (h[H_EPISODES] == 0) h[H_E0] = pos + first;
+      h[H_ELAST] = pos + last;
+      h[H_RUN_START] = pos + last + 1;
+      h[H_EPISODES] += cnt;
+    }
+    h[H_MEM_IDX] = pos + count;
+  }
+}
+
+// one transition handed over as a kernel parameter (no H2D copy): the
+// store_exp(state, action, reward, next_state, done) call of the training loop
+__global__ void __launch_bounds__(128)
+replay_store_host_kernel(const b200_replay_desc d, const __grid_constant__ HostRow row, int done, int64_t position,
+                         double reward_floor) {
+  const int S = d.state_dim, A = d.action_dim;
+  int64_t* h = d.header;
+  const int64_t pos = position >= 0 ? position : h[H_MEM_IDX];
+  __syncthreads();  // everybody has read the header before thread 0 advances it
+  const int64_t slot = pos % d.mem_size;
+  for (int c = threadIdx.x; c < 2 * S + A; c += blockDim.x) {
+    const float v = (float)row.v[c];
+    if (c < S) d.state_memory[slot * S + c] = v;
+    else if (c < S + A) d.action_memory[slot * A + (c - S)] = v;
+    else d.next_state_memory[slot * S + (c - S - A)] = v;
+  }
+  if (threadIdx.x == 0) {
+    d.reward_memory[slot] = to_reward(row.v[2 * S + A], reward_floor);
+    d.terminal_memory[slot] = done ? 1 : 0;
+    d.episode_start[slot] = (int32_t)h[H_RUN_START];
+    if (done) {
+      if (h[H_EPISODES] == 0) h[H_E0] = pos;
+      h[H_ELAST] = pos;
+      h[H_RUN_START] = pos + 1;
+      h[H_EPISODES] += 1;
+    }
+    h[H_MEM_IDX] = pos + 1;
+  }
+}
+
+// ------------------------------------------------------------------- draw
+// B distinct uniform indices in [0, filled) per batch, one block per batch.
+// Round r: every pending position t draws
+//   v = mulhi64(philox(t, r, batch, draw_index lo; seed ^ draw_index hi).xy, filled)
+// and claims v in a shared-memory hash set; the claim with the smallest
+// (round, t) owns the value, everybody else redraws in round r+1.  The result
+// depends only on (seed, draw_index, batch, filled, B) - oracle/replay_oracle.py
+// restates it word for word.
+constexpr unsigned long long SET_EMPTY = ~0ull;
+
+__global__ void __launch_bounds__(1024)
+replay_draw_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t B, uint64_t seed, uint64_t draw_index,
+                   int32_t table_size, int64_t* __restrict__ out_idx) {
+  extern __shared__ unsigned long long table[];
+  const int64_t filled = filled_arg >= 0 ? filled_arg : min(d.header[H_MEM_IDX], d.mem_size);
+  const uint32_t mask = (uint32_t)table_size - 1u;
+  const uint32_t k0 = (uint32_t)seed ^ (uint32_t)(draw_index >> 32), k1 = (uint32_t)(seed >> 32);
+  for (int s = threadIdx.x; s < table_size; s += blockDim.x) table[s] = SET_EMPTY;
+  __syncthreads();
+  // positions owned by this thread: t = threadIdx.x + j * blockDim.x (B <= 8 * 1024)
+  uint32_t pending_bits = 0;
+  uint32_t val[8];
+  for (int j = 0; j < 8; ++j)
+    if ((int)threadIdx.x + j * (int)blockDim.x < B) pending_bits |= 1u << j;
+  if (filled <= 0 || filled < B) {  // cannot draw B distinct values: flag every position
+    for (int j = 0; j < 8; ++j)
+      if (pending_bits >> j & 1) out_idx[(int64_t)blockIdx.x * B + threadIdx.x + j * blockDim.x] = -1;
+    return;
+  }
+  for (uint32_t round = 0;; ++round) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!(pending_bits >> j & 1)) continue;
+      const uint32_t t = threadIdx.x + j * blockDim.x;
+      const Philox4 p = philox4x32_10(t, round, blockIdx.x, (uint32_t)draw_index ^ PHILOX_TAG_REPLAY, k0, k1);
+      const unsigned long long u = ((unsigned long long)p.x << 32) | p.y;
+      const uint32_t v = (uint32_t)__umul64hi(u, (unsigned long long)filled);
+      val[j] = v;
+      const unsigned long long mine = ((unsigned long long)v << 32) | ((unsigned long long)round << 16) | t;
+      uint32_t s = (v * 0x9E3779B1u) & mask;
+      for (;;) {
+        unsigned long long cur = table[s];
+        if (cur == SET_EMPTY) {
+          cur = atomicCAS(&table[s], SET_EMPTY, mine);
+          if (cur == SET_EMPTY) break;
+        }
+        if ((uint32_t)(cur >> 32) == v) {
+          atomicMin(&table[s], mine);
+          break;
+        }
+        s = (s + 1) & mask;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!(pending_bits >> j & 1)) continue;
+      const uint32_t t = threadIdx.x + j * blockDim.x;
+      const uint32_t v = val[j];
+      uint32_t s = (v * 0x9E3779B1u) & mask;
+      while ((uint32_t)(table[s] >> 32) != v) s = (s + 1) & mask;
+      if ((uint32_t)(table[s] & 0xffffffffu) == ((round << 16) | t)) {
+        out_idx[(int64_t)blockIdx.x * B + t] = (int64_t)v;
+        pending_bits &= ~(1u << j);
+      }
+    }
+    if (!__syncthreads_or(pending_bits != 0)) break;
+  }
+}
+
+// ----------------------------------------------------------------- gather
+struct GammaPow {
+  float v[B200_REPLAY_MAX_STEPS];
+};
+
+template <int LANES>
+__global__ void __launch_bounds__(256)
+replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, int64_t n_samples,
+                     int64_t filled_arg, int32_t n_steps, int32_t additive, const __grid_constant__ GammaPow gp,
+                     float* __restrict__ out_state, float* __restrict__ out_action, float* __restrict__ out_reward,
+                     float* __restrict__ out_next_state, uint8_t* __restrict__ out_done,
+                     int64_t* __restrict__ out_eff) {
+  const int S = d.state_dim, A = d.action_dim;
+  const int lane = threadIdx.x % LANES;
+  const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
+  const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
+  const int64_t filled = filled_arg >= 0 ? filled_arg : min(d.header[H_MEM_IDX], d.mem_size);
+  const int64_t episodes = d.header[H_EPISODES], e0 = d.header[H_E0], elast = d.header[H_ELAST];
+
+  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; q < n_samples; q += groups) {
+    const int64_t i = idx[q];
+    const bool ok = i >= 0 && i < filled;
+    int64_t first = i;
+    int eff = ok ? 1 : 0;
+    float R = 0.0f;
+    const float* src_state = d.state_memory;
+    uint8_t term = 0;
+    if (ok) {
+      term = d.terminal_memory[i];
+      if (n_steps <= 1) {
+        R = d.reward_memory[i];
+      } else {
+        int64_t start, len;
+        if (episodes == 0 || i <= e0) { start = 0; len = i + 1; }
+        else if (i <= elast) { start = d.episode_start[i]; len = i - start + 1 + (term ? 0 : 1); }
+        else { start = 0; len = min(i - elast + 1, e0 + 1); }
+        eff = (int)min(len, (int64_t)n_steps);
+        first = start + len - eff;
+        src_state = d.next_state_memory;  // the reference's histories hold next_state (:132)
+        float acc = additive ? 0.0f : 1.0f;
+        for (int t0 = 0; t0 < n_steps - 1; t0 += LANES) {
+          const int t = t0 + lane;
+          float term_t = 0.0f;
+          if (t < eff - 1) term_t = gp.v[t] * d.reward_memory[first + t];
+          const int lim = min(LANES, n_steps - 1 - t0);
+          for (int j = 0; j < lim; ++j) {
+            const float x = __shfl_sync(gmask, term_t, j, LANES);
+            if (t0 + j < eff - 1) acc = additive ? acc + x : acc * x;
+          }
+        }
+        R = acc;
+      }
+    }
+    for (int c = lane; c < S; c += LANES) {
+      out_state[q * S + c] = ok ? src_state[first * S + c] : 0.0f;
+      out_next_state[q * S + c] = ok ? d.next_state_memory[i * S + c] : 0.0f;
+    }
+    for (int c = lane; c < A; c += LANES) out_action[q * A + c] = ok ? d.action_memory[first * A + c] : 0.0f;
+    if (lane == 0) {
+      out_reward[q] = R;
+      out_done[q] = term;
+      out_eff[q] = eff;
+    }
+  }
+}
+
+static int check_desc(const b200_replay_desc* d) {
+  B200_REQUIRE(d != nullptr, "replay: desc is NULL");
+  B200_REQUIRE(d->mem_size > 0 && d->mem_size < (1ll << 31), "replay: mem_size %lld outside 1..2^31-1",
+               (long long)d->mem_size);
+  B200_REQUIRE(d->state_dim > 0 && d->action_dim > 0, "replay: state_dim / action_dim must be positive");
+  B200_REQUIRE(d->state_memory && d->action_memory && d->reward_memory && d->next_state_memory &&
+                   d->terminal_memory && d->episode_start && d->header,
+               "replay: a buffer pointer in the desc is NULL");
+  return 0;
+}
+
+static int require_device() {
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  return 0;
+}
+
+template <typename T>
+static int store_impl(const b200_replay_desc* d, const void* state, const void* action, const void* reward,
+                      const void* next_state, const uint8_t* done, int64_t count, int64_t position,
+                      double reward_floor, cudaStream_t st) {
+  const int W = 2 * d->state_dim + d->action_dim;
+  const int64_t total = count * W;
+  const int grid_rows = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8);
+  replay_store_rows_kernel<T><<<grid_rows, 256, 0, st>>>(*d, (const T*)state, (const T*)action,
+                                                         (const T*)next_state, count, position);
+  const int tiles = (int)((count + 1023) / 1024);
+  replay_store_index_kernel<T><<<tiles, 1024, 0, st>>>(*d, (const T*)reward, done, count, position, reward_floor);
+  replay_commit_kernel<<<1, 1024, 0, st>>>(*d, done, count, position);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_replay_reset(const b200_replay_desc* d, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (int rc = check_desc(d)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA(cudaMemsetAsync(d->header, 0, 8 * sizeof(int64_t), st));
+  B200_CUDA(cudaMemsetAsync(d->terminal_memory, 0, (size_t)d->mem_size, st));
+  B200_CUDA(cudaMemsetAsync(d->episode_start, 0, (size_t)d->mem_size * sizeof(int32_t), st));
+  return 0;
+}
+
+extern "C" int b200_replay_store(const b200_replay_desc* d, const void* state, const void* action,
+                                 const void* reward, const void* next_state, const uint8_t* done, int64_t count,
+                                 int32_t is_f64, int64_t position, double reward_floor, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (int rc = check_desc(d)) return rc;
+  B200_REQUIRE(count >= 0, "replay_store: count %lld < 0", (long long)count);
+  if (count == 0) return 0;
+  B200_REQUIRE(state && action && reward && next_state && done, "replay_store: an input pointer is NULL");
+  B200_REQUIRE(count <= d->mem_size, "replay_store: count %lld exceeds mem_size %lld", (long long)count,
+               (long long)d->mem_size);
+  cudaStream_t st = (cudaStream_t)stream;
+  return is_f64 ? store_impl<double>(d, state, action, reward, next_state, done, count, position, reward_floor, st)
+                : store_impl<float>(d, state, action, reward, next_state, done, count, position, reward_floor, st);
+}
+
+extern "C" int b200_replay_store_host(const b200_replay_desc* d, const double* state_host, const double* action_host,
+                                      double reward, const double* next_state_host, int32_t done,
+                                      int64_t position, double reward_floor, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (int rc = check_desc(d)) return rc;
+  B200_REQUIRE(state_host && action_host && next_state_host, "replay_store_host: an input pointer is NULL");
+  const int S = d->state_dim, A = d->action_dim;
+  if (2 * S + A + 1 > STORE_HOST_MAX_WORDS)
+    return set_error(B200_ELIMIT, "replay_store_host: 2*state_dim + action_dim + 1 = %d exceeds %d words; use "
+                     "b200_replay_store with device buffers", 2 * S + A + 1, STORE_HOST_MAX_WORDS);
+  HostRow row;
+  for (int c = 0; c < S; ++c) row.v[c] = state_host[c];
+  for (int c = 0; c < A; ++c) row.v[S + c] = action_host[c];
+  for (int c = 0; c < S; ++c) row.v[S + A + c] = next_state_host[c];
+  row.v[2 * S + A] = reward;
+  replay_store_host_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(*d, row, done, position, reward_floor);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_replay_sample(const b200_replay_desc* d, const int64_t* idx, int64_t n_batches, int32_t batch,
+                                  int64_t filled, int32_t multi_steps, const float* gamma_pow_host,
+                                  int32_t additive, uint64_t seed, uint64_t draw_index, int64_t* out_idx,
+                                  float* out_state, float* out_action, float* out_reward, float* out_next_state,
+                                  uint8_t* out_done, int64_t* out_eff, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (int rc = check_desc(d)) return rc;
+  B200_REQUIRE(n_batches >= 0 && batch >= 0, "replay_sample: negative batch count / size");
+  const int64_t n_samples = n_batches * batch;
+  if (n_samples == 0) return 0;
+  B200_REQUIRE(multi_steps >= 1, "replay_sample: multi_steps %d < 1", multi_steps);
+  if (multi_steps > B200_REPLAY_MAX_STEPS)
+    return set_error(B200_ELIMIT, "replay_sample: multi_steps %d exceeds %d", multi_steps, B200_REPLAY_MAX_STEPS);
+  B200_REQUIRE(multi_steps == 1 || gamma_pow_host != nullptr, "replay_sample: gamma_pow_host is NULL");
+  B200_REQUIRE(out_state && out_action && out_reward && out_next_state && out_done && out_eff,
+               "replay_sample: an output pointer is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (idx == nullptr) {
+    B200_REQUIRE(out_idx != nullptr, "replay_sample: out_idx is NULL while indices are drawn on the device");
+    if (batch > 8192) return set_error(B200_ELIMIT, "replay_sample: on-device draw supports batch <= 8192 (got %d)", batch);
+    B200_REQUIRE(n_batches <= 0x7fffffff, "replay_sample: too many batches");
+    int table = 64;
+    while (table < 2 * batch) table <<= 1;
+    const int threads = std::min(1024, (batch + 31) / 32 * 32);
+    const size_t smem = (size_t)table * sizeof(unsigned long long);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    if (smem > 48 * 1024 && dev < 64 && !attr_set[dev]) {
+      B200_CUDA(cudaFuncSetAttribute(replay_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      attr_set[dev] = true;
+    }
+    replay_draw_kernel<<<(unsigned)n_batches, threads, smem, st>>>(*d, filled, batch, seed, draw_index, table, out_idx);
+    idx = out_idx;
+  }
+  GammaPow gp;
+  for (int t = 0; t < B200_REPLAY_MAX_STEPS; ++t) gp.v[t] = (multi_steps > 1 && t < multi_steps) ? gamma_pow_host[t] : 0.0f;
+  const int wide = d->state_dim >= 32;
+  const int lanes = wide ? 32 : 8;
+  const int64_t want_blocks = (n_samples * lanes + 255) / 256;
+  const int grid = (int)std::min<int64_t>(want_blocks, (int64_t)sm_count() * 8);
+  if (wide)
+    replay_gather_kernel<32><<<grid, 256, 0, st>>>(*d, idx, n_samples, filled, multi_steps, additive, gp, out_state,
+                                                    out_action, out_reward, out_next_state, out_done, out_eff);
+  else
+    replay_gather_kernel<8><<<grid, 256, 0, st>>>(*d, idx, n_samples, filled, multi_steps, additive, gp, out_state,
+                                                   out_action, out_reward, out_next_state, out_done, out_eff);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}

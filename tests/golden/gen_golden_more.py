@@ -66,3 +66,57 @@ def gen_env():
                             rewards=np.array(rewards), dones=np.array(dones), risks=np.array(risks),
                             resets=np.array(resets))
         print("wrote", out, np.array(states).shape, "episodes:", int(np.sum(resets)))
+
+
+def gen_replay():
+    """
+    tools/replay_torch.py ReplayBufferTorch (and the NumPy twin tools/replay.py) driven
+    through their public store_exp / sample_exp with `randperm` / `np.random.choice`
+    answering the fixture's pre-drawn batches.  terminal_memory is zeroed after
+    construction (T.empty leaves it uninitialised).
+    """
+    import torch
+
+    mod = ref_shim.load("tools.replay_torch")
+    for case in golden_io.REPLAY_CASES:
+        st = golden_io.replay_stream(case)
+        inputs = golden_io.replay_inputs_dict(case)
+        inputs["gpu"] = "cpu"
+        buf = mod.ReplayBufferTorch(inputs)
+        buf.terminal_memory[:] = False
+        pending = {"batch": None}
+        real_randperm = torch.randperm
+
+        def fake_randperm(n, *a, **k):
+            b = pending["batch"]
+            assert int(b.max()) < n
+            return torch.as_tensor(b)
+
+        out = {}
+        ev = 0
+        torch.randperm = fake_randperm
+        try:
+            for i in range(case["fill"] + 1):
+                while ev < len(case["events"]) and case["events"][ev] == i:
+                    pending["batch"] = st["batches"][ev]
+                    s, a, r, s2, d, eff = buf.sample_exp()
+                    out[f"ev{ev}_batch"] = st["batches"][ev]
+                    out[f"ev{ev}_states"] = np.array(torch.as_tensor(s).numpy(), dtype=np.float32).copy()
+                    out[f"ev{ev}_actions"] = np.array(torch.as_tensor(a).numpy(), dtype=np.float32).copy()
+                    out[f"ev{ev}_rewards"] = np.array(torch.as_tensor(r).numpy(), dtype=np.float32).copy()
+                    out[f"ev{ev}_next_states"] = s2.numpy().copy()
+                    out[f"ev{ev}_dones"] = d.numpy().copy()
+                    out[f"ev{ev}_eff"] = np.atleast_1d(torch.as_tensor(eff).numpy()).astype(np.int64)
+                    ev += 1
+                if i == case["fill"]:
+                    break
+                buf.store_exp(st["state"][i], st["action"][i], float(st["reward"][i]), st["next_state"][i],
+                              bool(st["done"][i]))
+        finally:
+            torch.randperm = real_randperm
+        assert ev == len(case["events"])
+        out["mem_idx"] = np.array(buf.mem_idx)
+        out["reward_memory"] = buf.reward_memory[: case["fill"]].numpy().copy()
+        path = os.path.join(HERE, f"replay_{case['name']}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, "events:", ev, "episodes:", int(st["done"].sum()))

@@ -142,3 +142,67 @@ def env_returns(family: str, draws: np.ndarray) -> np.ndarray:
         return np.where(draws < 1 / 6, 0.5, np.where(draws < 2 / 6, -0.5, 0.05))
     drift, vol = 0.0540025395205692, 0.1897916175617430
     return (drift - vol ** 2 / 2) + vol * draws
+
+
+# -------------------------------------------------------------------- replay
+# Seeded transition streams + sampling events for tools/replay_torch.py.
+# `lens`: episode lengths in order (cycled); `fill`: transitions stored in total;
+# `events`: fill levels at which a mini-batch is sampled (before storing further).
+REPLAY_CASES = [
+    # plain gather (multi_steps == 1)
+    dict(name="n1", mem=600, s=5, a=1, n=1, gamma=0.99, dyna="M", batch=64, r0=None,
+         lens=[7, 12, 5, 30, 9], fill=500, events=[64, 130, 500], seed=11),
+    # additive n-step, sampling while the first episode is still running and afterwards
+    dict(name="n3_A", mem=400, s=5, a=1, n=3, gamma=0.5, dyna="A", batch=32, r0=None,
+         lens=[40, 3, 5, 2, 17, 1, 1, 9], fill=330, events=[33, 40, 41, 77, 200, 330], seed=12),
+    # multiplicative n-step (the multiplicative envs' setting), reward floor active
+    dict(name="n5_M", mem=700, s=5, a=1, n=5, gamma=0.99, dyna="M", batch=48, r0=0.995,
+         lens=[9, 33, 4, 6, 60, 5, 2, 11], fill=640, events=[48, 49, 100, 333, 640], seed=13),
+    # n = 10, wider state / action (Dice_SH_InvC: 6 / 3), first transition terminal
+    dict(name="n10_M", mem=900, s=6, a=3, n=10, gamma=0.97, dyna="M", batch=96, r0=None,
+         lens=[1, 14, 25, 1, 8, 58, 10, 3], fill=800, events=[96, 97, 250, 611, 800], seed=14),
+    dict(name="n10_A", mem=500, s=3, a=2, n=10, gamma=0.9, dyna="A", batch=40, r0=-0.5,
+         lens=[12, 12, 30, 2, 21], fill=450, events=[40, 45, 222, 450], seed=15),
+    # n = 2: the shortest multi-step history
+    dict(name="n2_M", mem=300, s=5, a=1, n=2, gamma=0.99, dyna="M", batch=32, r0=None,
+         lens=[5, 6, 7, 1, 2, 50], fill=280, events=[32, 150, 280], seed=16),
+]
+
+
+def replay_case(name: str) -> dict:
+    for c in REPLAY_CASES:
+        if c["name"] == name:
+            return c
+    raise KeyError(name)
+
+
+def replay_stream(case: dict) -> dict:
+    """The transitions of a case: float64 arrays as an env would hand them over, python-bool dones."""
+    rs = np.random.RandomState(case["seed"])
+    f, s, a = case["fill"], case["s"], case["a"]
+    done = np.zeros(f, dtype=bool)
+    pos, k = -1, 0
+    while True:
+        pos += case["lens"][k % len(case["lens"])]
+        k += 1
+        if pos >= f:
+            break
+        done[pos] = True
+    state = rs.standard_normal((f, s))
+    action = rs.uniform(-0.99, 0.99, size=(f, a))
+    next_state = rs.standard_normal((f, s))
+    if case["dyna"] == "A":
+        reward = rs.standard_normal(f)
+    else:
+        reward = 1.0 + 0.01 * rs.standard_normal(f)
+    batches = [rs.permutation(e)[: case["batch"]].astype(np.int64) for e in case["events"]]
+    return dict(state=state, action=action, reward=reward, next_state=next_state, done=done, batches=batches)
+
+
+def replay_inputs_dict(case: dict) -> dict:
+    """The `inputs` dictionary keys tools/replay_torch.py:64-82 reads."""
+    return {
+        "gpu": "cuda:0", "input_dims": (case["s"],), "num_actions": case["a"], "mini_batch_size": case["batch"],
+        "discount": case["gamma"], "multi_steps": case["n"], "r_abs_zero": case["r0"], "dynamics": case["dyna"],
+        "buffer": case["mem"], "n_cumsteps": case["mem"] + 100,
+    }
