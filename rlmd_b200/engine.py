@@ -242,7 +242,14 @@ def lev_series(
         else:
             state = torch.empty((3, n), dtype=torch.float64, device=dev)
         if chunk_steps is None:
-            chunk_steps = max(32, min(h, chunk_bytes // max(4 * g * max(n, 1), 1), 2048 // g))
+            n_ref = max(n, 1)
+            if group is not None:   # every rank must walk the same chunks (one exchange per chunk)
+                import torch.distributed as dist
+
+                t = torch.tensor([n_ref], dtype=torch.int64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+                n_ref = int(t.item())
+            chunk_steps = max(32, min(h, chunk_bytes // max(4 * g * n_ref, 1), 2048 // g))
         tc_max = max(32, (int(chunk_steps) // 32) * 32)
         tc_max = min(tc_max, (h + 31) // 32 * 32)
         chunk = torch.empty((g * tc_max * max(n, 1),), dtype=torch.float32, device=dev)
@@ -342,21 +349,11 @@ def rowstats(values: torch.Tensor, top: int, *, n_total: Optional[int] = None, g
         if group is None:
             check(lib.b200_rowstats(ptr(values), rows, n, ld, n_total, int(top), ptr(ws), ptr(stats), -1, stream_ptr()))
             return stats
-        import torch.distributed as dist
+        from . import sharding
 
-        ex = (C.c_int64 * 5)()
-        wsf = ws.view(torch.float64)
-        for phase in range(6):
+        def run_phase(phase):
             check(lib.b200_rowstats(ptr(values), rows, n, ld, n_total, int(top), ptr(ws), ptr(stats), phase,
                                     stream_ptr()))
-            check(lib.b200_rowstats_exchange(phase, ex))
-            io, ic, do, dc, _ = list(ex)
-            if ic:
-                part = ws[:, io:io + ic].contiguous()
-                dist.all_reduce(part, group=group)
-                ws[:, io:io + ic] = part
-            if dc:
-                part = wsf[:, do:do + dc].contiguous()
-                dist.all_reduce(part, group=group)
-                wsf[:, do:do + dc] = part
+
+        sharding.exchange_phases(run_phase, ws, group)
     return stats

@@ -124,9 +124,29 @@ def _print_final(lev: np.ndarray, stats: np.ndarray, smart: bool = False) -> Non
                                 mean_adj, med_top if smart else med_adj, mad_adj, std_adj))
 
 
+_GROUP = None
+
+
+def set_process_group(group) -> None:
+    """
+    Multi-GPU use (one process per GPU): after this call the
+    functions below treat `outcomes` as THIS RANK'S investor rows, `top` as the
+    global top-K, and return global statistics on every rank (data_T stays the
+    local shard).  `None` restores single-GPU behaviour.
+    """
+    global _GROUP
+    _GROUP = group
+
+
+def _n_total(n_local: int, device) -> int:
+    from . import sharding
+    return n_local if _GROUP is None else sharding.global_count(n_local, _GROUP, device)
+
+
 def _final(kind, outcomes, table, lev, top, value_0, mode="chain"):
     res = engine.lev_sweep(kind, table, _as_float(value_0), outcomes=outcomes, mode=mode)
-    stats = engine.rowstats(res["data_T"], int(top))
+    n_total = _n_total(outcomes.shape[0], outcomes.device)
+    stats = engine.rowstats(res["data_T"], int(top), n_total=n_total, group=_GROUP)
     return res["data_T"], stats.cpu().numpy()
 
 
@@ -166,7 +186,8 @@ def _series(kind, outcomes, table, lev, investors, horizon, top, value_0) -> Tup
     n, h = outcomes.shape
     if (investors is not None and _as_int(investors) != n) or (horizon is not None and _as_int(horizon) != h):
         raise ValueError("investors/horizon do not match the shape of outcomes")
-    return engine.lev_series(kind, table, lev, _as_float(value_0), int(top), outcomes=outcomes)
+    return engine.lev_series(kind, table, lev, _as_float(value_0), int(top), outcomes=outcomes,
+                             n_total=_n_total(n, outcomes.device), group=_GROUP)
 
 
 def coin_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, down_r, lev_low, lev_high, lev_incr):

@@ -1,0 +1,70 @@
+"""
+Host-side logic of the multi-GPU path: the sweep shards
+by INVESTOR - one process per GPU, every rank holds the whole leverage grid and a
+contiguous block of investor rows, Philox counters carry the global investor id -
+so there is no data-path collective.  The only exchange is inside the
+cross-investor statistics: after each pass of b200_rowstats the per-row partial
+sums and radix histograms named by b200_rowstats_exchange are summed over ranks.
+
+Nothing here launches a kernel, so the module is exercised on CPU with the gloo
+backend (tests/test_sharding_gloo.py) as well as with NCCL on the GPUs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Tuple
+
+import torch
+
+from ._lib import check, lib
+
+N_PHASES = 6
+
+
+def shard_range(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """(offset, count) of the contiguous investor block of `rank`: sizes differ by at most one."""
+    if not 0 <= rank < world:
+        raise ValueError("rank outside the world")
+    base, extra = divmod(int(n_total), int(world))
+    count = base + (1 if rank < extra else 0)
+    offset = rank * base + min(rank, extra)
+    return offset, count
+
+
+def exchange_words(phase: int) -> Tuple[int, int, int, int, int]:
+    """(int_offset, int_count, double_offset, double_count, words_per_row) to sum after `phase`."""
+    ex = (C.c_int64 * 5)()
+    check(lib.b200_rowstats_exchange(int(phase), ex))
+    return tuple(int(v) for v in ex)
+
+
+def global_count(n_local: int, group, device) -> int:
+    """Sum of the ranks' local investor counts."""
+    import torch.distributed as dist
+
+    t = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, group=group)
+    return int(t.item())
+
+
+def exchange_phases(run_phase: Callable[[int], None], workspace: torch.Tensor, group) -> None:
+    """
+    Drives the statistics passes of one rank: `run_phase(p)` launches phase p on
+    the local rows (filling this rank's partials in `workspace` [rows, words],
+    int64), after which the phase's exchange region is all-reduced (SUM) so that
+    every rank resolves the same global histogram walk in phase p+1.
+    """
+    import torch.distributed as dist
+
+    ws_f = workspace.view(torch.float64)
+    for phase in range(N_PHASES):
+        run_phase(phase)
+        io, ic, do, dc, _ = exchange_words(phase)
+        if ic:
+            part = workspace[:, io:io + ic].contiguous()
+            dist.all_reduce(part, group=group)
+            workspace[:, io:io + ic] = part
+        if dc:
+            part = ws_f[:, do:do + dc].contiguous()
+            dist.all_reduce(part, group=group)
+            ws_f[:, do:do + dc] = part

@@ -1,0 +1,124 @@
+"""
+Multi-GPU parity (needs >= 2 GPUs; run with `gpurun --gpus 2`): two NCCL ranks,
+each holding half of the investors, must return the single-GPU statistics, and
+the drop-in shims must return the reference fixture's `data` from sharded rows.
+On one GPU: the CUDA passes against the CPU restatement of the pass structure,
+word for word on the exchanged workspace regions.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import golden_io
+from oracle import rowstats_passes as rp
+from test_oracle_lev import assert_stats_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_cuda_passes_fill_the_exchange_words_like_the_restatement():
+    from rlmd_b200 import engine, sharding
+    from rlmd_b200._lib import check, lib, ptr, stream_ptr
+
+    rs = np.random.RandomState(5)
+    rows, n, top = 3, 20_011, 13
+    v = np.exp(rs.standard_normal((rows, n)) * 2).astype(np.float32)
+    v[1, ::5] = v[1, 2]
+    vals = torch.as_tensor(v, device="cuda")
+    ws = engine.rowstats_workspace(rows, vals.device)
+    stats = torch.empty((rows, 12), dtype=torch.float64, device="cuda")
+    words = sharding.exchange_words(0)[4]
+    ws_cpu = np.zeros((rows, words), dtype=np.int64)
+    offs = {"h1": sharding.exchange_words(0)[0], "h2": sharding.exchange_words(1)[0],
+            "h3": sharding.exchange_words(2)[0], "cnt": sharding.exchange_words(3)[0]}
+    emu = rp.RowStatsPasses(v, n, top, ws_cpu, offs)
+    for phase in range(6):
+        check(lib.b200_rowstats(ptr(vals), rows, n, n, n, top, ptr(ws), ptr(stats), phase, stream_ptr()))
+        emu.run(phase)
+        io, ic, do, dc, _ = sharding.exchange_words(phase)
+        got = ws.cpu().numpy()
+        if ic:
+            assert np.array_equal(got[:, io:io + ic], ws_cpu[:, io:io + ic]), f"phase {phase}: integer words"
+        if dc:
+            np.testing.assert_allclose(got.view(np.float64)[:, do:do + dc], ws_cpu.view(np.float64)[:, do:do + dc],
+                                       rtol=1e-12)
+    np.testing.assert_allclose(stats.cpu().numpy(), emu.stats, rtol=1e-12)
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from rlmd_b200 import engine, lev_exp, sharding
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        # (1) rowstats over investor shards
+        rs = np.random.RandomState(21)
+        v = np.exp(rs.standard_normal((5, 100_003)) * 3).astype(np.float32)
+        v[2, ::9] = v[2, 1]
+        off, cnt = sharding.shard_range(v.shape[1], world, rank)
+        local = torch.as_tensor(v[:, off:off + cnt], device="cuda")
+        st = engine.rowstats(local, 11, n_total=v.shape[1], group=dist.group.WORLD)
+        np.save(os.path.join(out_dir, f"stats{rank}.npy"), st.cpu().numpy())
+        # (2) the dice_smart_lev shim on sharded rows of the reference's fixture
+        case = golden_io.lev_case("dice_top5")
+        oc = golden_io.draw_outcomes(case)
+        off, cnt = sharding.shard_range(case["n"], world, rank)
+        lev_exp.set_process_group(dist.group.WORLD)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            data, data_T = lev_exp.dice_smart_lev("cuda", torch.as_tensor(oc[off:off + cnt].astype(np.int64)), None,
+                                                  None, case["top"], case["v0"], case["up_r"], case["down_r"],
+                                                  case["mid_r"], *case["grid"])
+        lev_exp.set_process_group(None)
+        np.save(os.path.join(out_dir, f"data{rank}.npy"), data.cpu().numpy())
+        np.save(os.path.join(out_dir, f"dataT{rank}.npy"), data_T.cpu().numpy())
+        # (3) Philox sweeps are independent of the sharding
+        lev = np.asarray(lev_exp.param_range(0.1, 1.0, 0.1), dtype=np.float32)
+        off, cnt = sharding.shard_range(50_000, world, rank)
+        res = engine.lev_sweep("discrete", lev_exp.dice_factor_table(lev, 0.5, -0.5, 0.05), 100.0, n_investors=cnt,
+                               horizon=257, mode="chain", seed=9, investor_offset=off, probs=(1 / 6, 1 / 6, 2 / 3))
+        np.save(os.path.join(out_dir, f"phx{rank}.npy"), res["data_T"].cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_ranks_equal_one(tmp_path):
+    import torch.multiprocessing as mp
+    from rlmd_b200 import engine, lev_exp
+
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rs = np.random.RandomState(21)
+    v = np.exp(rs.standard_normal((5, 100_003)) * 3).astype(np.float32)
+    v[2, ::9] = v[2, 1]
+    want = engine.rowstats(torch.as_tensor(v, device="cuda"), 11).cpu().numpy()
+    for r in range(world):
+        got = np.load(tmp_path / f"stats{r}.npy")
+        assert np.array_equal(got[:, 9:12], want[:, 9:12])
+        np.testing.assert_allclose(got, want, rtol=1e-12)
+    case = golden_io.lev_case("dice_top5")
+    gold = golden_io.load("lev_dice_top5")
+    cols = gold["cols"]
+    for r in range(world):
+        data = np.load(tmp_path / f"data{r}.npy")
+        assert np.array_equal(data[:, 9:13, cols], gold["data"][:, 9:13]), "medians / leverage row must be exact"
+        assert_stats_close(data[:, :9, cols], gold["data"][:, :9])
+    data_T = np.concatenate([np.load(tmp_path / f"dataT{r}.npy") for r in range(world)], axis=1)
+    assert np.array_equal(data_T.view(np.uint32), gold["data_T"].view(np.uint32))
+    lev = np.asarray(lev_exp.param_range(0.1, 1.0, 0.1), dtype=np.float32)
+    one = engine.lev_sweep("discrete", lev_exp.dice_factor_table(lev, 0.5, -0.5, 0.05), 100.0, n_investors=50_000,
+                           horizon=257, mode="chain", seed=9, probs=(1 / 6, 1 / 6, 2 / 3))["data_T"].cpu().numpy()
+    two = np.concatenate([np.load(tmp_path / f"phx{r}.npy") for r in range(world)], axis=1)
+    assert np.array_equal(one.view(np.uint32), two.view(np.uint32))
