@@ -283,6 +283,32 @@ int b200_replay_sample(const b200_replay_desc* desc, const int64_t* idx, int64_t
                        float* out_action, float* out_reward, float* out_next_state,
                        uint8_t* out_done, int64_t* out_eff, void* stream);
 
+/* ------------------------------------------------------------------ *
+ * Growth-rate summaries (engine-added)
+ *
+ * The reference forms the time-average growth rate only as the env reward
+ * exp(log(W/W0)/t) (envs/coin_flip_envs.py:183-185) and summarises with mean /
+ * median / 5th percentile, np.percentile(method="median_unbiased")
+ * (tools/eval_episodes.py:276-315, plotting/plots_multiverse.py:167-169).
+ * Per row of log_w (the LOG sweep's fp64 log wealth, one row per leverage):
+ *   g_i = (log_w_i - log_v0) / horizon
+ * out[r][6 + n_q] (double):
+ *   0 valid runs (data_T finite and > 0: survived the reference's fp32 wealth;
+ *     data_T NULL -> log_w finite), 1 mean g, 2 population std g,
+ *   3 mean g over the valid runs, 4 min g, 5 max g,
+ *   6.. the n_q (<= 3) quantiles, Hyndman-Fan type 8 = numpy "median_unbiased"
+ *   (two equal neighbours, e.g. both -inf, give that value instead of numpy's nan).
+ * Exact order statistics (radix select on the fp64 bit pattern).  phase = -1
+ * runs everything; phase 0..6 one step each, a multi-GPU caller summing the
+ * words named by b200_growth_exchange(phase) over ranks in between.
+ * ------------------------------------------------------------------ */
+int64_t b200_growth_workspace_bytes(int64_t rows);
+int b200_growth_exchange(int32_t phase, int64_t out[5]);
+int b200_growth_summary(const double* log_w, const float* data_T, int64_t rows, int64_t n,
+                        int64_t ld, int64_t ld_T, int64_t n_total, double log_v0,
+                        int32_t horizon, const double* quantiles_host, int32_t n_q,
+                        void* workspace, double* out, int32_t phase, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

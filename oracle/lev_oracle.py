@@ -326,3 +326,32 @@ def galaxy_brain(ru_grid, rd_grid, pu_grid) -> np.ndarray:
             for k, rd in enumerate(rd_grid):
                 data[i, j, k] = (pu, ru, rd, pu / rd - (1 - pu) / ru)
     return data
+
+
+def growth_summary(log_w: np.ndarray, data_T, value_0: float, horizon: int, quantiles=(0.05, 0.5)) -> np.ndarray:
+    """
+    Time-average growth rates g = (log W_T - log V0) / H per leverage row, reduced the
+    way the reference's consumers reduce per-run quantities: mean / std with NumPy,
+    percentiles with np.percentile(method="median_unbiased")
+    (tools/eval_episodes.py:276-315, plotting/plots_multiverse.py:167-169).
+    Columns: valid runs (fp32 wealth finite and > 0), mean, population std, mean over the
+    valid runs, min, max, then the quantiles.
+    """
+    lw = np.asarray(log_w, dtype=np.float64)
+    out = np.zeros((lw.shape[0], 6 + len(quantiles)))
+    for r in range(lw.shape[0]):
+        g = (lw[r] - np.log(float(value_0))) / float(horizon)
+        if data_T is not None:
+            w = np.asarray(data_T[r], dtype=np.float32)
+            ok = np.isfinite(w) & (w > 0)
+        else:
+            ok = np.isfinite(lw[r])
+        with np.errstate(invalid="ignore"):
+            out[r, 0] = ok.sum()
+            out[r, 1] = g.mean()
+            out[r, 2] = np.sqrt(np.mean((g - g.mean()) ** 2))
+            out[r, 3] = g[ok].mean() if ok.any() else np.nan
+            out[r, 4], out[r, 5] = g.min(), g.max()
+            for j, q in enumerate(quantiles):
+                out[r, 6 + j] = np.percentile(g, 100.0 * q, method="median_unbiased")
+    return out

@@ -119,6 +119,10 @@ _SIGNATURES = {
                                          C.c_double, C.POINTER(C.c_double), _i32, _i64, C.c_double, _vp]),
     "b200_replay_sample": (C.c_int, [C.POINTER(ReplayDesc), _vp, _i64, _i32, _i64, _i32, C.POINTER(C.c_float), _i32,
                                      C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_growth_workspace_bytes": (_i64, [_i64]),
+    "b200_growth_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),
+    "b200_growth_summary": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, C.c_double, _i32, C.POINTER(C.c_double),
+                                      _i32, _vp, _vp, _i32, _vp]),
     "b200_rowstats_workspace_bytes": (_i64, [_i64]),
     "b200_rowstats": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "b200_rowstats_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),

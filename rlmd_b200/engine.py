@@ -357,3 +357,53 @@ def rowstats(values: torch.Tensor, top: int, *, n_total: Optional[int] = None, g
 
         sharding.exchange_phases(run_phase, ws, group)
     return stats
+
+
+# ------------------------------------------------------------ growth rates
+GROWTH_NAMES = ("valid", "mean", "std", "mean_valid", "min", "max")
+
+
+def growth_summary(log_w: torch.Tensor, horizon: int, value_0: float, *, data_T: Optional[torch.Tensor] = None,
+                   quantiles: Sequence[float] = (0.05, 0.5), n_total: Optional[int] = None, group=None) -> torch.Tensor:
+    """
+    Time-average growth rates g = (log W_T - log V0) / H of every leverage row of
+    `log_w` [G,N] (fp64, CUDA; the LOG sweep's output) reduced to
+    float64 [G, 6 + len(quantiles)]: valid-run count (data_T finite and > 0), mean,
+    population std, mean over the valid runs, min, max, then the quantiles
+    (numpy's method="median_unbiased", the reference's percentile convention,
+    tools/eval_episodes.py:276-315).  With `group` the rows are investor shards.
+    """
+    require_cuda()
+    if log_w.dim() != 2 or log_w.dtype != torch.float64 or not log_w.is_cuda or log_w.stride(1) != 1:
+        raise ValueError("log_w must be a [G,N] float64 CUDA tensor with unit inner stride")
+    rows, n = log_w.shape
+    q = [float(x) for x in quantiles]
+    if len(q) > 3:
+        raise ValueError("at most three quantiles per call")
+    ld = log_w.stride(0) if rows > 1 else max(log_w.stride(0), n)
+    ld_T = 0
+    if data_T is not None:
+        if tuple(data_T.shape) != (rows, n) or data_T.dtype != torch.float32 or data_T.stride(1) != 1:
+            raise ValueError("data_T must be a float32 [G,N] tensor matching log_w")
+        ld_T = data_T.stride(0) if rows > 1 else max(data_T.stride(0), n)
+    n_total = n if n_total is None else int(n_total)
+    dev = log_w.device
+    out = torch.empty((rows, 6 + len(q)), dtype=torch.float64, device=dev)
+    if rows == 0:
+        return out
+    qarr = (C.c_double * max(len(q), 1))(*q)
+    with torch.cuda.device(dev):
+        words = lib.b200_growth_workspace_bytes(1) // 8
+        ws = torch.empty((rows, words), dtype=torch.int64, device=dev)
+
+        def run_phase(phase):
+            check(lib.b200_growth_summary(ptr(log_w), ptr(data_T), rows, n, ld, ld_T, n_total, math.log(float(value_0)),
+                                          int(horizon), qarr, len(q), ptr(ws), ptr(out), phase, stream_ptr()))
+
+        if group is None:
+            run_phase(-1)
+        else:
+            from . import sharding
+
+            sharding.exchange_phases(run_phase, ws, group, what="growth", n_phases=7)
+    return out

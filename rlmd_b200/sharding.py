@@ -31,10 +31,11 @@ def shard_range(n_total: int, world: int, rank: int) -> Tuple[int, int]:
     return offset, count
 
 
-def exchange_words(phase: int) -> Tuple[int, int, int, int, int]:
+def exchange_words(phase: int, what: str = "rowstats") -> Tuple[int, int, int, int, int]:
     """(int_offset, int_count, double_offset, double_count, words_per_row) to sum after `phase`."""
     ex = (C.c_int64 * 5)()
-    check(lib.b200_rowstats_exchange(int(phase), ex))
+    fn = lib.b200_rowstats_exchange if what == "rowstats" else lib.b200_growth_exchange
+    check(fn(int(phase), ex))
     return tuple(int(v) for v in ex)
 
 
@@ -47,7 +48,8 @@ def global_count(n_local: int, group, device) -> int:
     return int(t.item())
 
 
-def exchange_phases(run_phase: Callable[[int], None], workspace: torch.Tensor, group) -> None:
+def exchange_phases(run_phase: Callable[[int], None], workspace: torch.Tensor, group, what: str = "rowstats",
+                    n_phases: int = N_PHASES) -> None:
     """
     Drives the statistics passes of one rank: `run_phase(p)` launches phase p on
     the local rows (filling this rank's partials in `workspace` [rows, words],
@@ -57,9 +59,9 @@ def exchange_phases(run_phase: Callable[[int], None], workspace: torch.Tensor, g
     import torch.distributed as dist
 
     ws_f = workspace.view(torch.float64)
-    for phase in range(N_PHASES):
+    for phase in range(n_phases):
         run_phase(phase)
-        io, ic, do, dc, _ = exchange_words(phase)
+        io, ic, do, dc, _ = exchange_words(phase, what)
         if ic:
             part = workspace[:, io:io + ic].contiguous()
             dist.all_reduce(part, group=group)
