@@ -309,6 +309,50 @@ int b200_growth_summary(const double* log_w, const float* data_T, int64_t rows, 
                         int32_t horizon, const double* quantiles_host, int32_t n_q,
                         void* workspace, double* out, int32_t phase, void* stream);
 
+/* ------------------------------------------------------------------ *
+ * State-dependent leverage sweeps (K3, "big brain")
+ *
+ * Sits behind lev/lev_exp.py coin_big_brain_lev :270-452 (with coin_optimal_lev
+ * :240-267) and dice_big_brain_lev :741-932 (dice_optimal_lev :704-738): for
+ * every (retention, stop-loss) grid point the chain
+ *   lev = eta (1 - floor(V) / V);  V <- V (1 + lev g_t)
+ * with the wealth after / leverage before every step written out for the
+ * per-step statistics (b200_rowstats) of data[R,S,26,H-1].
+ * ------------------------------------------------------------------ */
+enum { B200_BB_COIN = 0, /* fp32 chain (lev/lev_exp.py:323-379)                  */
+       B200_BB_DICE = 1  /* float64 wealth chain, mixed-precision leverage (:791) */ };
+#define B200_BB_MAX_POINTS 128
+
+typedef struct b200_bigbrain_desc {
+  int64_t n_investors;   /* N (local shard)                                       */
+  int64_t ld_outcomes;   /* row stride of the uint8 outcome codes                 */
+  int32_t horizon;       /* H                                                     */
+  int32_t n_points;      /* grid points of this call, <= B200_BB_MAX_POINTS       */
+  int32_t kind;          /* B200_BB_*                                             */
+  int32_t reserved;
+  float value_0;         /* V0 (fp32 like the scripts' tensor)                    */
+  float lev_factor32;    /* fl32(LEV_FACTOR)                                      */
+  double lev_factor64;   /* LEV_FACTOR (a float64 0-dim tensor in the scripts)    */
+  double returns[3];     /* return of outcome code 0,1,2 (coin: down, up, -;
+                            dice: up, down, mid)                                  */
+} b200_bigbrain_desc;
+
+/*
+ * Steps [s_begin, s_end) of the recurrence (step s consumes outcome column s;
+ * step 0 is the initialisation with the scalar leverage lev0 and writes no dump).
+ * stop_vmin_host / roll_host / lev0_host : HOST arrays [n_points]: fl32(stop*V0),
+ *            the fp32 retention ratio, and the float64 leverage of step 0.
+ * state    : float (coin) / double (dice) [2, n_points, N]: wealth then leverage;
+ *            in/out (ignored as input when s_begin == 0).
+ * dump     : float [n_points, s_end - max(s_begin,1), 2, N]: per step the leverage
+ *            BEFORE the update (statistic rows 12..23 of column s-1) and the
+ *            wealth AFTER it (rows 0..11); NULL = advance the state only.
+ */
+int b200_bigbrain_chunk(const b200_bigbrain_desc* desc, const uint8_t* outcomes,
+                        const float* stop_vmin_host, const float* roll_host,
+                        const double* lev0_host, int32_t s_begin, int32_t s_end, void* state,
+                        float* dump, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -269,53 +269,81 @@ def format_final(lev: np.ndarray, stats: np.ndarray) -> str:
 
 
 # ---------------------------------------------------------------------- big brain
-def optimal_lev(value_t, value_0, value_min, lev_factor, roll):
+def _opt_lev_f32(v, v0, vmin, eta32, roll):
     """
-    coin_optimal_lev / dice_optimal_lev (lev/lev_exp.py:240-267,704-738) in the
-    dtype the caller hands in; all operands are numpy scalars/arrays so that
-    NumPy reproduces torch's "0-dim operands do not promote" rule explicitly:
-    callers pass value_min, lev_factor, roll already rounded to the array dtype.
+    coin_optimal_lev / the retention branch of dice_optimal_lev (lev/lev_exp.py:258-267,
+    :730-738) on an fp32 vector: every operand fp32 (the float64 0-dim LEV_FACTOR of
+    the scripts does not promote an fp32 [N] tensor, it is rounded to fp32).
     """
-    dt = value_t.dtype if isinstance(value_t, np.ndarray) else np.asarray(value_t).dtype
-    one = dt.type(1)
+    one = F32(1)
     if roll == 0:
-        return lev_factor * (one - value_min / value_t)
-    floor = np.where(value_t <= value_0, value_min, value_0 + roll * (value_t - value_0))
-    return lev_factor * (one - floor.astype(dt) / value_t)
+        return (eta32 * (one - vmin / v)).astype(F32)
+    floor = np.where(v <= v0, vmin, v0 + roll * (v - v0)).astype(F32)
+    return (eta32 * (one - floor / v)).astype(F32)
 
 
-def coin_big_brain(outcomes, top, value_0, up_r, down_r, lev_factor,
-                   stop_grid, roll_grid):
+def _initial_lev_f64(v0, vmin, eta64) -> float:
     """
-    coin_big_brain_lev (lev/lev_exp.py:270-452): data [R,S,26,H-1] fp32.
-    All fp32: returns g = where(out==1, up_r, down_r) rounded to fp32,
-    V <- V*(1 + lev*g), lev from optimal_lev; stats of lev -> rows 12..23 at t
-    (before the update), stats of V -> rows 0..11 (after), rows 24/25 = stop, roll.
+    The leverage of step 0 (:327, :806-808): every operand is 0-dim, so the fp32 inner
+    term times the float64 LEV_FACTOR promotes to float64 (both branches of the rule
+    reduce to value_min because value_t == value_0).
+    """
+    inner = F32(1) - F32(vmin / v0)
+    return float(eta64) * float(F32(inner))
+
+
+def big_brain(kind, outcomes, top, value_0, returns, lev_factor, stop_grid, roll_grid, want_wealth=False):
+    """
+    coin_big_brain_lev (lev/lev_exp.py:270-452) / dice_big_brain_lev (:741-932):
+    data [R,S,26,H-1] fp32 - rows 0..11 wealth statistics after the step, 12..23
+    leverage statistics before it, 24 stop-loss, 25 retention ratio.
+
+    kind "coin": outcomes {0,1}, returns (up, down); the whole chain is fp32
+        g = fl32(return); V <- V * (1 + lev * g); lev <- opt(V).
+    kind "dice": outcomes {0,1,2}, returns (up, down, mid); the reference casts the
+        outcomes to float64 (:791) so returns and the WEALTH CHAIN are float64; with
+        retention 0 the leverage is float64 too (:727-728), otherwise it is computed
+        in fp32 from the fp32-rounded wealth (:731-738) and promoted in the update.
+    lev_factor: the float64 value of the scripts' LEV_FACTOR tensor.
     """
     oc = np.asarray(outcomes)
     n, h = oc.shape
     stop_grid = np.asarray(stop_grid, dtype=F32)
     roll_grid = np.asarray(roll_grid, dtype=F32)
     v0 = F32(value_0)
-    eta = F32(lev_factor)
-    ret = np.where(oc == 1, F32(up_r), F32(down_r)).astype(F32)
-    one = F32(1)
-    data = np.zeros((len(roll_grid), len(stop_grid), 26, h - 1), dtype=F32)
+    eta64, eta32 = float(lev_factor), F32(lev_factor)
+    if kind == "coin":
+        ret = np.where(oc == 1, F32(returns[0]), F32(returns[1])).astype(F32)
+    else:
+        ret = np.where(oc == 0, float(returns[0]), np.where(oc == 1, float(returns[1]), float(returns[2])))
+    data = np.zeros((len(roll_grid), len(stop_grid), 26, max(h - 1, 0)), dtype=F32)
+    wealth = np.zeros((len(roll_grid), len(stop_grid), n), dtype=np.float64)
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         for j, roll in enumerate(roll_grid):
             for i, stop in enumerate(stop_grid):
                 vmin = F32(stop * v0)
-                lev0 = optimal_lev(np.asarray(v0, dtype=F32), v0, vmin, eta, roll)
-                v = (v0 * (one + lev0 * ret[:, 0])).astype(F32)
-                lev = optimal_lev(v, v0, vmin, eta, roll).astype(F32)
+                lev0 = _initial_lev_f64(v0, vmin, eta64)
+                if kind == "coin":
+                    v = (v0 * (F32(1) + F32(lev0) * ret[:, 0])).astype(F32)
+                    lev = _opt_lev_f32(v, v0, vmin, eta32, roll)
+                else:
+                    v = float(v0) * (1.0 + lev0 * ret[:, 0])
+                    lev = (eta64 * (1.0 - float(vmin) / v)) if roll == 0 else \
+                        _opt_lev_f32(v.astype(F32), v0, vmin, eta32, roll)
                 for t in range(h - 1):
                     data[j, i, 12:24, t] = summary_stats(lev, top).astype(F32)
                     data[j, i, 24, t] = stop
                     data[j, i, 25, t] = roll
-                    v = (v * (one + lev * ret[:, t + 1])).astype(F32)
-                    lev = optimal_lev(v, v0, vmin, eta, roll).astype(F32)
+                    if kind == "coin":
+                        v = (v * (F32(1) + lev * ret[:, t + 1])).astype(F32)
+                        lev = _opt_lev_f32(v, v0, vmin, eta32, roll)
+                    else:
+                        v = v * (1.0 + lev.astype(np.float64) * ret[:, t + 1])
+                        lev = (eta64 * (1.0 - float(vmin) / v)) if roll == 0 else \
+                            _opt_lev_f32(v.astype(F32), v0, vmin, eta32, roll)
                     data[j, i, 0:12, t] = summary_stats(v, top).astype(F32)
-    return data
+                wealth[j, i] = v
+    return (data, wealth) if want_wealth else data
 
 
 def galaxy_brain(ru_grid, rd_grid, pu_grid) -> np.ndarray:

@@ -88,6 +88,24 @@ class ReplayDesc(C.Structure):
     ]
 
 
+BB_COIN, BB_DICE, BB_MAX_POINTS = 0, 1, 128
+
+
+class BigBrainDesc(C.Structure):
+    _fields_ = [
+        ("n_investors", C.c_int64),
+        ("ld_outcomes", C.c_int64),
+        ("horizon", C.c_int32),
+        ("n_points", C.c_int32),
+        ("kind", C.c_int32),
+        ("reserved", C.c_int32),
+        ("value_0", C.c_float),
+        ("lev_factor32", C.c_float),
+        ("lev_factor64", C.c_double),
+        ("returns", C.c_double * 3),
+    ]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"rlmd_b200 error {code}: {msg}")
@@ -119,6 +137,8 @@ _SIGNATURES = {
                                          C.c_double, C.POINTER(C.c_double), _i32, _i64, C.c_double, _vp]),
     "b200_replay_sample": (C.c_int, [C.POINTER(ReplayDesc), _vp, _i64, _i32, _i64, _i32, C.POINTER(C.c_float), _i32,
                                      C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_bigbrain_chunk": (C.c_int, [C.POINTER(BigBrainDesc), _vp, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_double), _i32, _i32, _vp, _vp, _vp]),
     "b200_growth_workspace_bytes": (_i64, [_i64]),
     "b200_growth_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),
     "b200_growth_summary": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, C.c_double, _i32, C.POINTER(C.c_double),

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import LevDesc, check, lib, ptr, require_cuda, stream_ptr
+from ._lib import BigBrainDesc, LevDesc, check, lib, ptr, require_cuda, stream_ptr
 
 STAT_NAMES = (
     "mean", "mean_top", "mean_adj", "mad", "mad_top", "mad_adj",
@@ -407,3 +407,95 @@ def growth_summary(log_w: torch.Tensor, horizon: int, value_0: float, *, data_T:
 
             sharding.exchange_phases(run_phase, ws, group, what="growth", n_phases=7)
     return out
+
+
+# ---------------------------------------------------------------- big brain
+def bigbrain_series(kind: str, outcomes: torch.Tensor, top: int, value_0: float, returns_by_code: Sequence[float],
+                    lev_factor: float, stop_grid, roll_grid, *, chunk_bytes: int = 2 << 30, rows_cap: int = 2048,
+                    chunk_steps: Optional[int] = None, n_total: Optional[int] = None, group=None):
+    """
+    State-dependent leverage over a retention x stop-loss grid (the *_big_brain_lev
+    contract): data [R,S,26,H-1] fp32 on the GPU (rows 0..11 wealth statistics after
+    each step, 12..23 leverage statistics before it, 24 stop-loss, 25 retention) and
+    the final wealth [R,S,N] (fp32 for "coin", fp64 for "dice").
+
+    outcomes: CUDA uint8 codes [N,H] (coin: 1 up / 0 down; dice: 0 up, 1 down, 2 mid);
+    returns_by_code: the return of code 0,1,2; lev_factor: the float64 value of the
+    scripts' LEV_FACTOR; grids: fp32 values as the reference's tensors hold them.
+    The grid is walked in point tiles and the horizon in chunks: b200_bigbrain_chunk
+    dumps leverage / wealth per step, b200_rowstats reduces every dumped row.
+    """
+    require_cuda()
+    if not outcomes.is_cuda or outcomes.dtype != torch.uint8 or outcomes.dim() != 2 or outcomes.stride(1) != 1:
+        raise ValueError("outcomes must be a [N,H] uint8 CUDA tensor with unit inner stride (engine.encode_codes)")
+    n, h = outcomes.shape
+    dev = outcomes.device
+    stop = np.asarray(stop_grid, dtype=np.float32).reshape(-1)
+    roll = np.asarray(roll_grid, dtype=np.float32).reshape(-1)
+    R, S = len(roll), len(stop)
+    P = R * S
+    v0 = np.float32(value_0)
+    eta64 = float(lev_factor)
+    # point p = j * S + i  (retention j outer, stop-loss i inner; lev/lev_exp.py:314-318)
+    vmin = np.tile((stop * v0).astype(np.float32), R)
+    rollp = np.repeat(roll, S).astype(np.float32)
+    inner = (np.float32(1) - (vmin / v0).astype(np.float32)).astype(np.float32)
+    lev0 = eta64 * inner.astype(np.float64)          # 0-dim float64 arithmetic of step 0 (:327)
+    d = BigBrainDesc()
+    d.n_investors, d.horizon = n, h
+    d.ld_outcomes = outcomes.stride(0) if n > 1 else max(outcomes.stride(0), h)
+    d.kind = {"coin": _lib.BB_COIN, "dice": _lib.BB_DICE}[kind]
+    d.value_0, d.lev_factor32, d.lev_factor64 = float(v0), float(np.float32(eta64)), eta64
+    rb = list(returns_by_code) + [0.0] * (3 - len(returns_by_code))
+    for k in range(3):
+        d.returns[k] = float(rb[k])
+    sdt = torch.float32 if kind == "coin" else torch.float64
+    n_total = n if n_total is None else int(n_total)
+
+    n_ref = max(n, 1)
+    if group is not None:
+        import torch.distributed as dist
+
+        t = torch.tensor([n_ref], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        n_ref = int(t.item())
+    ptile = min(P, 32, _lib.BB_MAX_POINTS)
+    while True:
+        tc = min(max(h - 1, 1), rows_cap // (2 * ptile), chunk_bytes // (8 * n_ref * ptile))
+        if tc >= 16 or ptile == 1:
+            break
+        ptile = max(1, ptile // 2)
+    tc = max(1, tc if chunk_steps is None else min(tc, int(chunk_steps)))
+
+    with torch.cuda.device(dev):
+        data = torch.zeros((P, 26, max(h - 1, 0)), dtype=torch.float32, device=dev)
+        wealth = torch.empty((P, n), dtype=sdt, device=dev)
+        if h > 1:
+            data[:, 24, :] = torch.as_tensor(np.tile(stop, R), device=dev)[:, None]
+            data[:, 25, :] = torch.as_tensor(rollp, device=dev)[:, None]
+        dump_buf = torch.empty((ptile * tc * 2 * max(n, 1),), dtype=torch.float32, device=dev)
+        ws = rowstats_workspace(ptile * tc * 2, dev)
+        fptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        for p0 in range(0, P, ptile):
+            pc = min(ptile, P - p0)
+            d.n_points = pc
+            vm, rl, l0 = (np.ascontiguousarray(vmin[p0:p0 + pc]), np.ascontiguousarray(rollp[p0:p0 + pc]),
+                          np.ascontiguousarray(lev0[p0:p0 + pc]))
+            state = torch.empty((2, pc, max(n, 1)), dtype=sdt, device=dev)[:, :, :n].contiguous()
+            s = 0
+            while s < h:
+                s_end = min(h, max(s, 1) + tc)
+                s_lo = max(s, 1)
+                steps = s_end - s_lo
+                dump = dump_buf[: pc * steps * 2 * n].view(pc * steps * 2, n) if steps > 0 else None
+                check(lib.b200_bigbrain_chunk(C.byref(d), ptr(outcomes), fptr(vm), fptr(rl),
+                                              l0.ctypes.data_as(C.POINTER(C.c_double)), s, s_end, ptr(state),
+                                              ptr(dump), stream_ptr()))
+                if steps > 0 and n > 0:
+                    st = rowstats(dump, top, n_total=n_total, group=group, workspace=ws[: pc * steps * 2])
+                    st = st.view(pc, steps, 2, 12).to(torch.float32)
+                    data[p0:p0 + pc, 12:24, s_lo - 1:s_end - 1] = st[:, :, 0, :].permute(0, 2, 1)
+                    data[p0:p0 + pc, 0:12, s_lo - 1:s_end - 1] = st[:, :, 1, :].permute(0, 2, 1)
+                s = s_end
+            wealth[p0:p0 + pc] = state[0]
+    return data.view(R, S, 26, max(h - 1, 0)), wealth.view(R, S, n)

@@ -225,3 +225,95 @@ def gbm_smart_lev(device, outcomes, investors, horizon, top, value_0, lev_low, l
     data, data_T = _series("gbm", _returns(outcomes), lev, lev, investors, horizon, top, value_0)
     _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
     return data, data_T
+
+
+# ------------------------------------------------- state-dependent leverage
+def coin_optimal_lev(value_t, value_0, value_min, lev_factor, roll):
+    """lev/lev_exp.py:240-267 - element-wise helper, kept as the same torch expression
+    (inside the sweeps the engine evaluates it in the CUDA chain, csrc/bigbrain.cu)."""
+    if roll == 0:
+        return lev_factor * (1 - T.maximum(value_min, value_min) / value_t)
+    rolling_loss = T.where(value_t <= value_0, value_min, value_0 + roll * (value_t - value_0))
+    return lev_factor * (1 - rolling_loss / value_t)
+
+
+def dice_optimal_lev(device, value_t, value_0, value_min, lev_factor, roll):
+    """lev/lev_exp.py:704-738 (the retention branch re-casts the wealth to fp32, :731)."""
+    if roll == 0:
+        return lev_factor * (1 - T.maximum(value_min, value_min) / value_t)
+    value_t = T.as_tensor(value_t).to(dtype=T.float, device=device)
+    rolling_loss = T.where(value_t <= value_0, value_min, value_0 + roll * (value_t - value_0))
+    return lev_factor * (1 - rolling_loss / value_t)
+
+
+_BB_FMT = """stop/roll {:1.0f}/{:1.0f}%:
+                    avg mean/med/mad/std:  $ {:1.2e} / {:1.2e} / {:1.1e} / {:1.1e}  l {:1.2f} / {:1.2f} / {:1.1f} / {:1.1f}
+                    top mean/med/mad/std:  $ {:1.2e} / {:1.2e} / {:1.1e} / {:1.1e}  l {:1.2f} / {:1.2f} / {:1.1f} / {:1.1f}
+                    adj mean/med/mad/std:  $ {:1.2e} / {:1.2e} / {:1.1e} / {:1.1e}  l {:1.2f} / {:1.2f} / {:1.1f} / {:1.1f}"""
+
+
+def _print_big_brain(data: T.Tensor) -> None:
+    """The per-grid-point report of lev/lev_exp.py:417-449 (statistics of the last step)."""
+    if data.shape[-1] == 0:
+        return
+    last = data[:, :, :, -1].cpu().numpy()
+    for j in range(last.shape[0]):
+        for i in range(last.shape[1]):
+            v, l = last[j, i, 0:12], last[j, i, 12:24]
+            args = [last[j, i, 24] * 100, last[j, i, 25] * 100]
+            for g in range(3):      # all / top / adj: mean, med, mad, std of wealth then of leverage
+                args += [v[0 + g], v[9 + g], v[3 + g], v[6 + g], l[0 + g], l[9 + g], l[3 + g], l[6 + g]]
+            print(_BB_FMT.format(*args))
+
+
+def _lev_factor64(lev_factor) -> float:
+    return float(lev_factor.item()) if isinstance(lev_factor, T.Tensor) else float(lev_factor)
+
+
+def _big_brain(kind, outcomes, investors, horizon, top, value_0, returns_by_code, lev_factor, stop, roll):
+    codes = _codes(outcomes)
+    n, h = codes.shape
+    if (investors is not None and _as_int(investors) != n) or (horizon is not None and _as_int(horizon) != h):
+        raise ValueError("investors/horizon do not match the shape of outcomes")
+    stop_grid = np.asarray(param_range(*stop), dtype=_F32)
+    roll_grid = np.asarray(param_range(*roll), dtype=_F32)
+    data, _ = engine.bigbrain_series(kind, codes, int(top), _as_float(value_0), returns_by_code,
+                                     _lev_factor64(lev_factor), stop_grid, roll_grid,
+                                     n_total=_n_total(n, codes.device), group=_GROUP)
+    _print_big_brain(data)
+    return data
+
+
+def coin_big_brain_lev(device, outcomes, investors, horizon, top, value_0, up_r, down_r, lev_factor, stop_min,
+                       stop_max, stop_incr, roll_min, roll_max, roll_incr):
+    """lev/lev_exp.py:270-452 -> data [R,S,26,H-1] fp32 on the GPU."""
+    return _big_brain("coin", outcomes, investors, horizon, top, value_0, (down_r, up_r), lev_factor,
+                      (stop_min, stop_max, stop_incr), (roll_min, roll_max, roll_incr))
+
+
+def dice_big_brain_lev(device, outcomes, investors, horizon, top, value_0, up_r, down_r, mid_r, lev_factor, stop_min,
+                       stop_max, stop_incr, roll_min, roll_max, roll_incr):
+    """lev/lev_exp.py:741-932 -> data [R,S,26,H-1] fp32 on the GPU."""
+    return _big_brain("dice", outcomes, investors, horizon, top, value_0, (up_r, down_r, mid_r), lev_factor,
+                      (stop_min, stop_max, stop_incr), (roll_min, roll_max, roll_incr))
+
+
+def coin_galaxy_brain_lev(device, ru_min, ru_max, ru_incr, rd_min, rd_max, rd_incr, pu_min, pu_max, pu_incr):
+    """
+    lev/lev_exp.py:455-505 - Kelly table [len(pu), len(ru), len(ru), 4] fp32 of
+    (pu, ru, rd, pu/rd - (1-pu)/ru).  Closed form on the host in Python-double
+    arithmetic like the reference's triple loop (no kernel: 1e6 divisions); the
+    table is allocated with len(ru) twice, as the reference does (:486).
+    """
+    ru = np.asarray(param_range(ru_min, ru_max, ru_incr), dtype=np.float64)
+    rd = np.asarray(param_range(rd_min, rd_max, rd_incr), dtype=np.float64)
+    pu = np.asarray(param_range(pu_min, pu_max, pu_incr), dtype=np.float64)
+    if len(rd) > len(ru):
+        raise IndexError("the reference's table holds len(ru_range) down-returns (lev/lev_exp.py:486)")
+    table = np.zeros((len(pu), len(ru), len(ru), 4), dtype=np.float32)
+    k = len(rd)
+    table[:, :, :k, 0] = pu[:, None, None]
+    table[:, :, :k, 1] = ru[None, :, None]
+    table[:, :, :k, 2] = rd[None, None, :]
+    table[:, :, :k, 3] = pu[:, None, None] / rd[None, None, :] - (1 - pu[:, None, None]) / ru[None, :, None]
+    return T.as_tensor(table, device=device)

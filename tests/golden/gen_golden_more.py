@@ -120,3 +120,45 @@ def gen_replay():
         path = os.path.join(HERE, f"replay_{case['name']}.npz")
         np.savez_compressed(path, **out)
         print("wrote", path, "events:", ev, "episodes:", int(st["done"].sum()))
+
+
+def gen_bigbrain():
+    """coin_big_brain_lev / dice_big_brain_lev of the unmodified reference on seeded outcomes."""
+    import torch
+
+    lev = ref_shim.load("lev.lev_exp")
+    dev = torch.device("cpu")
+    for case in golden_io.BIGBRAIN_CASES:
+        oc = golden_io.draw_outcomes(case)
+        n, h = case["n"], case["h"]
+        up, dn = case["up_r"], case["down_r"]
+        # lev/coin_flip.py:139-152 verbatim in meaning
+        value_0 = torch.tensor(case["v0"], device=dev)
+        investors = torch.tensor(int(n), dtype=torch.int32, device=dev)
+        horizon = torch.tensor(int(h), dtype=torch.int32, device=dev)
+        asym = torch.tensor(1e-12, device=dev)
+        bigger = np.abs(dn) if np.abs(up) >= np.abs(dn) else -np.abs(up)
+        lev_factor = torch.tensor(1 / bigger, device=dev)
+        lev_factor = lev_factor - asym if np.abs(up) > np.abs(dn) else lev_factor + asym
+        assert float(lev_factor) == golden_io.bigbrain_lev_factor(case) and lev_factor.dtype == torch.float64
+        with ref_shim.quiet() as buf:
+            if case["kind"] == "coin":
+                data = lev.coin_big_brain_lev(dev, torch.tensor(oc.astype(np.float32)), investors, horizon,
+                                              case["top"], value_0, up, dn, lev_factor, *case["stop"], *case["roll"])
+            else:
+                data = lev.dice_big_brain_lev(dev, torch.tensor(oc.astype(np.int64)), investors, horizon,
+                                              case["top"], value_0, up, dn, case["mid_r"], lev_factor,
+                                              *case["stop"], *case["roll"])
+        data = data.numpy()
+        cols = golden_io.kept_columns(case)
+        out = os.path.join(HERE, f"bigbrain_{case['name']}.npz")
+        np.savez_compressed(out, data=data[:, :, :, cols], cols=np.asarray(cols, dtype=np.int64),
+                            text=np.array(buf.getvalue()))
+        print("wrote", out, data.shape, os.path.getsize(out) // 1024, "KiB")
+
+    # Kelly table (coin_galaxy_brain_lev, lev/lev_exp.py:455-505) on a reduced grid
+    with ref_shim.quiet():
+        table = lev.coin_galaxy_brain_lev(dev, *golden_io.GALAXY_GRID)
+    out = os.path.join(HERE, "galaxy_brain.npz")
+    np.savez_compressed(out, data=table.numpy())
+    print("wrote", out, tuple(table.shape))

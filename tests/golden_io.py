@@ -206,3 +206,46 @@ def replay_inputs_dict(case: dict) -> dict:
         "discount": case["gamma"], "multi_steps": case["n"], "r_abs_zero": case["r0"], "dynamics": case["dyna"],
         "buffer": case["mem"], "n_cumsteps": case["mem"] + 100,
     }
+
+
+# ------------------------------------------------------------------ big brain
+# coin_big_brain_lev / dice_big_brain_lev (lev/lev_exp.py:270-452, 741-932): stop-loss
+# x retention grids (low, high, incr) as the scripts pass them; lev_factor is built
+# the way lev/coin_flip.py:146-152 / lev/dice_roll.py:133-139 build it.
+BIGBRAIN_CASES = [
+    # the reference's own smoke-test scale and grids (tests/test_script_lev.py:61-66,102-106)
+    dict(name="coin_inv2_testscale", kind="coin", n=10000, h=300, top=1, v0=1e2, seed=430, up_r=0.5, down_r=-0.4,
+         p=(0.5,), stop=(0.10, 0.10, 0.10), roll=(0.00, 0.00, 0.10), stride=23),
+    dict(name="coin_inv3_testscale", kind="coin", n=10000, h=300, top=1, v0=1e2, seed=431, up_r=0.5, down_r=-0.4,
+         p=(0.5,), stop=(0.70, 0.80, 0.10), roll=(0.70, 0.80, 0.10), stride=23),
+    dict(name="dice_inv2_testscale", kind="dice", n=10000, h=300, top=1, v0=1e2, seed=432, up_r=0.5, down_r=-0.5,
+         mid_r=0.05, p=(1 / 6, 1 / 6), stop=(0.10, 0.10, 0.10), roll=(0.00, 0.00, 0.10), stride=23),
+    dict(name="dice_inv3_testscale", kind="dice", n=10000, h=300, top=1, v0=1e2, seed=433, up_r=0.5, down_r=-0.5,
+         mid_r=0.05, p=(1 / 6, 1 / 6), stop=(0.70, 0.80, 0.10), roll=(0.70, 0.80, 0.10), stride=23),
+    # top-K > 1, ragged sizes, mixed grids (retention 0 and > 0 in one call)
+    dict(name="coin_grid_top4", kind="coin", n=1237, h=45, top=4, v0=1e2, seed=434, up_r=0.5, down_r=-0.4,
+         p=(0.5,), stop=(0.05, 0.95, 0.30), roll=(0.00, 0.90, 0.45), stride=1),
+    dict(name="dice_grid_top3", kind="dice", n=1111, h=37, top=3, v0=1e2, seed=435, up_r=0.5, down_r=-0.5,
+         mid_r=0.05, p=(1 / 6, 1 / 6), stop=(0.10, 0.90, 0.40), roll=(0.00, 0.90, 0.45), stride=1),
+    # the down move is the bigger payoff: lev_factor < 0 branch of the scripts
+    dict(name="coin_down_heavy", kind="coin", n=640, h=30, top=2, v0=1e2, seed=436, up_r=0.3, down_r=-0.5,
+         p=(0.6,), stop=(0.20, 0.60, 0.20), roll=(0.50, 0.50, 0.10), stride=1),
+]
+
+
+def bigbrain_case(name: str) -> dict:
+    for c in BIGBRAIN_CASES:
+        if c["name"] == name:
+            return c
+    raise KeyError(name)
+
+
+def bigbrain_lev_factor(case: dict):
+    """float64 value of the scripts' LEV_FACTOR (a float64 0-dim tensor there)."""
+    up, dn = case["up_r"], case["down_r"]
+    bigger = np.abs(dn) if np.abs(up) >= np.abs(dn) else -np.abs(up)
+    asym = float(np.float32(1e-12))          # T.tensor(1e-12) is fp32
+    return float(1 / bigger) - asym if np.abs(up) > np.abs(dn) else float(1 / bigger) + asym
+
+
+GALAXY_GRID = (0.2, 0.8, 0.05, 0.2, 0.8, 0.05, 0.25, 0.75, 0.25)   # ru, rd, pu (low, high, incr)
