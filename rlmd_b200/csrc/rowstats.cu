@@ -106,9 +106,7 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
   double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
   long long c0 = 0, c1 = 0;
 
-  const int64_t stride = (int64_t)gridDim.x * RS_THREADS;
-  for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
-    const float x = __ldg(v + i);
+  auto process = [&](const float x) {
     const uint32_t k = float_key(x);
     if (PASS == 0) {
       a0 += (double)x;
@@ -134,6 +132,32 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
     } else {
       if (k > thr_key) { const double d = (double)x - mean_t; a0 += fabs(d); a1 += d * d; }
       else if (k < thr_key) { const double d = (double)x - mean_j; a2 += fabs(d); a3 += d * d; }
+    }
+  };
+
+  // RS_ITEMS elements per thread per tile, loaded as independent 16-byte vectors
+  // before any of them is consumed (memory-level parallelism: the passes are
+  // HBM streams); rows whose base is not 16-byte aligned take scalar loads.
+  constexpr int64_t TILE = (int64_t)RS_THREADS * RS_ITEMS;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+  for (int64_t base = (int64_t)blockIdx.x * TILE; base < n; base += (int64_t)gridDim.x * TILE) {
+    if (vec_ok && base + TILE <= n) {
+      const float4* __restrict__ v4 = reinterpret_cast<const float4*>(v + base);
+      float4 t[RS_ITEMS / 4];
+#pragma unroll
+      for (int u = 0; u < RS_ITEMS / 4; ++u) t[u] = __ldcs(v4 + u * RS_THREADS + threadIdx.x);
+#pragma unroll
+      for (int u = 0; u < RS_ITEMS / 4; ++u) { process(t[u].x); process(t[u].y); process(t[u].z); process(t[u].w); }
+    } else {
+      float t[RS_ITEMS];
+#pragma unroll
+      for (int u = 0; u < RS_ITEMS; ++u) {
+        const int64_t i = base + (int64_t)u * RS_THREADS + threadIdx.x;
+        t[u] = i < n ? __ldcs(v + i) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < RS_ITEMS; ++u)
+        if (base + (int64_t)u * RS_THREADS + threadIdx.x < n) process(t[u]);
     }
   }
 

@@ -106,6 +106,82 @@ def main():
         print(json.dumps(dict(kernel="gbm_philox_G10", n=npx, h=h, best_s=b, median_s=m,
                               investor_steps_per_s=npx * h / b)), flush=True)
 
+    if a.only in ("", "series"):
+        # *_smart_lev: chain + per-step dump + 12 statistics per (leverage, step); H reduced to keep it short
+        hs = min(h, 512)
+        f = lev_exp.dice_factor_table(lev10, 0.5, -0.5, 0.05)
+        oc = engine.lev_draw("discrete", n, hs, seed=420, probs=(1 / 6, 1 / 6, 2 / 3))
+        b, m = timeit(lambda: engine.lev_series("discrete", f, lev10, 100.0, max(1, n // 10000), outcomes=oc),
+                      warm=1, reps=3)
+        ps = n * hs * 10
+        print(json.dumps(dict(kernel="series_dice_G10", n=n, h=hs, best_s=b, median_s=m,
+                              investor_steps_per_s=n * hs / b, path_steps_per_s=ps / b,
+                              bytes_per_path_step=24, GBps_dump_plus_5pass=ps * 24 / b / 1e9,
+                              hbm_frac=ps * 24 / b / 1e9 / hbm)), flush=True)
+        del oc
+    if a.only in ("", "bigbrain"):
+        hs = min(h, 256)
+        oc = engine.lev_draw("discrete", n, hs, seed=5, probs=(0.5, 0.5))
+        stop = np.asarray(lev_exp.param_range(0.05, 0.95, 0.05), np.float32)
+        roll = np.asarray(lev_exp.param_range(0.70, 0.95, 0.05), np.float32)
+        for kind, rets in (("coin", (-0.4, 0.5)), ("dice", (0.5, -0.5, 0.05))):
+            b, m = timeit(lambda: engine.bigbrain_series(kind, oc, max(1, n // 10000), 100.0, rets, 2.5, stop[:4],
+                                                         roll[:2]), warm=1, reps=2)
+            ps = n * hs * 8
+            print(json.dumps(dict(kernel=f"bigbrain_{kind}_P8", n=n, h=hs, best_s=b, median_s=m,
+                                  path_steps_per_s=ps / b, bytes_per_path_step=48,
+                                  hbm_frac=ps * 48 / b / 1e9 / hbm)), flush=True)
+        del oc
+    if a.only in ("", "env"):
+        from rlmd_b200 import envs
+        for e in (1, 100, 100_000, 10_000_000):
+            env = envs.Coin_InvA(1, n_envs=e) if e > 1 else envs.Coin_InvA(1)
+            env.reset()
+            if e > 1:
+                act = torch.rand((e, 1), dtype=torch.float64, device="cuda") * 1.98 - 0.99
+                fn = lambda: env.step(act)
+            else:
+                fn = lambda: env.step(np.array([0.3]))
+            b, m = timeit(fn, warm=3, reps=20)
+            print(json.dumps(dict(kernel="menv_step_coin_A1", n_envs=e, best_s=b, median_s=m, env_steps_per_s=e / b,
+                                  algorithmic_GBps=e * 130 / b / 1e9, hbm_frac=e * 130 / b / 1e9 / hbm)), flush=True)
+    if a.only in ("", "replay"):
+        from rlmd_b200.replay_torch import ReplayBufferTorch
+        mem = 1_000_000
+        rs = np.random.RandomState(0)
+        lens = rs.randint(5, 61, size=mem // 5)
+        done = np.zeros(mem, dtype=bool)
+        done[np.cumsum(lens)[np.cumsum(lens) < mem] - 1] = True
+        for nstep in (1, 5, 10):
+            for batch in (256, 512):
+                inputs = {"gpu": "cuda:0", "input_dims": (5,), "num_actions": 1, "mini_batch_size": batch,
+                          "discount": 0.99, "multi_steps": nstep, "r_abs_zero": None, "dynamics": "M", "buffer": mem,
+                          "n_cumsteps": mem}
+                buf = ReplayBufferTorch(inputs)
+                st = torch.randn((mem, 5), dtype=torch.float64, device="cuda")
+                t0 = timeit(lambda: None, warm=0, reps=1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                buf.store_batch(st, st[:, :1], 1 + 0.01 * st[:, 0], st, torch.as_tensor(done, device="cuda"))
+                e1.record()
+                e1.synchronize()
+                store_s = e0.elapsed_time(e1) * 1e-3
+                b1, m1 = timeit(lambda: buf.sample_exp(), warm=5, reps=50)
+                k = 1024
+                bk, mk = timeit(lambda: buf.sample_many(k), warm=2, reps=10)
+                bytes_per = 106 if nstep == 1 else 114 + 4 * (nstep - 1)
+                print(json.dumps(dict(kernel="replay", n_step=nstep, batch=batch, buffer=mem, store_1e6_s=store_s,
+                                      stores_per_s=mem / store_s, sample_call_us=b1 * 1e6, samples_per_s_one_call=batch / b1,
+                                      many_batches=k, samples_per_s_many=k * batch / bk,
+                                      algorithmic_GBps_many=k * batch * bytes_per / bk / 1e9,
+                                      hbm_frac_many=k * batch * bytes_per / bk / 1e9 / hbm)), flush=True)
+                del buf, st
+    if a.only in ("", "growth"):
+        lw = torch.randn((20, n), dtype=torch.float64, device="cuda")
+        b, m = timeit(lambda: engine.growth_summary(lw, h, 100.0, quantiles=(0.05, 0.5, 0.95)))
+        print(json.dumps(dict(kernel="growth_summary_20rows", n=n, best_s=b, median_s=m,
+                              GBps_6pass=6 * 20 * n * 8 / b / 1e9)), flush=True)
+
 
 if __name__ == "__main__":
     main()
