@@ -82,8 +82,10 @@ typedef struct b200_lev_desc {
   float log_mean;          /* GBM Philox: mean of x  (mu - sigma^2/2)        */
   float sigma;             /* GBM Philox: std of x                           */
   int32_t variant;         /* CHAIN kernel variant: 0 = library default,
-                              1 FSEL, 2 LDS table (both
-                              bit-identical; exposed for benchmarking)        */
+                              1 FSEL, 2 LDS table, 3 FMA-pipe selection (all
+                              bit-identical; exposed for benchmarking; 3 falls
+                              back when a factor is not reproducible by one
+                              fused multiply-add or K > 3)                    */
   uint32_t thresholds[B200_MAX_OUTCOMES]; /* discrete Philox: outcome =
                               #{k : draw >= thresholds[k]}, k < K-1, draw a
                               uniform uint32; thresholds ascending            */

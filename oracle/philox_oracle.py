@@ -62,21 +62,32 @@ def discrete_codes(seed, investor_ids, horizon, probs) -> np.ndarray:
     return code
 
 
+def box_muller_polar(a, b, sigma=1.0):
+    """
+    The engine's Box-Muller on two uint32 words (rlmd_b200/csrc/common.cuh):
+    u1 = fl32(fl32(a) 2^-32 + 2^-33), theta = fl32(int32(b)) pi 2^-31,
+    rho = sqrt(-2 ln2 sigma^2 log2(u1)); returns (rho cos theta, rho sin theta) in float64
+    (the device uses lg2/sqrt/sin/cos.approx: agreement to ~1e-6).
+    """
+    a32 = np.asarray(a, dtype=np.uint32).astype(np.float32).astype(np.float64)     # RN conversion
+    u1 = (a32 * 2.0 ** -32 + 2.0 ** -33).astype(np.float32).astype(np.float64)    # one rounding, like the FFMA
+    b32 = np.asarray(b, dtype=np.uint32).view(np.int32).astype(np.float32)
+    th = (b32 * np.float32(np.pi * 2.0 ** -31)).astype(np.float32).astype(np.float64)
+    s32 = np.float32(sigma)
+    scale2 = np.float64(np.float32(np.float32(np.float32(-1.3862943611198906) * s32) * s32))
+    rho = np.sqrt(np.maximum(np.log2(u1) * scale2, 0.0))
+    return rho * np.cos(th), rho * np.sin(th)
+
+
 def gbm_returns(seed, investor_ids, horizon, log_mean, sigma) -> np.ndarray:
     """
-    fp32 [N,H] (to ~1e-6: the device uses fast log/sin/cos intrinsics):
-    block words (a,b,c,d) -> Box-Muller pairs (a,b) -> z0,z1 and (c,d) -> z2,z3,
-    u1 = ((a >> 8) + 0.5) 2^-24, u2 = (b >> 8) 2^-24, r = sqrt(-2 ln u1),
-    z = r cos(2 pi u2), r sin(2 pi u2);  x = sigma z + log_mean.
+    fp32 [N,H] (to ~1e-6: the device uses the approx lg2/sqrt/sin/cos units):
+    block words (a,b,c,d) -> Box-Muller pairs (a,b) -> y0,y1 and (c,d) -> y2,y3 with
+    sigma folded into the radius;  x = y + log_mean.
     """
     nblk = (horizon + 3) // 4
     w = lev_words(seed, investor_ids, nblk * 4).reshape(len(investor_ids), nblk, 4)
-    u1a = ((w[..., 0] >> 8).astype(np.float64) + 0.5) * 2.0 ** -24
-    u2a = (w[..., 1] >> 8).astype(np.float64) * 2.0 ** -24
-    u1b = ((w[..., 2] >> 8).astype(np.float64) + 0.5) * 2.0 ** -24
-    u2b = (w[..., 3] >> 8).astype(np.float64) * 2.0 ** -24
-    ra, rb = np.sqrt(-2 * np.log(u1a)), np.sqrt(-2 * np.log(u1b))
-    z = np.stack([ra * np.cos(2 * np.pi * u2a), ra * np.sin(2 * np.pi * u2a),
-                  rb * np.cos(2 * np.pi * u2b), rb * np.sin(2 * np.pi * u2b)], axis=-1)
-    x = np.float64(np.float32(sigma)) * z + np.float64(np.float32(log_mean))
+    y0, y1 = box_muller_polar(w[..., 0], w[..., 1], sigma)
+    y2, y3 = box_muller_polar(w[..., 2], w[..., 3], sigma)
+    x = np.stack([y0, y1, y2, y3], axis=-1) + np.float64(np.float32(log_mean))
     return x.reshape(len(investor_ids), nblk * 4)[:, :horizon].astype(np.float32)

@@ -72,17 +72,30 @@ enum : uint32_t {
   PHILOX_TAG_REPLAY = 0x52504C00u // 'RPL'
 };
 
-// Box-Muller on two uniform words: u1 in (0,1], u2 in [0,1).
+// Box-Muller on two uniform words, 12 instructions per pair of normals (4 MUFU):
+//   u1    = fl32(fl32(a) * 2^-32 + 2^-33)        in (0, 1]   (one I2F, one FFMA)
+//   theta = fl32(int32(b)) * pi * 2^-31          in [-pi, pi] (one I2F, one FMUL)
+//   rho   = sqrt(scale2 * log2(u1)),  scale2 = -2 ln2 * sigma^2   (lg2/sqrt.approx)
+//   y0 = rho cos(theta), y1 = rho sin(theta)      ~ N(0, sigma^2)
+// oracle/philox_oracle.py:gbm_returns restates exactly this.
+__device__ __forceinline__ float box_muller_scale2(float sigma) { return -1.3862943611198906f * sigma * sigma; }
+__device__ __forceinline__ void box_muller_polar(uint32_t a, uint32_t b, float scale2, float& rho, float& c,
+                                                 float& s) {
+  const float u1 = __fmaf_rn(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  float l2;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  const float q = __fmul_rn(l2, scale2);
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rho) : "f"(q));
+  const float th = __fmul_rn(__int2float_rn((int32_t)b), 1.4629180792671596e-09f);  // pi * 2^-31
+  s = __sinf(th);
+  c = __cosf(th);
+}
+// Unit normals.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  const float two_m32 = 2.3283064365386963e-10f;  // 2^-32
-  float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 24 bits, never 0
-  float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;
-  (void)two_m32;
-  float r = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
+  float rho, c, s;
+  box_muller_polar(a, b, -1.3862943611198906f, rho, c, s);
+  z0 = rho * c;
+  z1 = rho * s;
 }
 
 // -------------------------------------------------------------- reductions

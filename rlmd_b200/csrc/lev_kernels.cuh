@@ -79,7 +79,27 @@ __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * TI
 //   V_FSEL : per g, (K-1) FSEL from constant-bank factors + 1 FMUL
 //   V_LDS  : factor rows m[code][*] fetched from a shared-memory table with
 //            LDS.128 (lanes that saw the same code share the fetch) + FMUL2
-enum { V_FSEL = 0, V_LDS = 1 };
+//   V_FMA  : (K <= 3) the code byte, moved to the top byte of a word, IS the
+//            float c in {0, 2^-125 (code 1), 2^-123 (code 2)}; the factor of the
+//            highest code is produced on the FMA pipe as fma(c, A_g, m[0][g])
+//            with A_g (row 3 of the table) chosen on the host so that the single
+//            rounding lands exactly on m[K-1][g] (fma_deltas() verifies every
+//            entry bit for bit, else the launch falls back).  K = 3 patches
+//            code 1 in with one FSEL; K = 2 splits the grid tile between FSEL
+//            and FMA selection so that the ALU and FMA pipes fill together.
+//            FFMA2/FMUL2 halve the issue slots.
+enum { V_FSEL = 0, V_LDS = 1, V_FMA = 2 };
+
+// Selector word of one step: the code itself, or code << 24 for V_FMA.
+template <int V>
+__device__ __forceinline__ uint32_t sel_from_word(uint32_t wd, int b) {
+  return V == V_FMA ? __byte_perm(wd, 0u, (uint32_t)((b << 12) | 0x444)) : ((wd >> (8 * b)) & 0xffu);
+}
+template <int V>
+__device__ __forceinline__ uint32_t sel_from_code(uint32_t code) { return V == V_FMA ? code << 24 : code; }
+
+// K = 2: grid points [0, fma_nsel) are selected by FSEL, the rest by FFMA.
+__host__ __device__ constexpr int fma_nsel(int GT) { return ((GT * 11 / 20) + 1) & ~1; }
 
 template <int GT>
 struct GridTile {
@@ -108,6 +128,31 @@ __device__ __forceinline__ void chain_step(float (&w)[GT], const FactorTable& f,
         w[g + 2] = r.x; w[g + 3] = r.y;
       } else if (g + 2 < GT) {
         w[g + 2] = __fmul_rn(w[g + 2], m.z);
+      }
+    }
+  } else if (V == V_FMA) {
+    const float c = __uint_as_float(code);  // code << 24 read as a float
+    const bool hit = (K == 2) ? (code != 0u) : (code == 0x01000000u);
+    constexpr int NSEL = (K == 2) ? fma_nsel(GT) : 0;
+    float m[GT];
+#pragma unroll
+    for (int g = 0; g < GT; g += 2) {
+      if (g + 1 < GT) {
+        if (g >= NSEL) {
+          const float2 r = __ffma2_rn(make_float2(c, c), make_float2(f.m[3][g], f.m[3][g + 1]),
+                                      make_float2(f.m[0][g], f.m[0][g + 1]));
+          m[g] = r.x; m[g + 1] = r.y;
+        }
+        if (K == 3 || g < NSEL) {
+          m[g] = hit ? f.m[1][g] : (K == 2 ? f.m[0][g] : m[g]);
+          m[g + 1] = hit ? f.m[1][g + 1] : (K == 2 ? f.m[0][g + 1] : m[g + 1]);
+        }
+        const float2 r = __fmul2_rn(make_float2(w[g], w[g + 1]), make_float2(m[g], m[g + 1]));
+        w[g] = r.x; w[g + 1] = r.y;
+      } else {
+        float mm = __fmaf_rn(c, f.m[3][g], f.m[0][g]);
+        if (K == 3) mm = hit ? f.m[1][g] : mm;
+        w[g] = __fmul_rn(w[g], mm);
       }
     }
   } else {
@@ -162,7 +207,7 @@ template <int GT, int K, int V, bool USE_TMA, bool DUMP>
 __global__ void __launch_bounds__(TILE_ROWS)
 chain_discrete_stream_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ outcomes,
                              int64_t ld, const __grid_constant__ FactorTable f,
-                             const __grid_constant__ ChainParams p) {
+                             const __grid_constant__ ChainParams p, const int stages) {
   extern __shared__ __align__(1024) uint8_t tiles[];
   __shared__ __align__(8) uint64_t full[STAGES];
   __shared__ __align__(16) float tab[V == V_LDS ? K * GridTile<GT>::STRIDE : 4];
@@ -177,12 +222,12 @@ chain_discrete_stream_kernel(const __grid_constant__ CUtensorMap tmap, const uin
   if (V == V_LDS) fill_table<GT, K>(tab, f);
   if (USE_TMA) {
     if (tid == 0) {
-      for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+      for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
       fence_barrier_init();
     }
     __syncthreads();
     if (tid == 0) {
-      const int pre = ntiles < STAGES ? ntiles : STAGES;
+      const int pre = ntiles < stages ? ntiles : stages;
       for (int s = 0; s < pre; ++s) {
         mbar_expect_tx(&full[s], TILE_SMEM);
         tma_load_2d(tiles + s * TILE_SMEM, &tmap, &full[s], p.t_begin + s * TILE_BYTES, (int)row0);
@@ -196,12 +241,13 @@ chain_discrete_stream_kernel(const __grid_constant__ CUtensorMap tmap, const uin
 #pragma unroll
   for (int g = 0; g < GT; ++g) w[g] = (p.state_in != nullptr && live && g < p.G) ? p.state_in[(int64_t)g * p.ldT + row] : p.V0;
 
+  int s = 0;
+  uint32_t phase = 0;
   for (int kt = 0; kt < ntiles; ++kt) {
-    const int s = USE_TMA ? kt % STAGES : 0;
     uint8_t* tile = tiles + s * TILE_SMEM;
     const int t0 = p.t_begin + kt * TILE_BYTES;
     if (USE_TMA) {
-      mbar_wait(&full[s], (uint32_t)((kt / STAGES) & 1));
+      mbar_wait(&full[s], phase);
     } else {
       // cooperative copy: consecutive threads read consecutive bytes of a row
       __syncthreads();
@@ -224,7 +270,7 @@ chain_discrete_stream_kernel(const __grid_constant__ CUtensorMap tmap, const uin
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
-            chain_step<GT, K, V>(w, f, tab, (wd[j] >> (8 * b)) & 0xffu);
+            chain_step<GT, K, V>(w, f, tab, sel_from_word<V>(wd[j], b));
             if (DUMP && live) dump_step<GT, DUMP>(w, p, t0 + c * 16 + j * 4 + b, row);
           }
         }
@@ -233,16 +279,17 @@ chain_discrete_stream_kernel(const __grid_constant__ CUtensorMap tmap, const uin
 #pragma unroll 1
       for (int t = 0; t < steps; ++t) {
         const uint32_t code = tile[swz(tid, t >> 4) + (t & 15)];
-        chain_step<GT, K, V>(w, f, tab, code);
+        chain_step<GT, K, V>(w, f, tab, sel_from_code<V>(code));
         if (DUMP && live) dump_step<GT, DUMP>(w, p, t0 + t, row);
       }
     }
     if (USE_TMA) {
       __syncthreads();  // every thread is done with stage s
-      if (tid == 0 && kt + STAGES < ntiles) {
+      if (tid == 0 && kt + stages < ntiles) {
         mbar_expect_tx(&full[s], TILE_SMEM);
-        tma_load_2d(tile, &tmap, &full[s], p.t_begin + (kt + STAGES) * TILE_BYTES, (int)row0);
+        tma_load_2d(tile, &tmap, &full[s], p.t_begin + (kt + stages) * TILE_BYTES, (int)row0);
       }
+      if (++s == stages) { s = 0; phase ^= 1u; }
     }
   }
 
@@ -289,7 +336,7 @@ chain_discrete_philox_kernel(const __grid_constant__ FactorTable f, const __grid
     const uint32_t u[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      chain_step<GT, K, V>(w, f, tab, draw_code<K>(u[b], th));
+      chain_step<GT, K, V>(w, f, tab, sel_from_code<V>(draw_code<K>(u[b], th)));
       dump_step<GT, DUMP>(w, p, 4 * j + b, row);
     }
   }
@@ -297,7 +344,7 @@ chain_discrete_philox_kernel(const __grid_constant__ FactorTable f, const __grid
     const Philox4 r = philox4x32_10(c0, c1, (uint32_t)j1, PHILOX_TAG_LEV, k0, k1);
     const uint32_t u[4] = {r.x, r.y, r.z, r.w};
     for (int b = 0; b < (p.t_end & 3); ++b) {
-      chain_step<GT, K, V>(w, f, tab, draw_code<K>(u[b], th));
+      chain_step<GT, K, V>(w, f, tab, sel_from_code<V>(draw_code<K>(u[b], th)));
       dump_step<GT, DUMP>(w, p, 4 * j1 + b, row);
     }
   }
@@ -319,6 +366,9 @@ inline bool tma_ok(const void* base, int64_t ld_bytes, int64_t n_rows) {
   return ((uintptr_t)base % 16 == 0) && (ld_bytes % 16 == 0) && n_rows < ((int64_t)1 << 31);
 }
 
+// TMA ring depth of the chain kernels (1..STAGES); B200_CHAIN_STAGES overrides for tuning.
+int chain_stages();
+
 // One grid tile (<= 32 points) of a discrete CHAIN sweep; defined per K in
 // lev_chain_k{2,3,4}.cu so that the instantiations compile in parallel.
 struct ChainLaunch {
@@ -326,7 +376,7 @@ struct ChainLaunch {
   const uint8_t* outcomes;
   FactorTable f;
   ChainParams p;
-  int variant;  // 1 = V_FSEL, 2 = V_LDS (0 = default for this K)
+  int variant;  // 1 = V_FSEL, 2 = V_LDS, 3 = V_FMA (0 = default for this K)
   cudaStream_t st;
 };
 template <int K>
@@ -350,12 +400,15 @@ static int chain_launch_impl(const ChainLaunch& a) {
   if (tma_ok(a.outcomes, d.ld_outcomes, N)) {
     int rc = make_row_tile_map(&map, a.outcomes, N, d.horizon, d.ld_outcomes, 1);
     if (rc) return rc;
+    // The chain is issue-bound, not HBM-bound: a short ring leaves room for more
+    // resident blocks per SM (the warps hide the ALU latency of the dependent chain).
+    const int stages = chain_stages();
     auto kern = chain_discrete_stream_kernel<GT, K, V, true, DUMP>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * TILE_SMEM));
-    kern<<<blocks, TILE_ROWS, STAGES * TILE_SMEM, a.st>>>(map, a.outcomes, d.ld_outcomes, a.f, a.p);
+    kern<<<blocks, TILE_ROWS, stages * TILE_SMEM, a.st>>>(map, a.outcomes, d.ld_outcomes, a.f, a.p, stages);
   } else {
     chain_discrete_stream_kernel<GT, K, V_FSEL, false, DUMP><<<blocks, TILE_ROWS, TILE_SMEM, a.st>>>(
-        map, a.outcomes, d.ld_outcomes, a.f, a.p);
+        map, a.outcomes, d.ld_outcomes, a.f, a.p, 1);
   }
   return check_cuda(cudaGetLastError(), "chain_discrete_stream launch");
 }
@@ -369,14 +422,22 @@ static int chain_launch_gt(const ChainLaunch& a) {
   return chain_launch_impl<32, K, V, DUMP>(a);
 }
 
-// Default variant per K, from the B200 measurements in profiles/r01_kernels.md:
-// two outcomes -> FSEL (1 select per path-step keeps the ALU pipe under the FMA
-// pipe); three or four -> shared-memory table.
+// Default variant, from the B200 measurements in profiles/r01_kernels_*.jsonl
+// (investor-steps/s at G = 10, 1e6 x 1e4):  streamed dice FSEL 7.7e11, LDS 9.0e11,
+// FMA 1.28e12; streamed coin FSEL 1.58e12, LDS 9.0e11, FMA 1.68e12; Philox dice
+// FSEL 5.6e11, LDS 8.9e11, FMA 6.7e11 (the generator already loads the FMA and ALU
+// pipes, so the shared-memory table wins there).
 template <int K>
-static int chain_launch_all(const ChainLaunch& a) {
+static int chain_launch_all(const ChainLaunch& a0) {
+  ChainLaunch a = a0;
   int v = a.variant;
-  if (v == 0) v = (K == 2) ? 1 : 2;
+  const int fallback = (K == 2) ? 1 : 2;
+  if (v == 0) v = (K <= 3 && a.d->source != B200_SRC_PHILOX) ? 3 : fallback;
+  if (v == 3 && !fma_deltas(a.f, K, a.p.G)) v = fallback;
   const bool dump = a.p.dump != nullptr;
+  if constexpr (K <= 3) {
+    if (v == 3) return dump ? chain_launch_gt<K, V_FMA, true>(a) : chain_launch_gt<K, V_FMA, false>(a);
+  }
   if (v == 2) return dump ? chain_launch_gt<K, V_LDS, true>(a) : chain_launch_gt<K, V_LDS, false>(a);
   return dump ? chain_launch_gt<K, V_FSEL, true>(a) : chain_launch_gt<K, V_FSEL, false>(a);
 }

@@ -8,6 +8,8 @@
 //   reference dtype's overflow/underflow saturation), thread per investor over
 //   TMA-staged fp32 tiles, or Philox + Box-Muller draws in registers.
 // CHAIN mode kernels live in lev_kernels.cuh / lev_chain_k*.cu.
+#include <cstdlib>
+
 #include "lev_kernels.cuh"
 
 namespace b200 {
@@ -232,17 +234,19 @@ log_gbm_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
   if (row < N) gbm_finish(acc.S, acc.Smax, acc.Smin, G, lv, logV0, row, ldT, data_T, log_w);
 }
 
-// x_t = log_mean + sigma * z_t; four steps per Philox block, two Box-Muller pairs.
+// x_t = log_mean + sigma * z_t; four steps per Philox block, two Box-Muller pairs;
+// sigma is folded into the radius, the mean into the final FFMA.
 __device__ __forceinline__ void gbm_draw4(uint32_t c0, uint32_t c1, uint32_t j, uint32_t k0, uint32_t k1,
                                           float log_mean, float sigma, float (&x)[4]) {
   const Philox4 r = philox4x32_10(c0, c1, j, PHILOX_TAG_LEV, k0, k1);
-  float z0, z1, z2, z3;
-  box_muller(r.x, r.y, z0, z1);
-  box_muller(r.z, r.w, z2, z3);
-  x[0] = fmaf(sigma, z0, log_mean);
-  x[1] = fmaf(sigma, z1, log_mean);
-  x[2] = fmaf(sigma, z2, log_mean);
-  x[3] = fmaf(sigma, z3, log_mean);
+  const float scale2 = box_muller_scale2(sigma);
+  float rho, c, s;
+  box_muller_polar(r.x, r.y, scale2, rho, c, s);
+  x[0] = __fmaf_rn(rho, c, log_mean);
+  x[1] = __fmaf_rn(rho, s, log_mean);
+  box_muller_polar(r.z, r.w, scale2, rho, c, s);
+  x[2] = __fmaf_rn(rho, c, log_mean);
+  x[3] = __fmaf_rn(rho, s, log_mean);
 }
 
 __global__ void __launch_bounds__(128)
@@ -483,6 +487,15 @@ static int run_log_gbm(const b200_lev_desc& d, const float* x, const float* lev_
   return check_cuda(cudaGetLastError(), "log_gbm_stream launch");
 }
 
+int chain_stages() {
+  static int v = [] {
+    const char* e = getenv("B200_CHAIN_STAGES");
+    int x = e ? atoi(e) : 2;
+    return x < 1 ? 1 : x > STAGES ? STAGES : x;
+  }();
+  return v;
+}
+
 static int validate(const b200_lev_desc* d) {
   B200_REQUIRE(d != nullptr, "lev: desc is NULL");
   B200_REQUIRE(d->n_investors >= 0 && d->n_investors < ((int64_t)1 << 40), "lev: n_investors out of range");
@@ -491,7 +504,7 @@ static int validate(const b200_lev_desc* d) {
   B200_REQUIRE(d->n_grid >= 1 && d->n_grid <= B200_MAX_GRID, "lev: n_grid must be in 1..%d", B200_MAX_GRID);
   B200_REQUIRE(d->kind == B200_LEV_DISCRETE || d->kind == B200_LEV_GBM, "lev: unknown kind %d", d->kind);
   B200_REQUIRE(d->source == B200_SRC_STREAM || d->source == B200_SRC_PHILOX, "lev: unknown source %d", d->source);
-  B200_REQUIRE(d->variant >= 0 && d->variant <= 2, "lev: variant must be 0 (auto), 1 (FSEL) or 2 (LDS)");
+  B200_REQUIRE(d->variant >= 0 && d->variant <= 3, "lev: variant must be 0 (auto), 1 (FSEL), 2 (LDS) or 3 (FMA)");
   if (d->kind == B200_LEV_DISCRETE) {
     B200_REQUIRE(d->n_outcomes >= 2 && d->n_outcomes <= B200_MAX_OUTCOMES, "lev: n_outcomes must be in 2..%d",
                  B200_MAX_OUTCOMES);

@@ -28,7 +28,7 @@ def eng():
     return engine
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("case", DISCRETE, ids=lambda c: c["name"])
 def test_chain_data_T_bit_exact_vs_reference(eng, case, variant):
     oc, f, lev, _ = oracle_inputs(case)
@@ -166,6 +166,47 @@ def test_grid_larger_than_one_tile(eng):
     f = (1 + rs.uniform(-0.4, 0.5, size=(45, 3))).astype(np.float32)
     got = eng.lev_sweep("discrete", f, 100.0, outcomes=eng.encode_codes(oc), mode="chain")["data_T"]
     assert np.array_equal(bits(got.cpu().numpy()), bits(lo.chain_discrete(oc, f, 100.0)))
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+@pytest.mark.parametrize("g", [1, 4, 7, 10, 20, 32, 33])
+def test_chain_variants_agree_bit_for_bit_on_random_tables(eng, g, k):
+    """FSEL, shared-memory and FMA selection are the same fp32 chain (variant 3 falls back for K = 4)."""
+    rs = np.random.RandomState(100 * g + k)
+    n, h = 777, 261                                   # ragged: partial row tile, partial step tile
+    oc = rs.randint(0, k, size=(n, h)).astype(np.uint8)
+    f = (1 + rs.uniform(-0.95, 1.5, size=(g, k))).astype(np.float32)
+    want = lo.chain_discrete(oc, f, 100.0)
+    codes = eng.encode_codes(oc)
+    for v in (1, 2, 3):
+        got = eng.lev_sweep("discrete", f, 100.0, outcomes=codes, mode="chain", variant=v)["data_T"]
+        assert np.array_equal(bits(got.cpu().numpy()), bits(want)), (g, k, v)
+
+
+def test_fma_variant_falls_back_when_a_delta_is_not_reproducible(eng):
+    """
+    Tables on which a single fused multiply-add cannot land on the factor (huge
+    spread, zero, overflowing scaled delta, inf) still give the exact chain.
+    """
+    rs = np.random.RandomState(9)
+    oc = rs.randint(0, 3, size=(300, 40)).astype(np.uint8)
+    codes = eng.encode_codes(oc)
+    tables = [
+        np.float32([[1e-8, 0.5, 3.0], [0.0, 1.0, 2.0], [1.5, 0.0, 0.0]]),
+        np.float32([[1.0, 0.5, 40.0], [1.0, 2.0, 3.0], [0.25, 0.5, 0.75]]),      # delta 39 * 2^123 overflows
+        np.float32([[1.0, 0.5, np.inf], [1.0, 2.0, 3.0], [0.25, 0.5, 0.75]]),
+        np.float32([[3.0000002, 0.5, 1e-8 + 1e-15], [1.0, 2.0, 3.0], [0.25, 0.5, 0.75]]),
+    ]
+    for f in tables:
+        with np.errstate(all="ignore"):
+            want = lo.chain_discrete(oc, f, 1.0)
+        got = eng.lev_sweep("discrete", f, 1.0, outcomes=codes, mode="chain", variant=3)["data_T"]
+        assert np.array_equal(bits(got.cpu().numpy()), bits(want))
+    f2 = np.float32([[1.0, 40.0], [0.5, 0.7]])
+    oc2 = (oc & 1).astype(np.uint8)
+    got = eng.lev_sweep("discrete", f2, 1.0, outcomes=eng.encode_codes(oc2), mode="chain", variant=3)["data_T"]
+    with np.errstate(all="ignore"):
+        assert np.array_equal(bits(got.cpu().numpy()), bits(lo.chain_discrete(oc2, f2, 1.0)))
 
 
 def test_empty_and_invalid_inputs(eng):

@@ -60,13 +60,13 @@ def main():
     if a.only in ("", "chain"):
         for g, lev, out in ((10, lev10, out10), (20, lev20, out20)):
             f = lev_exp.dice_factor_table(lev, 0.5, -0.5, 0.05)
-            for v in (1, 2):
+            for v in (1, 2, 3):
                 b, m = timeit(lambda: engine.lev_sweep("discrete", f, 100.0, outcomes=dice, mode="chain",
                                                         variant=v, out_data_T=out))
                 emit(f"chain_dice_G{g}_v{v}", b, m, steps, 1, G=g, path_steps_per_s=steps * g / b)
         coin = engine.lev_draw("discrete", n, h, seed=421, probs=(0.5, 0.5))
         f = lev_exp.coin_factor_table(lev10, 0.5, -0.4)
-        for v in (1, 2):
+        for v in (1, 2, 3):
             b, m = timeit(lambda: engine.lev_sweep("discrete", f, 100.0, outcomes=coin, mode="chain", variant=v,
                                                     out_data_T=out10))
             emit(f"chain_coin_G10_v{v}", b, m, steps, 1, G=10, path_steps_per_s=steps * 10 / b)
@@ -81,7 +81,7 @@ def main():
                               GBps_5pass=5 * 10 * n * 4 / b / 1e9)), flush=True)
     if a.only in ("", "philox"):
         f = lev_exp.dice_factor_table(lev10, 0.5, -0.5, 0.05)
-        for v in (1, 2):
+        for v in (1, 2, 3):
             b, m = timeit(lambda: engine.lev_sweep("discrete", f, 100.0, n_investors=n, horizon=h, seed=1,
                                                     probs=(1 / 6, 1 / 6, 2 / 3), mode="chain", variant=v,
                                                     out_data_T=out10), warm=1, reps=3)
