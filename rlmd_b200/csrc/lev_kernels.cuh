@@ -427,6 +427,36 @@ static int chain_launch_gt(const ChainLaunch& a) {
 // FMA 1.28e12; streamed coin FSEL 1.58e12, LDS 9.0e11, FMA 1.68e12; Philox dice
 // FSEL 5.6e11, LDS 8.9e11, FMA 6.7e11 (the generator already loads the FMA and ALU
 // pipes, so the shared-memory table wins there).
+// Fills row 3 of the table with the scaled FMA deltas of V_FMA; false when some
+// entry cannot be reproduced bit for bit by one fused multiply-add.
+inline bool fma_deltas(FactorTable& f, int K, int g_cnt) {
+  if (K > 3) return false;
+  const int scale_exp = (K == 2) ? 125 : 123;              // 1 / c of the highest code
+  const float c = ldexpf(1.0f, -scale_exp);
+  for (int g = 0; g < 32; ++g) {
+    f.m[3][g] = 0.0f;
+    if (g >= g_cnt) continue;
+    const float f0 = f.m[0][g], ft = f.m[K - 1][g];
+    uint32_t want, got;
+    memcpy(&want, &ft, 4);
+    const float a0 = (float)((double)ft - (double)f0);
+    const float cand[3] = {a0, nextafterf(a0, INFINITY), nextafterf(a0, -INFINITY)};
+    bool ok = false;
+    for (int i = 0; i < 3 && !ok; ++i) {
+      const float as = ldexpf(cand[i], scale_exp);
+      if (!std::isfinite(as)) continue;
+      const float r1 = fmaf(c, as, f0), r0 = fmaf(0.0f, as, f0);
+      memcpy(&got, &r1, 4);
+      uint32_t b0, w0;
+      memcpy(&b0, &r0, 4);
+      memcpy(&w0, &f0, 4);
+      if (got == want && b0 == w0) { f.m[3][g] = as; ok = true; }
+    }
+    if (!ok) return false;
+  }
+  return true;
+}
+
 template <int K>
 static int chain_launch_all(const ChainLaunch& a0) {
   ChainLaunch a = a0;
