@@ -286,6 +286,65 @@ int b200_replay_sample(const b200_replay_desc* desc, const int64_t* idx, int64_t
                        uint8_t* out_done, int64_t* out_eff, void* stream);
 
 /* ------------------------------------------------------------------ *
+ * Fused collector and evaluation rollouts
+ *
+ * Replaces the inner loop of scripts/rl_multiplicative.py:185-273
+ *   next_state, reward, env_done, risk = env.step(action)
+ *   agent.store_transistion(state, action, reward, next_state, learn_done)
+ *   state = next_state      # env.reset() after a done step
+ * for `n_envs` environments at once, and tools/eval_episodes.py:233-262 (the
+ * n_eval constant-action episodes of eval_multiplicative).  Environment e
+ * appends to lane e of the replay memory: slots [e*lane_len, (e+1)*lane_len),
+ * with its own 8-word header at replay.header + 8*e, i.e. every lane is a
+ * reference ReplayBufferTorch of lane_len slots (n_envs = 1: the reference's
+ * single stream).  The step / sample counters that key the Philox draws live in
+ * device memory (`counter`, int64[2]), so step + sample can be captured in a
+ * CUDA graph and replayed without host work.
+ * ------------------------------------------------------------------ */
+typedef struct b200_collect_desc {
+  b200_env_desc env;
+  b200_replay_desc replay;  /* mem_size >= n_envs*lane_len; header int64 [n_envs, 8] */
+  int64_t n_envs;
+  int64_t lane_len;
+  double reward_floor;      /* r_abs_zero, or -inf (tools/replay_torch.py:189)      */
+} b200_collect_desc;
+
+/* wealth [E], time [E], cur_state [E,S] (the observation the agent reads),
+ * counter int64 [2] on the device; zeroes every lane header and the counters. */
+int b200_collect_reset(const b200_collect_desc* desc, double* wealth, int32_t* time,
+                       double* cur_state, int64_t* counter, void* stream);
+
+/* One env step + append per environment.  action [E,A] double on the device;
+ * returns_in [E,n_gambles] or NULL = Philox draws keyed by counter[0]; optional
+ * outputs reward [E], done [E,2] bytes, risk [E,R] (NULL = not wanted).
+ * cur_state becomes next_state, or the reset state after a done step. */
+int b200_collect_step(const b200_collect_desc* desc, double* wealth, int32_t* time,
+                      double* cur_state, const double* action, const double* returns_in,
+                      int64_t* counter, double* reward, uint8_t* done, double* risk,
+                      void* stream);
+
+/* b200_replay_sample over the lanes: idx = slots (lane*lane_len + local) or NULL
+ * = n_batches x batch distinct draws over the filled part of all lanes, keyed by
+ * (seed, counter[1]); outputs as b200_replay_sample. */
+int b200_collect_sample(const b200_collect_desc* desc, const int64_t* idx, int64_t n_batches,
+                        int32_t batch, int32_t multi_steps, const float* gamma_pow_host,
+                        int32_t additive, uint64_t seed, int64_t* counter, int64_t* out_idx,
+                        float* out_state, float* out_action, float* out_reward,
+                        float* out_next_state, uint8_t* out_done, int64_t* out_eff,
+                        void* stream);
+
+/* n_episodes evaluation episodes, one constant action [A] each (action
+ * [n_episodes, A]), from the reset state until done or max_steps steps.
+ * returns_in [max_steps, n_episodes, n_gambles] or NULL = Philox draws with
+ * draw index draw_base + step (the stream b200_menv_step consumes with the same
+ * seed and draw_index).  reward [n], steps int32 [n], risk [n,R] of the last
+ * step taken; last_state [n,S] or NULL. */
+int b200_menv_rollout(const b200_env_desc* desc, int64_t n_episodes, const double* action,
+                      const double* returns_in, uint64_t draw_base, int32_t max_steps,
+                      double* reward, int32_t* steps, double* risk, double* last_state,
+                      void* stream);
+
+/* ------------------------------------------------------------------ *
  * Growth-rate summaries (engine-added)
  *
  * The reference forms the time-average growth rate only as the env reward

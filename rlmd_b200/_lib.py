@@ -88,6 +88,16 @@ class ReplayDesc(C.Structure):
     ]
 
 
+class CollectDesc(C.Structure):
+    _fields_ = [
+        ("env", EnvDesc),
+        ("replay", ReplayDesc),
+        ("n_envs", C.c_int64),
+        ("lane_len", C.c_int64),
+        ("reward_floor", C.c_double),
+    ]
+
+
 BB_COIN, BB_DICE, BB_MAX_POINTS = 0, 1, 128
 
 
@@ -137,6 +147,11 @@ _SIGNATURES = {
                                          C.c_double, C.POINTER(C.c_double), _i32, _i64, C.c_double, _vp]),
     "b200_replay_sample": (C.c_int, [C.POINTER(ReplayDesc), _vp, _i64, _i32, _i64, _i32, C.POINTER(C.c_float), _i32,
                                      C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_collect_reset": (C.c_int, [C.POINTER(CollectDesc), _vp, _vp, _vp, _vp, _vp]),
+    "b200_collect_step": (C.c_int, [C.POINTER(CollectDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_collect_sample": (C.c_int, [C.POINTER(CollectDesc), _vp, _i64, _i32, _i32, C.POINTER(C.c_float), _i32,
+                                      C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_menv_rollout": (C.c_int, [C.POINTER(EnvDesc), _i64, _vp, _vp, C.c_uint64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "b200_bigbrain_chunk": (C.c_int, [C.POINTER(BigBrainDesc), _vp, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_double), _i32, _i32, _vp, _vp, _vp]),
     "b200_growth_workspace_bytes": (_i64, [_i64]),

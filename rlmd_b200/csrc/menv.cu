@@ -11,13 +11,9 @@
 // the reference's do; only exp/log in the reward differ in the last ulp.
 // Returns are injected (parity runs) or drawn with Philox4x32-10:
 //   counter = (env lo, env hi, draw_index lo, TAG_ENV + block), key = seed ^ draw_index hi.
-#include "common.cuh"
+#include "menv_core.cuh"
 
 namespace b200 {
-
-constexpr int ENV_MAX_GAMBLES = B200_ENV_MAX_GAMBLES;
-
-__device__ __forceinline__ double clampd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 
 __global__ void __launch_bounds__(128)
 menv_reset_kernel(const __grid_constant__ b200_env_desc d, int64_t E, double* __restrict__ wealth,
@@ -45,147 +41,22 @@ menv_step_kernel(const __grid_constant__ b200_env_desc d, int64_t E, double* __r
                  uint8_t* __restrict__ done_out, double* __restrict__ risk, int S, int A, int R) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  const bool sh = d.family == B200_ENV_DICE_SH;
-  const bool gbm = d.family == B200_ENV_GBM;
-  const int n = sh ? 1 : d.n_gambles;
-  const double* a = action + e * A;
-
-  // ---- returns of this step
+  const int n = d.family == B200_ENV_DICE_SH ? 1 : d.n_gambles;
   double r[ENV_MAX_GAMBLES];
   if (r_in != nullptr) {
     for (int i = 0; i < n; ++i) r[i] = r_in[e * n + i];
   } else {
-    const uint32_t k0 = (uint32_t)d.seed ^ (uint32_t)(draw_index >> 32), k1 = (uint32_t)(d.seed >> 32);
-    uint32_t thr0, thr1;
-    {
-      const double c0 = d.probs[0] * 4294967296.0, c1 = (d.probs[0] + d.probs[1]) * 4294967296.0;
-      thr0 = c0 >= 4294967295.0 ? 0xffffffffu : (uint32_t)floor(c0);
-      thr1 = c1 >= 4294967295.0 ? 0xffffffffu : (uint32_t)floor(c1);
-    }
-    for (int j = 0; j * 4 < n; ++j) {
-      const Philox4 p = philox4x32_10((uint32_t)e, (uint32_t)((uint64_t)e >> 32), (uint32_t)draw_index,
-                                      PHILOX_TAG_ENV + (uint32_t)j, k0, k1);
-      const uint32_t u[4] = {p.x, p.y, p.z, p.w};
-      if (gbm) {
-        float z[4];
-        box_muller(u[0], u[1], z[0], z[1]);
-        box_muller(u[2], u[3], z[2], z[3]);
-        for (int b = 0; b < 4 && j * 4 + b < n; ++b) r[j * 4 + b] = d.log_mean + d.vol * (double)z[b];
-      } else {
-        for (int b = 0; b < 4 && j * 4 + b < n; ++b) {
-          int code = (u[b] >= thr0);
-          if (d.family != B200_ENV_COIN) code += (u[b] >= thr1);
-          r[j * 4 + b] = d.returns[code];
-        }
-      }
-    }
+    env_draw_returns(d, e, draw_index, n, r);
   }
-
-  // ---- actions -> leverages, stop-loss, retention
-  const int off = sh ? (d.investor == B200_INV_INSURED ? 0 : d.investor) : d.investor;  // A 0, B 1, C 2
-  double lev[ENV_MAX_GAMBLES];
-  double lev_sh = 0.0, r_sh = 0.0;
-  double stop = 0.0, retention = 0.0;
-  const bool has_stop = d.investor == B200_INV_B || d.investor == B200_INV_C;
-  const bool has_ret = d.investor == B200_INV_C;
-  if (has_stop) stop = d.stop_abs ? fabs(a[0]) : (a[0] + d.max_abs_action) / 2;
-  if (has_ret) retention = (a[1] + d.max_abs_action) / 2;
-
-  double step_return, factor;
-  if (sh) {
-    r_sh = (r[0] == d.returns[2]) ? d.sh_returns[2] : (r[0] == d.returns[0]) ? d.sh_returns[0] : d.sh_returns[1];
-    if (d.investor == B200_INV_INSURED) {
-      lev[0] = a[0] * d.i_lev_factor;
-      lev_sh = 1 - lev[0];
-    } else {
-      lev[0] = a[off] * d.lev_factor;
-      lev_sh = (a[off + 1] + d.max_abs_action) / 2 * d.sh_lev_factor;
-    }
-    step_return = clampd(lev[0] * r[0] + lev_sh * r_sh, d.min_return, d.max_return);
-    factor = 1 + step_return;
-  } else {
-    for (int i = 0; i < n; ++i) lev[i] = a[off + i] * d.lev_factor;
-    double total = lev[0] * r[0];
-    for (int i = 1; i < n; ++i) total = total + lev[i] * r[i];
-    if (gbm) {
-      step_return = fmax(total, d.min_return);
-      factor = fmin(exp(step_return), 1 + d.max_return);
-    } else {
-      step_return = clampd(total, d.min_return, d.max_return);
-      factor = 1 + step_return;
-    }
-  }
-
-  // ---- wealth update
-  const double w0 = wealth[e];
-  double wmin, w, active = 1.0;
-  if (!has_stop) {
-    wmin = d.min_value;
-    w = clampd(w0 * factor, d.min_value, d.max_value);
-  } else {
-    const double floor_b = fmax(d.initial_value * stop, d.min_value);
-    if (!has_ret || w0 <= d.initial_value) wmin = floor_b;
-    else wmin = d.initial_value + (w0 - d.initial_value) * retention;
-    active = fmax(w0 - wmin, 0.0);
-    w = clampd(wmin + active * factor, wmin, d.max_value);
-  }
+  EnvStep o;
   const int t = time[e];
-  const double growth = w / d.initial_value;
-  const double rew = exp(log(growth) / (double)t);
-
-  // ---- next state (normalised), done flags
-  double* ns = next_state + e * S;
-  const double s0 = w / d.max_value, s1 = step_return / d.max_value, s2 = growth / d.max_value,
-               s3 = rew / d.max_value;
-  ns[0] = s0; ns[1] = s1; ns[2] = s2; ns[3] = s3;
-  bool done_state = (s0 >= 1.0) || (s1 >= 1.0) || (s2 >= 1.0) || (s3 >= 1.0);
-  if (sh) {
-    const double q0 = r[0] / d.max_value, q1 = r_sh / d.max_value;
-    ns[4] = q0; ns[5] = q1;
-    done_state = done_state || q0 >= 1.0 || q1 >= 1.0;
-  } else {
-    for (int i = 0; i < n; ++i) {
-      const double q = r[i] / d.max_value;
-      ns[4 + i] = q;
-      done_state = done_state || q >= 1.0;
-    }
-  }
-  const double lev_cap = d.max_abs_action * d.lev_factor;
-  bool any_max = false, all_max = true, all_min = true;
-  for (int i = 0; i < n; ++i) {
-    const double al = fabs(lev[i]);
-    any_max = any_max || (al == lev_cap);
-    all_max = all_max && (al == lev_cap);
-    all_min = all_min && (al < d.min_weight);
-  }
-  bool done = (w == wmin) || (rew < d.min_reward) || (step_return == d.min_return) || (gbm ? all_max : any_max) ||
-              all_min || done_state;
-  if (has_stop) done = done || (active == 0.0);
-  done_out[e * 2 + 0] = done ? 1 : 0;
-  done_out[e * 2 + 1] = (done && !done_state) ? 1 : 0;
-  reward_out[e] = rew;
-
-  // ---- risk vector
-  double* rk = risk + e * R;
-  rk[0] = rew; rk[1] = w; rk[2] = step_return;
-  if (sh) {
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    rk[3] = lev[0];
-    rk[4] = has_stop ? stop : qnan;
-    rk[5] = has_ret ? retention : qnan;
-    rk[6] = lev_sh;
-  } else {
-    double m = lev[0];
-    for (int i = 1; i < n; ++i) m = m + lev[i];
-    rk[3] = m / (double)n;
-    int c = 4;
-    if (has_stop) rk[c++] = stop;
-    if (has_ret) rk[c++] = retention;
-    if (n > 1)
-      for (int i = 0; i < n; ++i) rk[c++] = lev[i];
-  }
-
-  wealth[e] = w;
+  env_step_core(d, action + e * A, r, wealth[e], t, o);
+  for (int i = 0; i < S; ++i) next_state[e * S + i] = o.ns[i];
+  for (int i = 0; i < R; ++i) risk[e * R + i] = o.rk[i];
+  done_out[e * 2 + 0] = o.done ? 1 : 0;
+  done_out[e * 2 + 1] = o.learn_done ? 1 : 0;
+  reward_out[e] = o.reward;
+  wealth[e] = o.w;
   time[e] = t + 1;
 }
 

@@ -200,9 +200,14 @@ constexpr unsigned long long SET_EMPTY = ~0ull;
 
 __global__ void __launch_bounds__(1024)
 replay_draw_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t B, uint64_t seed, uint64_t draw_index,
-                   int32_t table_size, int64_t* __restrict__ out_idx) {
+                   const int64_t* __restrict__ draw_counter, int64_t lanes, int64_t lane_len, int32_t table_size,
+                   int64_t* __restrict__ out_idx) {
   extern __shared__ unsigned long long table[];
-  const int64_t filled = filled_arg >= 0 ? filled_arg : min(d.header[H_MEM_IDX], d.mem_size);
+  // lanes > 1 (collector): every lane holds the same number of transitions; the
+  // draw is over lanes * lane_filled values and maps back to slots at the end
+  const int64_t lane_filled = filled_arg >= 0 ? filled_arg : min(d.header[H_MEM_IDX], lane_len);
+  const int64_t filled = lanes * lane_filled;
+  if (draw_counter != nullptr) draw_index += (uint64_t)draw_counter[0];
   const uint32_t mask = (uint32_t)table_size - 1u;
   const uint32_t k0 = (uint32_t)seed ^ (uint32_t)(draw_index >> 32), k1 = (uint32_t)(seed >> 32);
   for (int s = threadIdx.x; s < table_size; s += blockDim.x) table[s] = SET_EMPTY;
@@ -250,7 +255,8 @@ replay_draw_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t B, uint
       uint32_t s = (v * 0x9E3779B1u) & mask;
       while ((uint32_t)(table[s] >> 32) != v) s = (s + 1) & mask;
       if ((uint32_t)(table[s] & 0xffffffffu) == ((round << 16) | t)) {
-        out_idx[(int64_t)blockIdx.x * B + t] = (int64_t)v;
+        const int64_t lane = (int64_t)v / lane_filled;
+        out_idx[(int64_t)blockIdx.x * B + t] = lanes > 1 ? lane * lane_len + ((int64_t)v - lane * lane_filled) : (int64_t)v;
         pending_bits &= ~(1u << j);
       }
     }
@@ -266,7 +272,8 @@ struct GammaPow {
 template <int LANES>
 __global__ void __launch_bounds__(256)
 replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, int64_t n_samples,
-                     int64_t filled_arg, int32_t n_steps, int32_t additive, const __grid_constant__ GammaPow gp,
+                     int64_t filled_arg, int64_t lanes, int64_t lane_len, int32_t n_steps, int32_t additive,
+                     const __grid_constant__ GammaPow gp,
                      float* __restrict__ out_state, float* __restrict__ out_action, float* __restrict__ out_reward,
                      float* __restrict__ out_next_state, uint8_t* __restrict__ out_done,
                      int64_t* __restrict__ out_eff) {
@@ -274,25 +281,30 @@ replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, 
   const int lane = threadIdx.x % LANES;
   const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
   const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
-  const int64_t filled = filled_arg >= 0 ? filled_arg : min(d.header[H_MEM_IDX], d.mem_size);
-  const int64_t episodes = d.header[H_EPISODES], e0 = d.header[H_E0], elast = d.header[H_ELAST];
-
+  // A lane is a reference buffer of lane_len slots with its own header; the
+  // plain replay buffer is the one-lane case (lane_len = mem_size).
   for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; q < n_samples; q += groups) {
-    const int64_t i = idx[q];
-    const bool ok = i >= 0 && i < filled;
+    const int64_t slot = idx[q];
+    const int64_t lane_id = (slot >= 0 && lanes > 1) ? slot / lane_len : 0;
+    const int64_t base = lane_id * lane_len;
+    const int64_t i = slot - base;
+    const int64_t* __restrict__ hdr = d.header + (lane_id < lanes ? lane_id : 0) * 8;
+    const int64_t filled = filled_arg >= 0 ? filled_arg : min(hdr[H_MEM_IDX], lane_len);
+    const int64_t episodes = hdr[H_EPISODES], e0 = hdr[H_E0], elast = hdr[H_ELAST];
+    const bool ok = slot >= 0 && lane_id < lanes && i < filled;
     int64_t first = i;
     int eff = ok ? 1 : 0;
     float R = 0.0f;
     const float* src_state = d.state_memory;
     uint8_t term = 0;
     if (ok) {
-      term = d.terminal_memory[i];
+      term = d.terminal_memory[base + i];
       if (n_steps <= 1) {
-        R = d.reward_memory[i];
+        R = d.reward_memory[base + i];
       } else {
         int64_t start, len;
         if (episodes == 0 || i <= e0) { start = 0; len = i + 1; }
-        else if (i <= elast) { start = d.episode_start[i]; len = i - start + 1 + (term ? 0 : 1); }
+        else if (i <= elast) { start = d.episode_start[base + i]; len = i - start + 1 + (term ? 0 : 1); }
         else { start = 0; len = min(i - elast + 1, e0 + 1); }
         eff = (int)min(len, (int64_t)n_steps);
         first = start + len - eff;
@@ -301,7 +313,7 @@ replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, 
         for (int t0 = 0; t0 < n_steps - 1; t0 += LANES) {
           const int t = t0 + lane;
           float term_t = 0.0f;
-          if (t < eff - 1) term_t = gp.v[t] * d.reward_memory[first + t];
+          if (t < eff - 1) term_t = gp.v[t] * d.reward_memory[base + first + t];
           const int lim = min(LANES, n_steps - 1 - t0);
           for (int j = 0; j < lim; ++j) {
             const float x = __shfl_sync(gmask, term_t, j, LANES);
@@ -312,10 +324,10 @@ replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, 
       }
     }
     for (int c = lane; c < S; c += LANES) {
-      out_state[q * S + c] = ok ? src_state[first * S + c] : 0.0f;
-      out_next_state[q * S + c] = ok ? d.next_state_memory[i * S + c] : 0.0f;
+      out_state[q * S + c] = ok ? src_state[(base + first) * S + c] : 0.0f;
+      out_next_state[q * S + c] = ok ? d.next_state_memory[(base + i) * S + c] : 0.0f;
     }
-    for (int c = lane; c < A; c += LANES) out_action[q * A + c] = ok ? d.action_memory[first * A + c] : 0.0f;
+    for (int c = lane; c < A; c += LANES) out_action[q * A + c] = ok ? d.action_memory[(base + first) * A + c] : 0.0f;
     if (lane == 0) {
       out_reward[q] = R;
       out_done[q] = term;
@@ -406,13 +418,16 @@ extern "C" int b200_replay_store_host(const b200_replay_desc* d, const double* s
   return 0;
 }
 
-extern "C" int b200_replay_sample(const b200_replay_desc* d, const int64_t* idx, int64_t n_batches, int32_t batch,
-                                  int64_t filled, int32_t multi_steps, const float* gamma_pow_host,
-                                  int32_t additive, uint64_t seed, uint64_t draw_index, int64_t* out_idx,
-                                  float* out_state, float* out_action, float* out_reward, float* out_next_state,
-                                  uint8_t* out_done, int64_t* out_eff, void* stream) {
+namespace b200 {
+int replay_sample_lanes(const b200_replay_desc* d, int64_t lanes, int64_t lane_len, const int64_t* idx,
+                        int64_t n_batches, int32_t batch, int64_t filled, int32_t multi_steps,
+                        const float* gamma_pow_host, int32_t additive, uint64_t seed, uint64_t draw_index,
+                        const int64_t* draw_counter, int64_t* out_idx, float* out_state, float* out_action,
+                        float* out_reward, float* out_next_state, uint8_t* out_done, int64_t* out_eff,
+                        void* stream) {
   if (int rc = require_device()) return rc;
   if (int rc = check_desc(d)) return rc;
+  B200_REQUIRE(lanes >= 1 && lane_len >= 1 && lanes * lane_len <= d->mem_size, "replay_sample: lanes x lane_len exceeds mem_size");
   B200_REQUIRE(n_batches >= 0 && batch >= 0, "replay_sample: negative batch count / size");
   const int64_t n_samples = n_batches * batch;
   if (n_samples == 0) return 0;
@@ -438,21 +453,36 @@ extern "C" int b200_replay_sample(const b200_replay_desc* d, const int64_t* idx,
       B200_CUDA(cudaFuncSetAttribute(replay_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
       attr_set[dev] = true;
     }
-    replay_draw_kernel<<<(unsigned)n_batches, threads, smem, st>>>(*d, filled, batch, seed, draw_index, table, out_idx);
+    replay_draw_kernel<<<(unsigned)n_batches, threads, smem, st>>>(*d, filled, batch, seed, draw_index, draw_counter,
+                                                                    lanes, lane_len, table, out_idx);
     idx = out_idx;
   }
   GammaPow gp;
   for (int t = 0; t < B200_REPLAY_MAX_STEPS; ++t) gp.v[t] = (multi_steps > 1 && t < multi_steps) ? gamma_pow_host[t] : 0.0f;
   const int wide = d->state_dim >= 32;
-  const int lanes = wide ? 32 : 8;
-  const int64_t want_blocks = (n_samples * lanes + 255) / 256;
+  const int width = wide ? 32 : 8;
+  const int64_t want_blocks = (n_samples * width + 255) / 256;
   const int grid = (int)std::min<int64_t>(want_blocks, (int64_t)sm_count() * 8);
   if (wide)
-    replay_gather_kernel<32><<<grid, 256, 0, st>>>(*d, idx, n_samples, filled, multi_steps, additive, gp, out_state,
-                                                    out_action, out_reward, out_next_state, out_done, out_eff);
+    replay_gather_kernel<32><<<grid, 256, 0, st>>>(*d, idx, n_samples, filled, lanes, lane_len, multi_steps, additive,
+                                                    gp, out_state, out_action, out_reward, out_next_state, out_done,
+                                                    out_eff);
   else
-    replay_gather_kernel<8><<<grid, 256, 0, st>>>(*d, idx, n_samples, filled, multi_steps, additive, gp, out_state,
-                                                   out_action, out_reward, out_next_state, out_done, out_eff);
+    replay_gather_kernel<8><<<grid, 256, 0, st>>>(*d, idx, n_samples, filled, lanes, lane_len, multi_steps, additive,
+                                                   gp, out_state, out_action, out_reward, out_next_state, out_done,
+                                                   out_eff);
   B200_CUDA(cudaGetLastError());
   return 0;
+}
+}  // namespace b200
+
+extern "C" int b200_replay_sample(const b200_replay_desc* d, const int64_t* idx, int64_t n_batches, int32_t batch,
+                                  int64_t filled, int32_t multi_steps, const float* gamma_pow_host,
+                                  int32_t additive, uint64_t seed, uint64_t draw_index, int64_t* out_idx,
+                                  float* out_state, float* out_action, float* out_reward, float* out_next_state,
+                                  uint8_t* out_done, int64_t* out_eff, void* stream) {
+  if (d == nullptr) return set_error(B200_EINVAL, "replay: desc is NULL");
+  return replay_sample_lanes(d, 1, d->mem_size, idx, n_batches, batch, filled, multi_steps, gamma_pow_host, additive,
+                             seed, draw_index, nullptr, out_idx, out_state, out_action, out_reward, out_next_state,
+                             out_done, out_eff, stream);
 }

@@ -176,6 +176,42 @@ def main():
                                       algorithmic_GBps_many=k * batch * bytes_per / bk / 1e9,
                                       hbm_frac_many=k * batch * bytes_per / bk / 1e9 / hbm)), flush=True)
                 del buf, st
+    if a.only in ("", "collect"):
+        # fused collector: env step + append per environment (one kernel), then an n-step sample of 256;
+        # eager = one C call per stage from Python, graph = the captured pair replayed
+        from rlmd_b200 import collector, envs
+        for e in (1, 256, 65_536, 1_048_576):
+            lane = 1_000_000 if e == 1 else max(64, 64_000_000 // e)
+            env = envs.Coin_InvA(1, n_envs=e, seed=1)
+            inputs = {"mini_batch_size": 256, "discount": 0.99, "multi_steps": 5, "r_abs_zero": None, "dynamics": "M"}
+            col = collector.Collector(env, lane, inputs, seed=2)
+            act = torch.rand((e, 1), dtype=torch.float64, device="cuda") * 0.8 + 0.1
+            for _ in range(8):
+                col.step(act)
+            reps = min(200, lane - 20)
+            def eager():
+                col.step(act)
+                col.sample(1)
+            be, me = timeit(eager, warm=3, reps=reps // 4)
+            run = col.capture(act, k=1)
+            bg, mg = timeit(run, warm=3, reps=reps // 4)
+            def steps_only():
+                col.step(act)
+            bs, ms = timeit(steps_only, warm=3, reps=reps // 4)
+            bytes_step = e * (8 + 8 * 5 * 2 + 8 + 53 + 8 * 5 + 8 + 2 + 32)
+            print(json.dumps(dict(kernel="collect_step_sample", n_envs=e, lane_len=lane, eager_us=me * 1e6,
+                                  graph_us=mg * 1e6, step_only_us=ms * 1e6, env_steps_per_s_graph=e / mg,
+                                  env_steps_per_s_eager=e / me, env_steps_per_s_step_only=e / ms,
+                                  step_GBps=bytes_step / ms / 1e9)), flush=True)
+            del col, env
+        env = envs.Coin_InvA(1, seed=3)
+        for n_eval, steps in ((100, 1000), (100_000, 1000), (4_000_000, 200)):
+            a_ev = torch.full((n_eval, 1), 0.25, dtype=torch.float64, device="cuda")
+            b, m = timeit(lambda: collector.rollout(env, a_ev, steps), warm=1, reps=5)
+            _, st, _, _ = collector.rollout(env, a_ev, steps)
+            tot = float(st.sum())
+            print(json.dumps(dict(kernel="eval_rollout_coin_A1", n_eval=n_eval, max_steps=steps, best_s=b,
+                                  env_steps_per_s=tot / b, mean_steps=tot / n_eval)), flush=True)
     if a.only in ("", "growth"):
         lw = torch.randn((20, n), dtype=torch.float64, device="cuda")
         b, m = timeit(lambda: engine.growth_summary(lw, h, 100.0, quantiles=(0.05, 0.5, 0.95)))

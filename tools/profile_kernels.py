@@ -97,6 +97,18 @@ def main():
             buf.store_batch(st, st[:, :1], 1 + 0.01 * st[:, 0], st, torch.as_tensor(done, device="cuda"))
             buf.sample_exp()
             buf.sample_many(1024)
+    if on("collect"):
+        from rlmd_b200 import collector, envs
+        e = 1_048_576
+        env = envs.Coin_InvA(1, n_envs=e, seed=1)
+        inputs = {"mini_batch_size": 256, "discount": 0.99, "multi_steps": 5, "r_abs_zero": None, "dynamics": "M"}
+        col = collector.Collector(env, 64, inputs, seed=2)
+        act = torch.rand((e, 1), dtype=torch.float64, device="cuda") * 0.8 + 0.1
+        for _ in range(3):
+            col.step(act)
+        col.sample(1024)
+        collector.rollout(envs.Coin_InvA(1, seed=3), torch.full((1_000_000, 1), 0.25, dtype=torch.float64,
+                                                                 device="cuda"), 200)
     if on("growth"):
         lw = torch.randn((20, n), dtype=torch.float64, device="cuda")
         engine.growth_summary(lw, h, 100.0, quantiles=(0.05, 0.5, 0.95))
