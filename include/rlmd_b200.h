@@ -294,7 +294,8 @@ int b200_replay_sample(const b200_replay_desc* desc, const int64_t* idx, int64_t
  *   state = next_state      # env.reset() after a done step
  * for `n_envs` environments at once, and tools/eval_episodes.py:233-262 (the
  * n_eval constant-action episodes of eval_multiplicative).  Environment e
- * appends to lane e of the replay memory: slots [e*lane_len, (e+1)*lane_len),
+ * appends to lane e of the replay memory: its j-th transition sits at slot
+ * j*n_envs + e (slot-major, so the appends of one step are contiguous rows),
  * with its own 8-word header at replay.header + 8*e, i.e. every lane is a
  * reference ReplayBufferTorch of lane_len slots (n_envs = 1: the reference's
  * single stream).  The step / sample counters that key the Philox draws live in
@@ -323,7 +324,7 @@ int b200_collect_step(const b200_collect_desc* desc, double* wealth, int32_t* ti
                       int64_t* counter, double* reward, uint8_t* done, double* risk,
                       void* stream);
 
-/* b200_replay_sample over the lanes: idx = slots (lane*lane_len + local) or NULL
+/* b200_replay_sample over the lanes: idx = slots (local*n_envs + lane) or NULL
  * = n_batches x batch distinct draws over the filled part of all lanes, keyed by
  * (seed, counter[1]); outputs as b200_replay_sample. */
 int b200_collect_sample(const b200_collect_desc* desc, const int64_t* idx, int64_t n_batches,

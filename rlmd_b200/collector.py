@@ -15,7 +15,8 @@ reference,
 as device-side pipelines without a host round trip per step.  `Collector.step`
 is ONE kernel (env step + append + observation carry) for `n_envs` environments,
 each writing its own lane of the replay memory (a lane is a reference replay
-buffer; `n_envs = 1` is the reference's single stream); `Collector.sample` is
+buffer, its j-th transition at slot `j * n_envs + lane`; `n_envs = 1` is the
+reference's single stream); `Collector.sample` is
 the n-step gather over the lanes; `Collector.capture` records step + sample in
 a CUDA graph.  There is no CPU path.
 """
@@ -146,7 +147,7 @@ class Collector:
         """
         k mini-batches of the reference's `sample_exp` 6-tuple over all lanes
         (states, actions, rewards, next_states, dones, eff_length), shaped [k*B, ...].
-        batch: optional int64 slots [k, B] (slot = lane * lane_len + local index).
+        batch: optional int64 slots [k, B] (slot = local index * n_envs + lane).
         """
         if batch is not None:
             batch = torch.as_tensor(batch, device=self.device).to(torch.int64).reshape(k, self.batch_size).contiguous()

@@ -10,7 +10,9 @@
 // collect_step_kernel: one thread per environment does the env step (the shared
 // core of menv_core.cuh), appends the transition to ITS lane of the replay
 // memory with the reference's episode bookkeeping (replay.cu restates it; a lane
-// is a reference buffer of lane_len slots with its own 8-word header), and
+// is a reference buffer of lane_len transitions with its own 8-word header,
+// local index j of lane e at slot j * n_envs + e so that one step's appends are
+// contiguous rows), and
 // carries the observation forward (reset state once the episode is done).  No
 // host round trip between step, store and sample: the step counter that feeds
 // the Philox draws lives on the device, so one collect-step + sample pair can be
@@ -82,7 +84,7 @@ collect_step_kernel(const __grid_constant__ b200_collect_desc c, double* __restr
   int64_t* h = m.header + e * 8;
   const int64_t pos = h[H_MEM_IDX];
   const int64_t local = pos % c.lane_len;
-  const int64_t slot = e * c.lane_len + local;
+  const int64_t slot = local * c.n_envs + e;   // slot-major: the lanes' writes of one step coalesce
   for (int i = 0; i < S; ++i) {
     m.state_memory[slot * S + i] = (float)st[i];
     m.next_state_memory[slot * S + i] = (float)o.ns[i];

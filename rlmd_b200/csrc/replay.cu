@@ -203,8 +203,9 @@ replay_draw_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t B, uint
                    const int64_t* __restrict__ draw_counter, int64_t lanes, int64_t lane_len, int32_t table_size,
                    int64_t* __restrict__ out_idx) {
   extern __shared__ unsigned long long table[];
-  // lanes > 1 (collector): every lane holds the same number of transitions; the
-  // draw is over lanes * lane_filled values and maps back to slots at the end
+  // lanes > 1 (collector): every lane holds the same number of transitions and the
+  // memory is slot-major (slot = local * lanes + lane), so the filled part is the
+  // prefix [0, lanes * lane_filled) and a drawn value is a slot
   const int64_t lane_filled = filled_arg >= 0 ? filled_arg : min(d.header[H_MEM_IDX], lane_len);
   const int64_t filled = lanes * lane_filled;
   if (draw_counter != nullptr) draw_index += (uint64_t)draw_counter[0];
@@ -255,8 +256,7 @@ replay_draw_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t B, uint
       uint32_t s = (v * 0x9E3779B1u) & mask;
       while ((uint32_t)(table[s] >> 32) != v) s = (s + 1) & mask;
       if ((uint32_t)(table[s] & 0xffffffffu) == ((round << 16) | t)) {
-        const int64_t lane = (int64_t)v / lane_filled;
-        out_idx[(int64_t)blockIdx.x * B + t] = lanes > 1 ? lane * lane_len + ((int64_t)v - lane * lane_filled) : (int64_t)v;
+        out_idx[(int64_t)blockIdx.x * B + t] = (int64_t)v;
         pending_bits &= ~(1u << j);
       }
     }
@@ -281,30 +281,31 @@ replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, 
   const int lane = threadIdx.x % LANES;
   const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
   const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
-  // A lane is a reference buffer of lane_len slots with its own header; the
+  // A lane is a reference buffer of lane_len transitions with its own header,
+  // stored slot-major: local index j of lane e sits at slot j * lanes + e.  The
   // plain replay buffer is the one-lane case (lane_len = mem_size).
   for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; q < n_samples; q += groups) {
     const int64_t slot = idx[q];
-    const int64_t lane_id = (slot >= 0 && lanes > 1) ? slot / lane_len : 0;
-    const int64_t base = lane_id * lane_len;
-    const int64_t i = slot - base;
-    const int64_t* __restrict__ hdr = d.header + (lane_id < lanes ? lane_id : 0) * 8;
+    const int64_t lane_id = (slot >= 0 && lanes > 1) ? slot % lanes : 0;
+    const int64_t i = (slot >= 0 && lanes > 1) ? slot / lanes : slot;
+    auto at = [&](int64_t j) { return j * lanes + lane_id; };
+    const int64_t* __restrict__ hdr = d.header + lane_id * 8;
     const int64_t filled = filled_arg >= 0 ? filled_arg : min(hdr[H_MEM_IDX], lane_len);
     const int64_t episodes = hdr[H_EPISODES], e0 = hdr[H_E0], elast = hdr[H_ELAST];
-    const bool ok = slot >= 0 && lane_id < lanes && i < filled;
+    const bool ok = slot >= 0 && i < filled;
     int64_t first = i;
     int eff = ok ? 1 : 0;
     float R = 0.0f;
     const float* src_state = d.state_memory;
     uint8_t term = 0;
     if (ok) {
-      term = d.terminal_memory[base + i];
+      term = d.terminal_memory[at(i)];
       if (n_steps <= 1) {
-        R = d.reward_memory[base + i];
+        R = d.reward_memory[at(i)];
       } else {
         int64_t start, len;
         if (episodes == 0 || i <= e0) { start = 0; len = i + 1; }
-        else if (i <= elast) { start = d.episode_start[base + i]; len = i - start + 1 + (term ? 0 : 1); }
+        else if (i <= elast) { start = d.episode_start[at(i)]; len = i - start + 1 + (term ? 0 : 1); }
         else { start = 0; len = min(i - elast + 1, e0 + 1); }
         eff = (int)min(len, (int64_t)n_steps);
         first = start + len - eff;
@@ -313,7 +314,7 @@ replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, 
         for (int t0 = 0; t0 < n_steps - 1; t0 += LANES) {
           const int t = t0 + lane;
           float term_t = 0.0f;
-          if (t < eff - 1) term_t = gp.v[t] * d.reward_memory[base + first + t];
+          if (t < eff - 1) term_t = gp.v[t] * d.reward_memory[at(first + t)];
           const int lim = min(LANES, n_steps - 1 - t0);
           for (int j = 0; j < lim; ++j) {
             const float x = __shfl_sync(gmask, term_t, j, LANES);
@@ -324,10 +325,10 @@ replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, 
       }
     }
     for (int c = lane; c < S; c += LANES) {
-      out_state[q * S + c] = ok ? src_state[(base + first) * S + c] : 0.0f;
-      out_next_state[q * S + c] = ok ? d.next_state_memory[(base + i) * S + c] : 0.0f;
+      out_state[q * S + c] = ok ? src_state[at(first) * S + c] : 0.0f;
+      out_next_state[q * S + c] = ok ? d.next_state_memory[at(i) * S + c] : 0.0f;
     }
-    for (int c = lane; c < A; c += LANES) out_action[q * A + c] = ok ? d.action_memory[(base + first) * A + c] : 0.0f;
+    for (int c = lane; c < A; c += LANES) out_action[q * A + c] = ok ? d.action_memory[at(first) * A + c] : 0.0f;
     if (lane == 0) {
       out_reward[q] = R;
       out_done[q] = term;

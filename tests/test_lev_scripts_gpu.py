@@ -34,7 +34,9 @@ def test_coin_flip_files(scripts, tmp_path, capsys):
     assert sorted(files) == ["coin_inv1_val", "coin_inv1_val_T", "coin_inv2_val", "coin_inv3_val", "coin_inv4_lev"]
     assert files["coin_inv1_val"].shape == (10, 13, h - 1) and files["coin_inv1_val_T"].shape == (10, n)
     assert files["coin_inv2_val"].shape == (1, 1, 26, h - 1)
-    assert files["coin_inv3_val"].shape == (3, 3, 26, h - 1)
+    from rlmd_b200.lev_exp import param_range                      # the reference's grid quirks (App. A)
+    assert files["coin_inv3_val"].shape == (len(param_range(0.70, 0.90, 0.10)), len(param_range(0.25, 0.75, 0.25)),
+                                            26, h - 1)
     assert files["coin_inv4_lev"].shape[0] == 3 and files["coin_inv4_lev"].shape[3] == 4
     for k, a in files.items():
         assert a.dtype == np.float32, k
