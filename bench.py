@@ -169,6 +169,88 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+# ------------------------------------------------- the metric's other clauses
+def _event_time(torch, fn, warm, reps):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) * 1e-3 / reps
+
+
+def run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world):
+    """
+    Side numbers for the other clauses of BASELINE.json's metric, outside the timed
+    region of the headline (every rank runs them; times are the max over ranks):
+    * C4: GBM leverage sweep, on-device Philox draws, 1.25e7 investors x 1e4 steps per
+      GPU (1e8 investors over 8 GPUs), grid param_range(-1, 1, 0.2);
+    * C5: n-step replay sampling, batch 256 from a full 1e6 buffer (per call, and 1024
+      mini-batches per launch), and the fused collector (env step + append + sample).
+    """
+    from rlmd_b200 import collector, envs
+    from rlmd_b200.replay_torch import ReplayBufferTorch
+
+    out = {}
+    n_g, h = 12_500_000, HORIZON
+    levg = np.asarray(lev_exp.param_range(-1.0, 1.0, 0.2), np.float32)
+    buf = torch.empty((len(levg), n_g), dtype=torch.float32, device=dev)
+    t = _event_time(torch, lambda: engine.lev_sweep(
+        "gbm", levg, V0, n_investors=n_g, horizon=h, seed=420, investor_offset=rank * n_g, log_mean=0.05 - 0.1,
+        sigma=0.2 ** 0.5, mode="log", out_data_T=buf, device=dev), 1, 3)
+    del buf
+    mem, batch = 1_000_000, 256
+    rs = np.random.RandomState(0)
+    ends = np.cumsum(rs.randint(5, 61, size=mem // 5))
+    done = np.zeros(mem, dtype=bool)
+    done[ends[ends < mem] - 1] = True
+    rep = {}
+    times = [t]
+    for nstep in (1, 5, 10):
+        inputs = {"gpu": str(dev), "input_dims": (5,), "num_actions": 1, "mini_batch_size": batch, "discount": 0.99,
+                  "multi_steps": nstep, "r_abs_zero": None, "dynamics": "M", "buffer": mem, "n_cumsteps": mem}
+        rb = ReplayBufferTorch(inputs)
+        st = torch.randn((mem, 5), dtype=torch.float64, device=dev)
+        rb.store_batch(st, st[:, :1], 1 + 0.01 * st[:, 0], st, torch.as_tensor(done, device=dev))
+        t1 = _event_time(torch, lambda: rb.sample_exp(), 5, 50)
+        tk = _event_time(torch, lambda: rb.sample_many(1024), 2, 10)
+        rep[nstep] = (t1, tk)
+        times += [t1, tk]
+        del rb, st
+    env = envs.Coin_InvA(1, n_envs=1, seed=1, device=dev)
+    col = collector.Collector(env, 100_000, {"mini_batch_size": batch, "discount": 0.99, "multi_steps": 5,
+                                             "r_abs_zero": None, "dynamics": "M"}, seed=2)
+    act = torch.full((1, 1), 0.4, dtype=torch.float64, device=dev)
+    run = col.capture(act, k=1)
+    tc = _event_time(torch, run, 20, 2000)
+    times.append(tc)
+    if world > 1:
+        tt = torch.tensor(times, dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        times = [float(x) for x in tt]
+    t = times[0]
+    out["gbm_philox_sweep"] = {
+        "value": world * n_g * h / t, "unit": UNIT, "ms_per_launch": t * 1e3,
+        "workload": "lev/gbm.py final-time sweep, Philox4x32-10 + Box-Muller on device, 1.25e7 investors x 1e4 steps "
+                    "per GPU, 10 leverages",
+    }
+    out["replay_nstep_sampling"] = {
+        "unit": "samples/s", "buffer": mem, "batch": batch, "per_gpu": True,
+        "per_call": {str(n): batch / times[1 + 2 * i] for i, n in enumerate((1, 5, 10))},
+        "per_call_us": {str(n): times[1 + 2 * i] * 1e6 for i, n in enumerate((1, 5, 10))},
+        "1024_batches_per_launch": {str(n): 1024 * batch / times[2 + 2 * i] for i, n in enumerate((1, 5, 10))},
+    }
+    out["collector_graph_coin_invA"] = {
+        "unit": "env-steps/s", "n_envs": 1, "value": 1 / times[-1], "us_per_step_store_sample": times[-1] * 1e6,
+        "note": "one CUDA-graph replay = env step + replay append + 5-step sample of 256",
+    }
+    return out
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import numpy as np
@@ -253,11 +335,13 @@ def run_gpu(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
         for _ in range(e2e_steps):
-            st = engine.lev_final_host("discrete", table, V0, top_total, host, **kw)
+            st = engine.lev_final_host("discrete", table, V0, top_total, host, **kw)   # ends with the D2H read
+        e_end.record()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt = e_start.elapsed_time(e_end) * 1e-3
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -269,6 +353,8 @@ def run_gpu(args):
                     "statistics read back to the host every step",
         }
         del host
+
+    secondary = None if args.no_secondary else run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -314,7 +400,7 @@ def run_gpu(args):
         },
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
-        "path_steps_per_s": value * g,
+        "path_steps_per_s": value * g, "secondary": secondary,
         "check": {"median_wealth_lev0": float(stats[0, 9]), "mean_wealth_lev0": float(stats[0, 0])},
     }
     print(json.dumps(line), flush=True)
@@ -333,7 +419,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=10_000, help="investors in the cpu_baseline sample")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the GBM-Philox / replay / collector side numbers")
+    ap.add_argument("--cpu-sample", type=int, default=60_000, help="investors in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=4_000, help="investors per step of --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":
