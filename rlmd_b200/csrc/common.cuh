@@ -66,6 +66,41 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
   return Philox4{c0, c1, c2, c3};
 }
 
+// The ten round keys (k + r * Weyl constant) formed once on the host and handed
+// to a kernel as a parameter: the rounds then read them straight from the
+// constant bank instead of re-deriving them with uniform-datapath adds, which
+// cost issue slots in the generator-bound sweeps.
+struct PhiloxKeys {
+  uint32_t k0[10], k1[10];
+};
+inline PhiloxKeys philox_keys(uint64_t seed) {
+  PhiloxKeys K;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    K.k0[r] = a;
+    K.k1[r] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return K;
+}
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 const PhiloxKeys& K) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ K.k0[r];
+    const uint32_t n2 = hi0 ^ c3 ^ K.k1[r];
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
 enum : uint32_t {
   PHILOX_TAG_LEV = 0x4C455600u,   // 'LEV'
   PHILOX_TAG_ENV = 0x454E5600u,   // 'ENV'

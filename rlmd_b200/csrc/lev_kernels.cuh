@@ -315,7 +315,8 @@ __device__ __forceinline__ uint32_t draw_code(uint32_t u, const Thresholds& th) 
 template <int GT, int K, int V, bool DUMP>
 __global__ void __launch_bounds__(128)
 chain_discrete_philox_kernel(const __grid_constant__ FactorTable f, const __grid_constant__ Thresholds th,
-                             uint64_t seed, int64_t investor_offset, const __grid_constant__ ChainParams p) {
+                             const __grid_constant__ PhiloxKeys keys, int64_t investor_offset,
+                             const __grid_constant__ ChainParams p) {
   __shared__ __align__(16) float tab[V == V_LDS ? K * GridTile<GT>::STRIDE : 4];
   if (V == V_LDS) {
     fill_table<GT, K>(tab, f);
@@ -325,14 +326,13 @@ chain_discrete_philox_kernel(const __grid_constant__ FactorTable f, const __grid
   if (row >= p.N) return;
   const uint64_t id = (uint64_t)(row + investor_offset);
   const uint32_t c0 = (uint32_t)id, c1 = (uint32_t)(id >> 32);
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   float w[GT];
 #pragma unroll
   for (int g = 0; g < GT; ++g) w[g] = (p.state_in != nullptr && g < p.G) ? p.state_in[(int64_t)g * p.ldT + row] : p.V0;
   const int j0 = p.t_begin >> 2, j1 = p.t_end >> 2;
 #pragma unroll 2
   for (int j = j0; j < j1; ++j) {
-    const Philox4 r = philox4x32_10(c0, c1, (uint32_t)j, PHILOX_TAG_LEV, k0, k1);
+    const Philox4 r = philox4x32_10(c0, c1, (uint32_t)j, PHILOX_TAG_LEV, keys);
     const uint32_t u[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -341,7 +341,7 @@ chain_discrete_philox_kernel(const __grid_constant__ FactorTable f, const __grid
     }
   }
   if (p.t_end & 3) {
-    const Philox4 r = philox4x32_10(c0, c1, (uint32_t)j1, PHILOX_TAG_LEV, k0, k1);
+    const Philox4 r = philox4x32_10(c0, c1, (uint32_t)j1, PHILOX_TAG_LEV, keys);
     const uint32_t u[4] = {r.x, r.y, r.z, r.w};
     for (int b = 0; b < (p.t_end & 3); ++b) {
       chain_step<GT, K, V>(w, f, tab, sel_from_code<V>(draw_code<K>(u[b], th)));
@@ -391,7 +391,7 @@ static int chain_launch_impl(const ChainLaunch& a) {
     Thresholds th;
     for (int k = 0; k < B200_MAX_OUTCOMES; ++k) th.t[k] = d.thresholds[k];
     const unsigned blocks = (unsigned)((N + 127) / 128);
-    chain_discrete_philox_kernel<GT, K, V, DUMP><<<blocks, 128, 0, a.st>>>(a.f, th, d.seed, d.investor_offset, a.p);
+    chain_discrete_philox_kernel<GT, K, V, DUMP><<<blocks, 128, 0, a.st>>>(a.f, th, philox_keys(d.seed), d.investor_offset, a.p);
     return check_cuda(cudaGetLastError(), "chain_discrete_philox launch");
   }
   const unsigned blocks = (unsigned)((N + TILE_ROWS - 1) / TILE_ROWS);

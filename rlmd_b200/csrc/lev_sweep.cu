@@ -236,9 +236,16 @@ log_gbm_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
 
 // x_t = log_mean + sigma * z_t; four steps per Philox block, two Box-Muller pairs;
 // sigma is folded into the radius, the mean into the final FFMA.
+__device__ __forceinline__ void gbm_from_words(const Philox4& r, float log_mean, float sigma, float (&x)[4]);
 __device__ __forceinline__ void gbm_draw4(uint32_t c0, uint32_t c1, uint32_t j, uint32_t k0, uint32_t k1,
                                           float log_mean, float sigma, float (&x)[4]) {
-  const Philox4 r = philox4x32_10(c0, c1, j, PHILOX_TAG_LEV, k0, k1);
+  gbm_from_words(philox4x32_10(c0, c1, j, PHILOX_TAG_LEV, k0, k1), log_mean, sigma, x);
+}
+__device__ __forceinline__ void gbm_draw4(uint32_t c0, uint32_t c1, uint32_t j, const PhiloxKeys& K,
+                                          float log_mean, float sigma, float (&x)[4]) {
+  gbm_from_words(philox4x32_10(c0, c1, j, PHILOX_TAG_LEV, K), log_mean, sigma, x);
+}
+__device__ __forceinline__ void gbm_from_words(const Philox4& r, float log_mean, float sigma, float (&x)[4]) {
   const float scale2 = box_muller_scale2(sigma);
   float rho, c, s;
   box_muller_polar(r.x, r.y, scale2, rho, c, s);
@@ -250,14 +257,14 @@ __device__ __forceinline__ void gbm_draw4(uint32_t c0, uint32_t c1, uint32_t j, 
 }
 
 __global__ void __launch_bounds__(128)
-log_gbm_philox_kernel(const __grid_constant__ LevGrid lv, uint64_t seed, int64_t investor_offset, float log_mean,
+log_gbm_philox_kernel(const __grid_constant__ LevGrid lv, const __grid_constant__ PhiloxKeys K,
+                      int64_t investor_offset, float log_mean,
                       float sigma, int32_t H, int64_t N, int32_t G, double logV0, float* __restrict__ data_T,
                       double* __restrict__ log_w, int64_t ldT) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= N) return;
   const uint64_t id = (uint64_t)(row + investor_offset);
   const uint32_t c0 = (uint32_t)id, c1 = (uint32_t)(id >> 32);
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   GbmAcc acc;
   const int nblk = H >> 2;
   int j = 0;
@@ -265,19 +272,19 @@ log_gbm_philox_kernel(const __grid_constant__ LevGrid lv, uint64_t seed, int64_t
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       float x[4];
-      gbm_draw4(c0, c1, (uint32_t)(j + u), k0, k1, log_mean, sigma, x);
+      gbm_draw4(c0, c1, (uint32_t)(j + u), K, log_mean, sigma, x);
       acc.step(x[0]); acc.step(x[1]); acc.step(x[2]); acc.step(x[3]);
     }
     acc.fold();
   }
   for (; j < nblk; ++j) {
     float x[4];
-    gbm_draw4(c0, c1, (uint32_t)j, k0, k1, log_mean, sigma, x);
+    gbm_draw4(c0, c1, (uint32_t)j, K, log_mean, sigma, x);
     acc.step(x[0]); acc.step(x[1]); acc.step(x[2]); acc.step(x[3]);
   }
   if (H & 3) {
     float x[4];
-    gbm_draw4(c0, c1, (uint32_t)nblk, k0, k1, log_mean, sigma, x);
+    gbm_draw4(c0, c1, (uint32_t)nblk, K, log_mean, sigma, x);
     for (int t = 0; t < (H & 3); ++t) acc.step(x[t]);
   }
   acc.fold();
@@ -466,7 +473,7 @@ static int run_log_gbm(const b200_lev_desc& d, const float* x, const float* lev_
   const int64_t N = d.n_investors;
   if (d.source == B200_SRC_PHILOX) {
     const unsigned blocks = (unsigned)((N + 127) / 128);
-    log_gbm_philox_kernel<<<blocks, 128, 0, st>>>(lv, d.seed, d.investor_offset, d.log_mean, d.sigma, d.horizon, N,
+    log_gbm_philox_kernel<<<blocks, 128, 0, st>>>(lv, philox_keys(d.seed), d.investor_offset, d.log_mean, d.sigma, d.horizon, N,
                                                   d.n_grid, logV0, data_T, log_w, out_ld(d));
     return check_cuda(cudaGetLastError(), "log_gbm_philox launch");
   }

@@ -91,12 +91,26 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
   constexpr int HBINS = PASS == 0 ? L1_BINS : PASS == 1 ? NT * L2_BINS : PASS == 2 ? NT * L3_BINS : 0;
   for (int i = threadIdx.x; i < HBINS; i += RS_THREADS) smem_hist[i] = 0;
 
-  uint32_t pfx[NT];
+  // Targets that fell into the same bin so far need the same histogram: only the
+  // first of them (its representative) counts, the others copy it at the flush.
+  // cmp[j] is the bin prefix a key must show to be counted for target j; a
+  // duplicate gets a prefix no key can have.
+  __shared__ int rep_s[NT];
+  uint32_t cmp[NT];
   double mean_a = 0, mean_t = 0, mean_j = 0;
   uint32_t thr_key = 0;
   if (PASS == 1 || PASS == 2) {
+    constexpr int SH = PASS == 1 ? 32 - L1_BITS : L3_BITS;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) pfx[j] = (uint32_t)w->prefix[j];
+    for (int j = 0; j < NT; ++j) {
+      cmp[j] = (uint32_t)w->prefix[j] >> SH;
+      int rep = j;
+#pragma unroll
+      for (int jj = NT - 1; jj >= 0; --jj)
+        if (jj < j && ((uint32_t)w->prefix[jj] >> SH) == cmp[j]) rep = jj;
+      if (threadIdx.x == 0) rep_s[j] = rep;
+      if (rep != j) cmp[j] = 0xffffffffu;
+    }
   }
   if (PASS == 1) mean_a = w->mean_all;
   if (PASS >= 3) thr_key = (uint32_t)w->prefix[1];
@@ -119,13 +133,13 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
       const uint32_t mid = (k >> L3_BITS) & (L2_BINS - 1);
 #pragma unroll
       for (int j = 0; j < NT; ++j)
-        if (top == (pfx[j] >> (32 - L1_BITS))) atomicAdd(&smem_hist[j * L2_BINS + mid], 1u);
+        if (top == cmp[j]) atomicAdd(&smem_hist[j * L2_BINS + mid], 1u);
     } else if (PASS == 2) {
       const uint32_t hi = k >> L3_BITS;
       const uint32_t lo = k & (L3_BINS - 1);
 #pragma unroll
       for (int j = 0; j < NT; ++j)
-        if (hi == (pfx[j] >> L3_BITS)) atomicAdd(&smem_hist[j * L3_BINS + lo], 1u);
+        if (hi == cmp[j]) atomicAdd(&smem_hist[j * L3_BINS + lo], 1u);
     } else if (PASS == 3) {
       if (k > thr_key) { a0 += (double)x; ++c0; }
       else if (k < thr_key) { a1 += (double)x; ++c1; }
@@ -187,8 +201,10 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
   if (HBINS > 0) {
     __syncthreads();
     long long* gh = PASS == 0 ? w->hist1 : PASS == 1 ? &w->hist2[0][0] : &w->hist3[0][0];
+    constexpr int BINS = PASS == 0 ? L1_BINS : PASS == 1 ? L2_BINS : L3_BINS;
     for (int i = threadIdx.x; i < HBINS; i += RS_THREADS) {
-      const unsigned int c = smem_hist[i];
+      const int j = i / BINS;
+      const unsigned int c = PASS == 0 ? smem_hist[i] : smem_hist[rep_s[j] * BINS + (i - j * BINS)];
       if (c) atomic_add_i64(gh + i, (long long)c);
     }
   }
