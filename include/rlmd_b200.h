@@ -346,6 +346,47 @@ int b200_menv_rollout(const b200_env_desc* desc, int64_t n_episodes, const doubl
                       void* stream);
 
 /* ------------------------------------------------------------------ *
+ * Market environments
+ *
+ * Sits behind envs/market_envs.py Market_Inv{A,B,C}_{D1,Dx}: reset(assets)
+ * :204-222 / :684-703 and step(action, next_assets) :133-202, :283-358,
+ * :440-528, :611-682, :765-841, :924-1013, with market_dones
+ * (tools/env_resources.py:140-200).  The wealth update of the multiplicative
+ * envs fed by historical prices: returns are next_assets / assets - 1 with
+ * `assets` the prices handed to reset() (the reference never advances them).
+ * ------------------------------------------------------------------ */
+#define B200_MARKET_MAX_ASSETS 128
+
+typedef struct b200_market_desc {
+  int32_t investor;     /* B200_INV_A / _B / _C                                   */
+  int32_t n_assets;     /* 1..128                                                 */
+  int32_t obs_days;     /* 1 = the _D1 classes; > 1 = _Dx (state holds the history) */
+  int32_t time_length;  /* step count that ends an episode (_Dx: the caller passes
+                           time_length - obs_days + 1, envs/market_envs.py:581)    */
+  double max_value, initial_value, min_value;      /* 1e34, 1e4, 100              */
+  double max_abs_action, min_reward, min_return;   /* 0.99, 1e-3, -0.9            */
+  double max_return, min_weight, lev_factor;       /* 1e10, 1e-5, 3               */
+} b200_market_desc;
+
+/* S = 4 + obs_days*n_assets, A = investor + n_assets, R as the reference's risk */
+int b200_market_dims(const b200_market_desc* desc, int32_t* state_dim, int32_t* action_dim,
+                     int32_t* risk_dim);
+
+/* assets_in [E, obs_days*n_assets] (observed_market_state of step 0) is copied to
+ * the env-owned `assets` [E, W]; wealth [E], time [E]; state [E,S] or NULL; mask
+ * [E] bytes or NULL = every env. */
+int b200_market_reset(const b200_market_desc* desc, int64_t n_envs, double* wealth,
+                      int32_t* time, const double* assets_in, double* assets, double* state,
+                      const uint8_t* mask, void* stream);
+
+/* action [E,A], next_assets [E,W]; next_state [E,S], reward [E], done [E,2] bytes
+ * (done, learn_done), risk [E,R].  wealth / time are updated in place. */
+int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealth,
+                     int32_t* time, const double* assets, const double* action,
+                     const double* next_assets, double* next_state, double* reward,
+                     uint8_t* done, double* risk, void* stream);
+
+/* ------------------------------------------------------------------ *
  * Growth-rate summaries (engine-added)
  *
  * The reference forms the time-average growth rate only as the env reward

@@ -57,6 +57,33 @@ def dims(family: str, investor: str, n_gambles: int):
     return 4 + n_gambles, extra + n_gambles, risk
 
 
+def np_sum_rows(x: np.ndarray) -> np.ndarray:
+    """
+    Row sums of x [E,n] in the order np.sum uses on ONE contiguous fp64 row (the
+    reference sums per-env vectors): NumPy's pairwise_sum - left to right below
+    8 elements, 8 running partial sums from 8 on (n <= 128).  Checked against
+    np.sum itself in tests/test_oracle_env.py.
+    """
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[1]
+    if n < 8:
+        res = x[:, 0].copy()
+        for i in range(1, n):
+            res = res + x[:, i]
+        return res
+    r = [x[:, j].copy() for j in range(8)]
+    i = 8
+    while i < n - (n % 8):
+        for j in range(8):
+            r[j] = r[j] + x[:, i + j]
+        i += 8
+    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+    while i < n:
+        res = res + x[:, i]
+        i += 1
+    return res
+
+
 class BatchedEnv:
     """E lock-step copies of one reference env class (family, investor, n_gambles)."""
 
@@ -112,9 +139,7 @@ class BatchedEnv:
             o = {"A": 0, "B": 1, "C": 2}[inv]
             r = np.asarray(r, dtype=np.float64).reshape(E, n)
             levs = action[:, o:] * c["eta"]
-            total = (levs[:, 0] * r[:, 0]).copy()
-            for i in range(1, n):  # np.sum over < 8 elements adds left to right
-                total = total + levs[:, i] * r[:, i]
+            total = np_sum_rows(levs * r)
             if self.family == "gbm":
                 step_return = np.maximum(total, c["min_return"])
                 factor = np.minimum(np.exp(step_return), 1 + MAX_RETURN)
@@ -160,10 +185,7 @@ class BatchedEnv:
             done = done | (active == 0)
         learn_done = done & ~done_state
 
-        mean_lev = levs[:, 0].copy()
-        for i in range(1, levs.shape[1]):
-            mean_lev = mean_lev + levs[:, i]
-        mean_lev = mean_lev / levs.shape[1]
+        mean_lev = np_sum_rows(levs) / levs.shape[1]
         if self.family == "dice_sh":
             cols = [reward, wealth, step_return, levs[:, 0], stop if stop is not None else nan,
                     retention if retention is not None else nan, lev_sh]

@@ -88,6 +88,27 @@ class ReplayDesc(C.Structure):
     ]
 
 
+class MarketDesc(C.Structure):
+    _fields_ = [
+        ("investor", C.c_int32),
+        ("n_assets", C.c_int32),
+        ("obs_days", C.c_int32),
+        ("time_length", C.c_int32),
+        ("max_value", C.c_double),
+        ("initial_value", C.c_double),
+        ("min_value", C.c_double),
+        ("max_abs_action", C.c_double),
+        ("min_reward", C.c_double),
+        ("min_return", C.c_double),
+        ("max_return", C.c_double),
+        ("min_weight", C.c_double),
+        ("lev_factor", C.c_double),
+    ]
+
+
+MARKET_MAX_ASSETS = 128
+
+
 class CollectDesc(C.Structure):
     _fields_ = [
         ("env", EnvDesc),
@@ -147,6 +168,9 @@ _SIGNATURES = {
                                          C.c_double, C.POINTER(C.c_double), _i32, _i64, C.c_double, _vp]),
     "b200_replay_sample": (C.c_int, [C.POINTER(ReplayDesc), _vp, _i64, _i32, _i64, _i32, C.POINTER(C.c_float), _i32,
                                      C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_market_dims": (C.c_int, [C.POINTER(MarketDesc)] + [C.POINTER(_i32)] * 3),
+    "b200_market_reset": (C.c_int, [C.POINTER(MarketDesc), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_market_step": (C.c_int, [C.POINTER(MarketDesc), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_collect_reset": (C.c_int, [C.POINTER(CollectDesc), _vp, _vp, _vp, _vp, _vp]),
     "b200_collect_step": (C.c_int, [C.POINTER(CollectDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_collect_sample": (C.c_int, [C.POINTER(CollectDesc), _vp, _i64, _i32, _i32, C.POINTER(C.c_float), _i32,

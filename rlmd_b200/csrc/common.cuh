@@ -133,6 +133,29 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   z1 = rho * s;
 }
 
+// np.sum / np.mean of a contiguous fp64 vector: NumPy's pairwise_sum
+// (numpy/core/src/umath/loops_utils.h.src) for n <= PW_BLOCKSIZE (128) - plain
+// left-to-right below 8 elements, 8 running partial sums from 8 on.  The envs'
+// exact-equality termination tests need the reference's summation order.
+template <typename F>
+__device__ __forceinline__ double np_sum(int n, F term) {
+  if (n < 8) {
+    double res = term(0);
+    for (int i = 1; i < n; ++i) res = res + term(i);
+    return res;
+  }
+  double r0 = term(0), r1 = term(1), r2 = term(2), r3 = term(3), r4 = term(4), r5 = term(5), r6 = term(6),
+         r7 = term(7);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
+    r0 = r0 + term(i); r1 = r1 + term(i + 1); r2 = r2 + term(i + 2); r3 = r3 + term(i + 3);
+    r4 = r4 + term(i + 4); r5 = r5 + term(i + 5); r6 = r6 + term(i + 6); r7 = r7 + term(i + 7);
+  }
+  double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+  for (; i < n; ++i) res = res + term(i);
+  return res;
+}
+
 // -------------------------------------------------------------- reductions
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -86,8 +86,7 @@ __device__ __forceinline__ void env_step_core(const b200_env_desc& d, const doub
     factor = 1 + step_return;
   } else {
     for (int i = 0; i < n; ++i) lev[i] = a[off + i] * d.lev_factor;
-    double total = lev[0] * r[0];
-    for (int i = 1; i < n; ++i) total = total + lev[i] * r[i];
+    const double total = np_sum(n, [&](int i) { return lev[i] * r[i]; });   // np.sum(lev * r)
     if (gbm) {
       step_return = fmax(total, d.min_return);
       factor = fmin(exp(step_return), 1 + d.max_return);
@@ -154,9 +153,7 @@ __device__ __forceinline__ void env_step_core(const b200_env_desc& d, const doub
     rk[5] = has_ret ? retention : qnan;
     rk[6] = lev_sh;
   } else {
-    double m = lev[0];
-    for (int i = 1; i < n; ++i) m = m + lev[i];
-    rk[3] = m / (double)n;
+    rk[3] = np_sum(n, [&](int i) { return lev[i]; }) / (double)n;           // np.mean(lev)
     int c = 4;
     if (has_stop) rk[c++] = stop;
     if (has_ret) rk[c++] = retention;

@@ -101,6 +101,7 @@ ENV_CASES = [
     ("coin_B2", "envs.coin_flip_envs", "Coin_InvB", "coin", "B", 2),
     ("coin_C1", "envs.coin_flip_envs", "Coin_InvC", "coin", "C", 1),
     ("coin_C3", "envs.coin_flip_envs", "Coin_InvC", "coin", "C", 3),
+    ("coin_A8", "envs.coin_flip_envs", "Coin_InvA", "coin", "A", 8),     # n >= 8: NumPy's pairwise np.sum order
     ("dice_A1", "envs.dice_roll_envs", "Dice_InvA", "dice", "A", 1),
     ("dice_B2", "envs.dice_roll_envs", "Dice_InvB", "dice", "B", 2),
     ("dice_C1", "envs.dice_roll_envs", "Dice_InvC", "dice", "C", 1),
@@ -249,3 +250,54 @@ def bigbrain_lev_factor(case: dict):
 
 
 GALAXY_GRID = (0.2, 0.8, 0.05, 0.2, 0.8, 0.05, 0.25, 0.75, 0.25)   # ru, rd, pu (low, high, incr)
+
+
+# -------------------------------------------------------------------- market
+# (fixture name, investor, history (Dx), n_assets, obs_days, time_length, steps)
+MARKET_CASES = [
+    ("A_D1_n1", "A", False, 1, 1, 40, 400),
+    ("B_D1_n3", "B", False, 3, 1, 60, 400),
+    ("C_D1_n9", "C", False, 9, 1, 50, 400),        # n >= 8: NumPy's pairwise summation order
+    ("A_Dx_n3_d5", "A", True, 3, 5, 45, 300),
+    ("B_Dx_n1_d3", "B", True, 1, 3, 30, 300),
+    ("C_Dx_n26_d4", "C", True, 26, 4, 40, 120),
+]
+
+
+def market_case(name: str):
+    for c in MARKET_CASES:
+        if c[0] == name:
+            return c
+    raise KeyError(name)
+
+
+def market_inputs(case):
+    """
+    Seeded inputs of one market fixture: a price history [L, n] (geometric random
+    walk, 2 % daily volatility) and actions [T, A]; a few actions are saturated /
+    vanishing so that every termination rule fires.
+    """
+    name, investor, history, n, d, tl, steps = case
+    seed = int(hashlib.sha256(("market_" + name).encode()).hexdigest()[:8], 16)
+    rs = np.random.RandomState(seed)
+    a_dim = {"A": 0, "B": 1, "C": 2}[investor] + n
+    length = 4000
+    prices = 100.0 * np.exp(np.cumsum(0.02 * rs.standard_normal((length, n)), axis=0))
+    actions = rs.uniform(-0.99, 0.99, size=(steps, a_dim))
+    special = rs.random_sample(steps)
+    actions[special < 0.02] = 0.99
+    actions[(special >= 0.02) & (special < 0.04)] = 1e-8
+    return prices, actions
+
+
+def market_observed(extract: np.ndarray, time_step: int, obs_days: int) -> np.ndarray:
+    """tools/env_resources.py:203-226 with action_days = 1."""
+    if obs_days == 1:
+        return extract[time_step]
+    hi = time_step + obs_days if time_step > 0 else obs_days
+    return extract[time_step:hi].reshape(-1)[::-1]
+
+
+def market_episode_start(k: int, length: int, time_length: int, obs_days: int) -> int:
+    """First row of the k-th episode's market extract (deterministic stand-in for time_slice)."""
+    return (977 * k) % (length - time_length - 2 * obs_days - 8)
