@@ -387,6 +387,23 @@ int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealt
                      uint8_t* done, double* risk, void* stream);
 
 /* ------------------------------------------------------------------ *
+ * Multi-GPU statistics exchange
+ *
+ * After phase p of b200_rowstats / b200_growth_summary every rank must sum, per
+ * row, the integer words [int_offset, +int_count) and the double words
+ * [dbl_offset, +dbl_count) of its workspace with its peers (the *_exchange calls
+ * name them).  pack gathers both regions of all rows into ONE contiguous fp64
+ * buffer staging[rows, int_count + dbl_count] (counts are < 2^53: exact), the
+ * caller all-reduces it (one NCCL call per phase), unpack scatters it back.
+ * ------------------------------------------------------------------ */
+int b200_exchange_pack(const void* workspace, int64_t words_per_row, int64_t rows,
+                       int64_t int_offset, int64_t int_count, int64_t dbl_offset,
+                       int64_t dbl_count, double* staging, void* stream);
+int b200_exchange_unpack(void* workspace, int64_t words_per_row, int64_t rows,
+                         int64_t int_offset, int64_t int_count, int64_t dbl_offset,
+                         int64_t dbl_count, const double* staging, void* stream);
+
+/* ------------------------------------------------------------------ *
  * Growth-rate summaries (engine-added)
  *
  * The reference forms the time-average growth rate only as the env reward

@@ -58,6 +58,25 @@ def exchange_phases(run_phase: Callable[[int], None], workspace: torch.Tensor, g
     """
     import torch.distributed as dist
 
+    if workspace.is_cuda:
+        # one packed fp64 all-reduce per phase (pack / unpack kernels of the C ABI)
+        from ._lib import ptr, stream_ptr
+
+        rows, words = workspace.shape
+        with torch.cuda.device(workspace.device):
+            for phase in range(n_phases):
+                run_phase(phase)
+                io, ic, do, dc, _ = exchange_words(phase, what)
+                if ic + dc == 0:
+                    continue
+                staging = torch.empty((rows, ic + dc), dtype=torch.float64, device=workspace.device)
+                check(lib.b200_exchange_pack(ptr(workspace), words, rows, io, ic, do, dc, ptr(staging), stream_ptr()))
+                dist.all_reduce(staging, group=group)
+                check(lib.b200_exchange_unpack(ptr(workspace), words, rows, io, ic, do, dc, ptr(staging),
+                                               stream_ptr()))
+        return
+
+    # host tensors (gloo, the CPU tests of this module): the same exchange, region by region
     ws_f = workspace.view(torch.float64)
     for phase in range(n_phases):
         run_phase(phase)

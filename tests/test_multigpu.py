@@ -122,3 +122,32 @@ def test_two_ranks_equal_one(tmp_path):
                            horizon=257, mode="chain", seed=9, probs=(1 / 6, 1 / 6, 2 / 3))["data_T"].cpu().numpy()
     two = np.concatenate([np.load(tmp_path / f"phx{r}.npy") for r in range(world)], axis=1)
     assert np.array_equal(one.view(np.uint32), two.view(np.uint32))
+
+
+def test_exchange_pack_unpack_round_trip():
+    """The packed fp64 staging buffer carries integer and double words exactly."""
+    from rlmd_b200 import sharding
+    from rlmd_b200._lib import check, lib, ptr, stream_ptr
+
+    rs = np.random.RandomState(1)
+    rows = 7
+    for what, phases in (("rowstats", 6), ("growth", 7)):
+        words = sharding.exchange_words(0, what)[4]
+        src = torch.from_numpy(rs.randint(0, 2 ** 40, size=(rows, words)).astype(np.int64)).cuda()
+        for phase in range(phases):
+            io, ic, do, dc, _ = sharding.exchange_words(phase, what)
+            if ic + dc == 0:
+                continue
+            src_f = src.view(torch.float64)
+            src_f[:, do:do + dc] = torch.from_numpy(rs.standard_normal((rows, dc))).cuda()
+            staging = torch.empty((rows, ic + dc), dtype=torch.float64, device="cuda")
+            check(lib.b200_exchange_pack(ptr(src), words, rows, io, ic, do, dc, ptr(staging), stream_ptr()))
+            assert torch.equal(staging[:, :ic], src[:, io:io + ic].double())
+            dst = torch.zeros_like(src)
+            check(lib.b200_exchange_unpack(ptr(dst), words, rows, io, ic, do, dc, ptr(staging * 2), stream_ptr()))
+            assert torch.equal(dst[:, io:io + ic], 2 * src[:, io:io + ic])
+            assert torch.equal(dst.view(torch.float64)[:, do:do + dc], 2 * src_f[:, do:do + dc])
+            untouched = torch.ones(words, dtype=torch.bool)
+            untouched[io:io + ic] = False
+            untouched[do:do + dc] = False
+            assert int(dst[:, untouched.cuda()].abs().sum()) == 0
