@@ -211,29 +211,42 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
 }
 
 // One block per row: walk a histogram to find the bin that holds `rank`.
+// blockDim.x == 256: each thread sums a contiguous run of bins, a block-wide
+// inclusive scan of the 256 partials (warp shuffles + 8 warp totals) names the
+// thread whose run holds the rank, and that thread walks its <= 8 bins.
 __device__ void find_bin(const long long* __restrict__ hist, int bins, long long rank, int* bin_out,
-                         long long* rem_out, long long* scratch /* >= 1024+1 */) {
-  // blockDim.x == 256; each thread sums a contiguous run of bins, then a serial
-  // scan over 256 partials by thread 0 (tiny), then the owner thread refines.
+                         long long* rem_out, long long* scratch /* >= 8 */) {
   const int per = bins / 256;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   long long local = 0;
   for (int i = 0; i < per; ++i) local += hist[threadIdx.x * per + i];
-  scratch[threadIdx.x] = local;
+  long long incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  __syncthreads();  // scratch may still be read by a previous call
+  if (lane == 31) scratch[wid] = incl;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    long long acc = 0;
-    int owner = 255;
-    long long before = 0;
-    for (int t = 0; t < 256; ++t) {
-      if (rank < acc + scratch[t]) { owner = t; before = acc; break; }
-      acc += scratch[t];
-      before = acc;
-    }
-    long long r = rank - before;
-    int b = owner * per;
+  long long before_warp = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const long long t = scratch[w];
+    if (w < wid) before_warp += t;
+    total += t;
+  }
+  incl += before_warp;
+  const long long excl = incl - local;
+  // the run that holds the rank; a rank beyond the total (cannot happen for
+  // consistent counts) is given to the last thread
+  const bool owner = (rank >= excl && rank < incl) || (threadIdx.x == 255 && rank >= total);
+  if (owner) {
+    long long r = rank - excl;
+    int b = threadIdx.x * per;
     for (int i = 0; i < per; ++i) {
-      const long long c = hist[owner * per + i];
-      if (r < c || i == per - 1) { b = owner * per + i; break; }
+      const long long c = hist[threadIdx.x * per + i];
+      if (r < c || i == per - 1) { b = threadIdx.x * per + i; break; }
       r -= c;
     }
     *bin_out = b;
