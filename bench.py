@@ -326,11 +326,24 @@ def run_gpu(args):
     # ---- end to end: pinned host outcomes -> H2D (overlapped with the sweep) -> statistics -> host
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((n, h), dtype=torch.uint8, pin_memory=True)
-        host.copy_(outcomes)
+        n_host = n
+        while True:   # 10 GB of pinned memory per rank; halve the e2e sample if the host refuses to pin that much
+            try:
+                host = torch.empty((n_host, h), dtype=torch.uint8, pin_memory=True)
+                break
+            except RuntimeError:
+                n_host //= 2
+                if n_host < 1000:
+                    raise
+        host.copy_(outcomes[:n_host])
         torch.cuda.synchronize()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        kw = dict(mode="log", device=dev, group=group, n_total=n_total)
+        if world > 1:   # every rank must run the same sample size (the statistics are collective)
+            t = torch.tensor([n_host], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            n_host = int(t[0])
+            host = host[:n_host]
+        kw = dict(mode="log", device=dev, group=group, n_total=n_host * world)
         engine.lev_final_host("discrete", table, V0, top_total, host, **kw)  # warm-up
         torch.cuda.synchronize()
         if world > 1:
@@ -347,7 +360,8 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t[0])
         e2e = {
-            "value": n_total * h * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * h,
+            "value": n_host * world * h * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_host * h,
+            "investors_per_gpu": n_host,
             "d2h_bytes_per_step": int(st.nbytes), "steps": e2e_steps,
             "note": "per-rank pinned uint8 outcomes copied H2D in 256 MiB row chunks overlapped with the sweep; "
                     "statistics read back to the host every step",

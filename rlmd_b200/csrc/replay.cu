@@ -337,6 +337,88 @@ replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, 
   }
 }
 
+// Narrow rows (state_dim < 32, the multiplicative envs' 5..12 floats): one THREAD
+// per sample.  Every load of a sample that does not depend on another one is
+// issued before the first use, so a resident warp keeps 32 samples x ~12 loads in
+// flight (the lane-group kernel above keeps 4): the gather is a chain of three
+// dependent memory latencies (slot -> bookkeeping -> rows), and throughput is
+// the number of chains in flight.  Same arithmetic, term by term.
+__global__ void __launch_bounds__(256)
+replay_gather_thread_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, int64_t n_samples,
+                            int64_t filled_arg, int64_t lanes, int64_t lane_len, int32_t n_steps, int32_t additive,
+                            const __grid_constant__ GammaPow gp, float* __restrict__ out_state,
+                            float* __restrict__ out_action, float* __restrict__ out_reward,
+                            float* __restrict__ out_next_state, uint8_t* __restrict__ out_done,
+                            int64_t* __restrict__ out_eff) {
+  const int S = d.state_dim, A = d.action_dim;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_samples;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t slot = idx[q];
+    const int64_t lane_id = (slot >= 0 && lanes > 1) ? slot % lanes : 0;
+    const int64_t i = (slot >= 0 && lanes > 1) ? slot / lanes : slot;
+    auto at = [&](int64_t j) { return j * lanes + lane_id; };
+    const int64_t* __restrict__ hdr = d.header + lane_id * 8;
+    const int64_t filled = filled_arg >= 0 ? filled_arg : min(hdr[H_MEM_IDX], lane_len);
+    const int64_t episodes = hdr[H_EPISODES], e0 = hdr[H_E0], elast = hdr[H_ELAST];
+    const bool ok = slot >= 0 && i < filled;
+    int64_t first = ok ? i : 0;
+    int eff = ok ? 1 : 0;
+    float R = 0.0f;
+    uint8_t term = 0;
+    const float* src_state = d.state_memory;
+    if (ok) {
+      // independent of each other: issued together
+      term = d.terminal_memory[at(i)];
+      const int32_t es = d.episode_start[at(i)];
+      const float ri = d.reward_memory[at(i)];
+      if (n_steps <= 1) {
+        R = ri;
+      } else {
+        int64_t start, len;
+        if (episodes == 0 || i <= e0) { start = 0; len = i + 1; }
+        else if (i <= elast) { start = es; len = i - start + 1 + (term ? 0 : 1); }
+        else { start = 0; len = min(i - elast + 1, e0 + 1); }
+        eff = (int)min(len, (int64_t)n_steps);
+        first = start + len - eff;
+        src_state = d.next_state_memory;
+        float acc = additive ? 0.0f : 1.0f;
+        for (int t0 = 0; t0 < eff - 1; t0 += 8) {
+          float rw[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) rw[u] = (t0 + u < eff - 1) ? d.reward_memory[at(first + t0 + u)] : 0.0f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (t0 + u < eff - 1) {
+              const float x = gp.v[t0 + u] * rw[u];
+              acc = additive ? acc + x : acc * x;
+            }
+          }
+        }
+        R = acc;
+      }
+    }
+    const float* __restrict__ rs = src_state + at(first) * S;
+    const float* __restrict__ rn = d.next_state_memory + (ok ? at(i) : 0) * S;
+    const float* __restrict__ ra = d.action_memory + at(first) * A;
+    for (int c0 = 0; c0 < S; c0 += 8) {
+      float vs[8], vn[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool in = ok && c0 + u < S;
+        vs[u] = in ? rs[c0 + u] : 0.0f;
+        vn[u] = in ? rn[c0 + u] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u < S) { out_state[q * S + c0 + u] = vs[u]; out_next_state[q * S + c0 + u] = vn[u]; }
+    }
+    for (int c = 0; c < A; ++c) out_action[q * A + c] = ok ? ra[c] : 0.0f;
+    out_reward[q] = R;
+    out_done[q] = term;
+    out_eff[q] = eff;
+  }
+}
+
 static int check_desc(const b200_replay_desc* d) {
   B200_REQUIRE(d != nullptr, "replay: desc is NULL");
   B200_REQUIRE(d->mem_size > 0 && d->mem_size < (1ll << 31), "replay: mem_size %lld outside 1..2^31-1",
@@ -460,18 +542,19 @@ int replay_sample_lanes(const b200_replay_desc* d, int64_t lanes, int64_t lane_l
   }
   GammaPow gp;
   for (int t = 0; t < B200_REPLAY_MAX_STEPS; ++t) gp.v[t] = (multi_steps > 1 && t < multi_steps) ? gamma_pow_host[t] : 0.0f;
-  const int wide = d->state_dim >= 32;
-  const int width = wide ? 32 : 8;
-  const int64_t want_blocks = (n_samples * width + 255) / 256;
-  const int grid = (int)std::min<int64_t>(want_blocks, (int64_t)sm_count() * 8);
-  if (wide)
+  if (d->state_dim >= 32) {
+    const int64_t want_blocks = (n_samples * 32 + 255) / 256;
+    const int grid = (int)std::min<int64_t>(want_blocks, (int64_t)sm_count() * 8);
     replay_gather_kernel<32><<<grid, 256, 0, st>>>(*d, idx, n_samples, filled, lanes, lane_len, multi_steps, additive,
                                                     gp, out_state, out_action, out_reward, out_next_state, out_done,
                                                     out_eff);
-  else
-    replay_gather_kernel<8><<<grid, 256, 0, st>>>(*d, idx, n_samples, filled, lanes, lane_len, multi_steps, additive,
-                                                   gp, out_state, out_action, out_reward, out_next_state, out_done,
-                                                   out_eff);
+  } else {
+    const int64_t want_blocks = (n_samples + 255) / 256;
+    const int grid = (int)std::min<int64_t>(want_blocks, (int64_t)sm_count() * 8);
+    replay_gather_thread_kernel<<<grid, 256, 0, st>>>(*d, idx, n_samples, filled, lanes, lane_len, multi_steps,
+                                                      additive, gp, out_state, out_action, out_reward, out_next_state,
+                                                      out_done, out_eff);
+  }
   B200_CUDA(cudaGetLastError());
   return 0;
 }

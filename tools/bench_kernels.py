@@ -169,12 +169,20 @@ def main():
                 b1, m1 = timeit(lambda: buf.sample_exp(), warm=5, reps=50)
                 k = 1024
                 bk, mk = timeit(lambda: buf.sample_many(k), warm=2, reps=10)
+                k2 = 16384        # 4.2e6 (batch 256) samples per launch: the kernels, not the Python call, set the time
+                bk2, _ = timeit(lambda: buf.sample_many(k2), warm=2, reps=10)
+                pre = torch.randint(0, mem, (k2, batch), device="cuda")
+                bg, _ = timeit(lambda: buf.sample_many(k2, batches=pre), warm=2, reps=10)
                 bytes_per = 106 if nstep == 1 else 114 + 4 * (nstep - 1)
                 print(json.dumps(dict(kernel="replay", n_step=nstep, batch=batch, buffer=mem, store_1e6_s=store_s,
                                       stores_per_s=mem / store_s, sample_call_us=b1 * 1e6, samples_per_s_one_call=batch / b1,
                                       many_batches=k, samples_per_s_many=k * batch / bk,
                                       algorithmic_GBps_many=k * batch * bytes_per / bk / 1e9,
-                                      hbm_frac_many=k * batch * bytes_per / bk / 1e9 / hbm)), flush=True)
+                                      hbm_frac_many=k * batch * bytes_per / bk / 1e9 / hbm,
+                                      samples_per_s_16384_batches=k2 * batch / bk2,
+                                      gather_only_samples_per_s=k2 * batch / bg,
+                                      gather_only_algorithmic_GBps=k2 * batch * bytes_per / bg / 1e9,
+                                      gather_only_hbm_frac=k2 * batch * bytes_per / bg / 1e9 / hbm)), flush=True)
                 del buf, st
     if a.only in ("", "collect"):
         # fused collector: env step + append per environment (one kernel), then an n-step sample of 256;
