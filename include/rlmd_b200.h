@@ -149,7 +149,7 @@ int64_t b200_rowstats_workspace_bytes(int64_t rows);
 /* values: float [rows, ld] (row r at values + r*ld), n valid entries per row.
  * n_total / top describe the GLOBAL vector when the rows are investor shards
  * (multi-GPU): single-GPU callers pass n_total = n.
- * phase = -1 runs every pass back to back (single GPU).  phase = 0..5 runs
+ * phase = -1 runs every pass back to back (single GPU).  phase = 0..4 runs
  * one pass; between passes a multi-GPU caller all-reduces (SUM) the
  * workspace's exchange region (see b200_rowstats_exchange) across ranks. */
 int b200_rowstats(const float* values, int64_t rows, int64_t n, int64_t ld,

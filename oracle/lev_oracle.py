@@ -190,7 +190,9 @@ def group_stats(v: np.ndarray):
     if not np.isfinite(v64).all():
         # torch.std_mean runs Welford's update: one inf (then inf - inf) makes the
         # mean, hence std and MAD, nan (seen in tests/golden/lev_coin_overflow.npz)
-        return float("nan"), float("nan"), float("nan"), med
+        # (a one-element group keeps its element as the mean: the first update is exact)
+        mean = float(v64[0]) if v64.shape[0] == 1 else float("nan")
+        return mean, float("nan"), float("nan"), med
     with np.errstate(over="ignore", invalid="ignore"):
         mean = v64.mean()
         mad = np.abs(v64 - mean).mean()

@@ -1,6 +1,6 @@
 """
 TEST INFRASTRUCTURE ONLY - NumPy restatement of the PASS STRUCTURE of
-rlmd_b200/csrc/rowstats.cu (the five streaming passes + the resolve steps of the
+rlmd_b200/csrc/rowstats.cu (the four streaming passes + the resolve steps of the
 3-level radix select), writing its partial sums / histograms at the same
 workspace words the CUDA kernels use (b200_rowstats_exchange).
 
@@ -38,7 +38,7 @@ def _find_bin(hist: np.ndarray, rank: int):
 
 
 class RowStatsPasses:
-    """run(phase) for phases 0..5 on `values` [rows, n_local]; `ws` is the int64 [rows, words] workspace."""
+    """run(phase) for phases 0..4 on `values` [rows, n_local]; `ws` is the int64 [rows, words] workspace."""
 
     def __init__(self, values: np.ndarray, n_total: int, top: int, ws: np.ndarray, offsets: dict):
         self.v = np.ascontiguousarray(values, dtype=np.float32)
@@ -94,10 +94,17 @@ class RowStatsPasses:
                     self.prefix[r, j] |= np.uint64(b << L3)
                     self.rank[r, j] = rem
                 low = (k & np.uint64((1 << L3) - 1)).astype(np.int64)
+                hi = k >> np.uint64(L3)
                 for j in range(NT):
-                    sel = (k >> np.uint64(L3)) == (self.prefix[r, j] >> np.uint64(L3))
+                    sel = hi == (self.prefix[r, j] >> np.uint64(L3))
                     lo = off["h3"] + j * (1 << L3)
                     I[lo:lo + (1 << L3)] = np.bincount(low[sel], minlength=1 << L3)
+                # coarse split about thr's 22-bit prefix (the rest comes from thr's level-3 bins)
+                thr_hi = self.prefix[r, 1] >> np.uint64(L3)
+                gt, lt = hi > thr_hi, hi < thr_hi
+                with np.errstate(invalid="ignore"):
+                    D[3], D[4] = x[gt].sum(), x[lt].sum()
+                I[off["cnt"]] = int(gt.sum())     # the count below follows from the total (phase 3)
             elif phase == 3:
                 for j in range(NT):
                     lo = off["h3"] + j * (1 << L3)
@@ -105,21 +112,33 @@ class RowStatsPasses:
                     self.prefix[r, j] |= np.uint64(b)
                     self.rank[r, j] = rem
                     self.value[r, j] = key_float(int(self.prefix[r, j]))
-                thr = self.prefix[r, 1]
-                gt, lt = k > thr, k < thr
-                with np.errstate(invalid="ignore"):
-                    D[3], D[4] = x[gt].sum(), x[lt].sum()
-                I[off["cnt"]], I[off["cnt"] + 1] = int(gt.sum()), int(lt.sum())
-            elif phase == 4:
-                thr_v = self.value[r, 1]
-                n_eq = n - int(I[off["cnt"]]) - int(I[off["cnt"] + 1])
-                tt = K - int(I[off["cnt"]])
-                self.ties[r] = [tt, n_eq - tt]
-                self.mean[r, 1] = (D[3] + (tt * thr_v if tt > 0 else 0.0)) / K
-                self.mean[r, 2] = (D[4] + ((n_eq - tt) * thr_v if n_eq - tt > 0 else 0.0)) / (n - K)
-                thr = self.prefix[r, 1]
-                gt, lt = k > thr, k < thr
+                thr = int(self.prefix[r, 1])
+                thr_lo, base = thr & ((1 << L3) - 1), thr & ~((1 << L3) - 1)
+                h3 = I[off["h3"] + (1 << L3):off["h3"] + 2 * (1 << L3)]
+                n_gt, s_gt, s_lt = int(I[off["cnt"]]), D[3], D[4]
+                n_lt = n - n_gt - int(h3.sum())
+                f_gt = f_lt = 0.0
+                c_gt = c_lt = 0
                 with np.errstate(invalid="ignore", over="ignore"):
+                    for lo in np.nonzero(h3)[0]:
+                        c = int(h3[lo])
+                        if lo > thr_lo:
+                            f_gt, c_gt = f_gt + c * key_float(base | int(lo)), c_gt + c
+                        elif lo < thr_lo:
+                            f_lt, c_lt = f_lt + c * key_float(base | int(lo)), c_lt + c
+                    if c_gt:
+                        s_gt = s_gt + f_gt
+                    if c_lt:
+                        s_lt = s_lt + f_lt
+                n_gt, n_lt = n_gt + c_gt, n_lt + c_lt
+                thr_v = self.value[r, 1]
+                n_eq = n - n_gt - n_lt
+                tt = K - n_gt
+                self.ties[r] = [tt, n_eq - tt]
+                with np.errstate(invalid="ignore", over="ignore"):
+                    self.mean[r, 1] = (s_gt + (tt * thr_v if tt > 0 else 0.0)) / K
+                    self.mean[r, 2] = (s_lt + ((n_eq - tt) * thr_v if n_eq - tt > 0 else 0.0)) / (n - K)
+                    gt, lt = k > np.uint64(thr), k < np.uint64(thr)
                     dt, da = x[gt] - self.mean[r, 1], x[lt] - self.mean[r, 2]
                     D[5], D[6], D[7], D[8] = np.abs(dt).sum(), (dt * dt).sum(), np.abs(da).sum(), (da * da).sum()
             else:
@@ -136,8 +155,11 @@ class RowStatsPasses:
                 with np.errstate(invalid="ignore"):
                     s[6:9] = [np.sqrt(D[2] / n), np.sqrt(sq_top / K), np.sqrt(sq_adj / (n - K))]
                 s[9:12] = [self.value[r, 0], self.value[r, 2], self.value[r, 3]]
+                size = (n, K, n - K)
+                single = (np.nan, self.value[r, 1], self.value[r, 3])
                 for j in range(3):
                     if self.nonfinite[r, j]:
-                        s[j] = s[3 + j] = s[6 + j] = np.nan
+                        s[j] = single[j] if size[j] == 1 else np.nan
+                        s[3 + j] = s[6 + j] = np.nan
                     if self.has_nan[r, j]:
                         s[9 + j] = np.nan

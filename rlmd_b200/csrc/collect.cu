@@ -56,6 +56,7 @@ collect_reset_kernel(const __grid_constant__ b200_collect_desc c, double* __rest
   for (int i = 0; i < 8; ++i) c.replay.header[e * 8 + i] = 0;
 }
 
+template <int NG>
 __global__ void __launch_bounds__(128)
 collect_step_kernel(const __grid_constant__ b200_collect_desc c, double* __restrict__ wealth,
                     int32_t* __restrict__ time, double* __restrict__ cur_state, const double* __restrict__ action,
@@ -66,18 +67,20 @@ collect_step_kernel(const __grid_constant__ b200_collect_desc c, double* __restr
   const b200_env_desc& d = c.env;
   int S, A, R;
   env_dims_dev(d, S, A, R);
-  const int n = d.family == B200_ENV_DICE_SH ? 1 : d.n_gambles;
-  double r[ENV_MAX_GAMBLES];
+  using Dm = EnvDims<NG>;
+  const int n = NG > 0 ? NG : d.n_gambles;
+  double r[Dm::G];
   if (r_in != nullptr) {
-    for (int i = 0; i < n; ++i) r[i] = r_in[e * n + i];
+    copy_n<Dm::G>(r, r_in + e * n, n);
   } else {
     env_draw_returns(d, e, (uint64_t)counter[CTR_STEP], n, r);
   }
-  const double* a = action + e * A;
+  double a[Dm::A];
+  copy_n<Dm::A>(a, action + e * A, A);
   double* st = cur_state + e * S;
-  EnvStep o;
+  EnvStep<NG> o;
   const int t = time[e];
-  env_step_core(d, a, r, wealth[e], t, o);
+  env_step_core<NG>(d, a, r, wealth[e], t, o);
 
   // ---- append (state, action, reward, next_state, learn_done) to lane e
   const b200_replay_desc& m = c.replay;
@@ -85,11 +88,9 @@ collect_step_kernel(const __grid_constant__ b200_collect_desc c, double* __restr
   const int64_t pos = h[H_MEM_IDX];
   const int64_t local = pos % c.lane_len;
   const int64_t slot = local * c.n_envs + e;   // slot-major: the lanes' writes of one step coalesce
-  for (int i = 0; i < S; ++i) {
-    m.state_memory[slot * S + i] = (float)st[i];
-    m.next_state_memory[slot * S + i] = (float)o.ns[i];
-  }
-  for (int i = 0; i < A; ++i) m.action_memory[slot * A + i] = (float)a[i];
+  copy_n<Dm::S>(m.state_memory + slot * S, st, S);
+  copy_n<Dm::S>(m.next_state_memory + slot * S, o.ns, S);
+  copy_n<Dm::A>(m.action_memory + slot * A, a, A);
   m.reward_memory[slot] = (float)(o.reward > c.reward_floor ? o.reward : c.reward_floor);
   m.terminal_memory[slot] = o.learn_done ? 1 : 0;
   m.episode_start[slot] = (int32_t)h[H_RUN_START];
@@ -104,8 +105,7 @@ collect_step_kernel(const __grid_constant__ b200_collect_desc c, double* __restr
   // ---- outputs of the step, then carry the observation (auto-reset when done)
   if (reward_out != nullptr) reward_out[e] = o.reward;
   if (done_out != nullptr) { done_out[e * 2] = o.done ? 1 : 0; done_out[e * 2 + 1] = o.learn_done ? 1 : 0; }
-  if (risk_out != nullptr)
-    for (int i = 0; i < R; ++i) risk_out[e * R + i] = o.rk[i];
+  if (risk_out != nullptr) copy_n<Dm::R>(risk_out + e * R, o.rk, R);
   if (o.done) {
     wealth[e] = d.initial_value;
     time[e] = 1;
@@ -113,13 +113,14 @@ collect_step_kernel(const __grid_constant__ b200_collect_desc c, double* __restr
   } else {
     wealth[e] = o.w;
     time[e] = t + 1;
-    for (int i = 0; i < S; ++i) st[i] = o.ns[i];
+    copy_n<Dm::S>(st, o.ns, S);
   }
 }
 
 __global__ void counter_bump_kernel(int64_t* __restrict__ counter, int which) { counter[which] += 1; }
 
 // One evaluation episode per thread: constant action, until done or max_steps.
+template <int NG>
 __global__ void __launch_bounds__(128)
 rollout_kernel(const __grid_constant__ b200_env_desc d, int64_t E, const double* __restrict__ action,
                const double* __restrict__ r_in, int64_t r_stride_t, uint64_t draw_base, int32_t max_steps,
@@ -129,22 +130,23 @@ rollout_kernel(const __grid_constant__ b200_env_desc d, int64_t E, const double*
   if (e >= E) return;
   int S, A, R;
   env_dims_dev(d, S, A, R);
-  const int n = d.family == B200_ENV_DICE_SH ? 1 : d.n_gambles;
-  double a[ENV_MAX_GAMBLES + 2];
-  for (int i = 0; i < A; ++i) a[i] = action[e * A + i];
+  using Dm = EnvDims<NG>;
+  const int n = NG > 0 ? NG : d.n_gambles;
+  double a[Dm::A];
+  copy_n<Dm::A>(a, action + e * A, A);
   double w = d.initial_value;
-  EnvStep o;
+  EnvStep<NG> o;
   o.reward = 0.0;
   o.done = false;
   int step = 0;
   while (step < max_steps) {
-    double r[ENV_MAX_GAMBLES];
+    double r[Dm::G];
     if (r_in != nullptr) {
-      for (int i = 0; i < n; ++i) r[i] = r_in[(int64_t)step * r_stride_t + e * n + i];
+      copy_n<Dm::G>(r, r_in + (int64_t)step * r_stride_t + e * n, n);
     } else {
       env_draw_returns(d, e, draw_base + (uint64_t)step, n, r);
     }
-    env_step_core(d, a, r, w, step + 1, o);
+    env_step_core<NG>(d, a, r, w, step + 1, o);
     w = o.w;
     ++step;
     if (o.done) break;
@@ -152,9 +154,8 @@ rollout_kernel(const __grid_constant__ b200_env_desc d, int64_t E, const double*
   reward_out[e] = o.reward;
   steps_out[e] = step;
   if (step > 0) {
-    for (int i = 0; i < R; ++i) risk_out[e * R + i] = o.rk[i];
-    if (state_out != nullptr)
-      for (int i = 0; i < S; ++i) state_out[e * S + i] = o.ns[i];
+    copy_n<Dm::R>(risk_out + e * R, o.rk, R);
+    if (state_out != nullptr) copy_n<Dm::S>(state_out + e * S, o.ns, S);
   }
 }
 
@@ -201,8 +202,8 @@ extern "C" int b200_collect_step(const b200_collect_desc* c, double* wealth, int
   B200_REQUIRE(wealth && time && cur_state && action && counter, "collect_step: NULL buffer");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)((c->n_envs + 127) / 128);
-  collect_step_kernel<<<blocks, 128, 0, st>>>(*c, wealth, time, cur_state, action, returns_in, counter, reward, done,
-                                              risk);
+  B200_ENV_DISPATCH(env_ng(c->env), (collect_step_kernel<NG><<<blocks, 128, 0, st>>>(
+                                        *c, wealth, time, cur_state, action, returns_in, counter, reward, done, risk)));
   counter_bump_kernel<<<1, 1, 0, st>>>(counter, CTR_STEP);
   return check_cuda(cudaGetLastError(), "collect_step launch");
 }
@@ -236,7 +237,8 @@ extern "C" int b200_menv_rollout(const b200_env_desc* desc, int64_t n_episodes, 
   B200_REQUIRE(action && reward && steps && risk, "menv_rollout: NULL buffer");
   const int n = desc->family == B200_ENV_DICE_SH ? 1 : desc->n_gambles;
   const unsigned blocks = (unsigned)((n_episodes + 127) / 128);
-  rollout_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(*desc, n_episodes, action, returns_in, n_episodes * n,
-                                                           draw_base, max_steps, reward, steps, risk, last_state);
+  B200_ENV_DISPATCH(env_ng(*desc), (rollout_kernel<NG><<<blocks, 128, 0, (cudaStream_t)stream>>>(
+                                       *desc, n_episodes, action, returns_in, n_episodes * n, draw_base, max_steps,
+                                       reward, steps, risk, last_state)));
   return check_cuda(cudaGetLastError(), "menv_rollout launch");
 }

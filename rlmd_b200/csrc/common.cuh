@@ -137,11 +137,17 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
 // (numpy/core/src/umath/loops_utils.h.src) for n <= PW_BLOCKSIZE (128) - plain
 // left-to-right below 8 elements, 8 running partial sums from 8 on.  The envs'
 // exact-equality termination tests need the reference's summation order.
-template <typename F>
+// NG > 0: n == NG is a compile-time constant (the short form unrolls).
+template <int NG = 0, typename F>
 __device__ __forceinline__ double np_sum(int n, F term) {
-  if (n < 8) {
+  if (NG > 0 ? NG < 8 : n < 8) {
     double res = term(0);
-    for (int i = 1; i < n; ++i) res = res + term(i);
+    if (NG > 0) {
+#pragma unroll
+      for (int i = 1; i < (NG > 0 ? NG : 1); ++i) res = res + term(i);
+    } else {
+      for (int i = 1; i < n; ++i) res = res + term(i);
+    }
     return res;
   }
   double r0 = term(0), r1 = term(1), r2 = term(2), r3 = term(3), r4 = term(4), r5 = term(5), r6 = term(6),

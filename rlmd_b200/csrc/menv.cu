@@ -11,6 +11,8 @@
 // the reference's do; only exp/log in the reward differ in the last ulp.
 // Returns are injected (parity runs) or drawn with Philox4x32-10:
 //   counter = (env lo, env hi, draw_index lo, TAG_ENV + block), key = seed ^ draw_index hi.
+#include <algorithm>
+
 #include "menv_core.cuh"
 
 namespace b200 {
@@ -34,30 +36,65 @@ menv_reset_kernel(const __grid_constant__ b200_env_desc d, int64_t E, double* __
   }
 }
 
-__global__ void __launch_bounds__(128)
+// The [E, S] / [E, A] / [E, R] rows of a block's 128 environments are one
+// contiguous span each: they move between global and shared memory with
+// unit-stride accesses, a thread touches its own row in shared memory only.
+constexpr int MENV_THREADS = 128;
+
+__device__ __forceinline__ void span_to_smem(double* __restrict__ sm, const double* __restrict__ g, int64_t words) {
+  for (int64_t i = threadIdx.x; i < words; i += MENV_THREADS) sm[i] = __ldcs(g + i);
+}
+__device__ __forceinline__ void smem_to_span(double* __restrict__ g, const double* __restrict__ sm, int64_t words) {
+  for (int64_t i = threadIdx.x; i < words; i += MENV_THREADS) __stcs(g + i, sm[i]);
+}
+
+template <int NG>
+__global__ void __launch_bounds__(MENV_THREADS)
 menv_step_kernel(const __grid_constant__ b200_env_desc d, int64_t E, double* __restrict__ wealth,
                  int32_t* __restrict__ time, const double* __restrict__ action, const double* __restrict__ r_in,
                  uint64_t draw_index, double* __restrict__ next_state, double* __restrict__ reward_out,
                  uint8_t* __restrict__ done_out, double* __restrict__ risk, int S, int A, int R) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const int n = d.family == B200_ENV_DICE_SH ? 1 : d.n_gambles;
-  double r[ENV_MAX_GAMBLES];
+  using Dm = EnvDims<NG>;
+  extern __shared__ double stage[];   // MENV_THREADS * max(S, A, R) doubles
+  const int64_t e0 = (int64_t)blockIdx.x * MENV_THREADS;
+  const int64_t e = e0 + threadIdx.x;
+  const int64_t live = min((int64_t)MENV_THREADS, E - e0);   // environments of this block
+  const bool on = e < E;
+  const int n = NG > 0 ? NG : d.n_gambles;
+
+  // ---- actions (and injected returns) through shared memory
+  double a[Dm::A];
+  span_to_smem(stage, action + e0 * A, live * A);
+  __syncthreads();
+  if (on) copy_n<Dm::A>(a, stage + threadIdx.x * A, A);
+  __syncthreads();
+  double r[Dm::G];
   if (r_in != nullptr) {
-    for (int i = 0; i < n; ++i) r[i] = r_in[e * n + i];
-  } else {
+    span_to_smem(stage, r_in + e0 * n, live * n);
+    __syncthreads();
+    if (on) copy_n<Dm::G>(r, stage + threadIdx.x * n, n);
+    __syncthreads();
+  } else if (on) {
     env_draw_returns(d, e, draw_index, n, r);
   }
-  EnvStep o;
-  const int t = time[e];
-  env_step_core(d, action + e * A, r, wealth[e], t, o);
-  for (int i = 0; i < S; ++i) next_state[e * S + i] = o.ns[i];
-  for (int i = 0; i < R; ++i) risk[e * R + i] = o.rk[i];
-  done_out[e * 2 + 0] = o.done ? 1 : 0;
-  done_out[e * 2 + 1] = o.learn_done ? 1 : 0;
-  reward_out[e] = o.reward;
-  wealth[e] = o.w;
-  time[e] = t + 1;
+
+  EnvStep<NG> o;
+  if (on) {
+    const int t = time[e];
+    env_step_core<NG>(d, a, r, wealth[e], t, o);
+    done_out[e * 2 + 0] = o.done ? 1 : 0;
+    done_out[e * 2 + 1] = o.learn_done ? 1 : 0;
+    reward_out[e] = o.reward;
+    wealth[e] = o.w;
+    time[e] = t + 1;
+    copy_n<Dm::S>(stage + threadIdx.x * S, o.ns, S);
+  }
+  __syncthreads();
+  smem_to_span(next_state + e0 * S, stage, live * S);
+  __syncthreads();
+  if (on) copy_n<Dm::R>(stage + threadIdx.x * R, o.rk, R);
+  __syncthreads();
+  smem_to_span(risk + e0 * R, stage, live * R);
 }
 
 static int env_dims(const b200_env_desc* d, int* S, int* A, int* R) {
@@ -114,8 +151,10 @@ extern "C" int b200_menv_step(const b200_env_desc* desc, int64_t n_envs, double*
   B200_REQUIRE(n_envs >= 0, "menv_step: negative n_envs");
   if (n_envs == 0) return 0;
   B200_REQUIRE(wealth && time && action && next_state && reward && done && risk, "menv_step: NULL buffer");
-  const unsigned blocks = (unsigned)((n_envs + 127) / 128);
-  menv_step_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(*desc, n_envs, wealth, time, action, returns_in,
-                                                             draw_index, next_state, reward, done, risk, S, A, R);
+  const unsigned blocks = (unsigned)((n_envs + MENV_THREADS - 1) / MENV_THREADS);
+  const size_t smem = (size_t)MENV_THREADS * std::max(S, std::max(A, R)) * sizeof(double);
+  B200_ENV_DISPATCH(env_ng(*desc), (menv_step_kernel<NG><<<blocks, MENV_THREADS, smem, (cudaStream_t)stream>>>(
+                                       *desc, n_envs, wealth, time, action, returns_in, draw_index, next_state, reward,
+                                       done, risk, S, A, R)));
   return check_cuda(cudaGetLastError(), "menv_step launch");
 }

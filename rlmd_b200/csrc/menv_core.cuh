@@ -19,8 +19,9 @@ __device__ __forceinline__ double clampd(double x, double lo, double hi) { retur
 
 // Returns of one step of env `e`: counter = (env lo, env hi, draw_index lo,
 // TAG_ENV + block), key = seed ^ draw_index hi.
+template <int GS>
 __device__ __forceinline__ void env_draw_returns(const b200_env_desc& d, int64_t e, uint64_t draw_index, int n,
-                                                 double (&r)[ENV_MAX_GAMBLES]) {
+                                                 double (&r)[GS]) {
   const bool gbm = d.family == B200_ENV_GBM;
   const uint32_t k0 = (uint32_t)d.seed ^ (uint32_t)(draw_index >> 32), k1 = (uint32_t)(d.seed >> 32);
   uint32_t thr0, thr1;
@@ -29,7 +30,9 @@ __device__ __forceinline__ void env_draw_returns(const b200_env_desc& d, int64_t
     thr0 = c0 >= 4294967295.0 ? 0xffffffffu : (uint32_t)floor(c0);
     thr1 = c1 >= 4294967295.0 ? 0xffffffffu : (uint32_t)floor(c1);
   }
-  for (int j = 0; j * 4 < n; ++j) {
+#pragma unroll
+  for (int j = 0; j * 4 < GS; ++j) {
+    if (j * 4 >= n) break;
     const Philox4 p = philox4x32_10((uint32_t)e, (uint32_t)((uint64_t)e >> 32), (uint32_t)draw_index,
                                     PHILOX_TAG_ENV + (uint32_t)j, k0, k1);
     const uint32_t u[4] = {p.x, p.y, p.z, p.w};
@@ -37,34 +40,62 @@ __device__ __forceinline__ void env_draw_returns(const b200_env_desc& d, int64_t
       float z[4];
       box_muller(u[0], u[1], z[0], z[1]);
       box_muller(u[2], u[3], z[2], z[3]);
-      for (int b = 0; b < 4 && j * 4 + b < n; ++b) r[j * 4 + b] = d.log_mean + d.vol * (double)z[b];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (j * 4 + b < GS && j * 4 + b < n) r[j * 4 + b] = d.log_mean + d.vol * (double)z[b];
     } else {
-      for (int b = 0; b < 4 && j * 4 + b < n; ++b) {
-        int code = (u[b] >= thr0);
-        if (d.family != B200_ENV_COIN) code += (u[b] >= thr1);
-        r[j * 4 + b] = d.returns[code];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (j * 4 + b < GS && j * 4 + b < n) {
+          int code = (u[b] >= thr0);
+          if (d.family != B200_ENV_COIN) code += (u[b] >= thr1);
+          r[j * 4 + b] = code == 0 ? d.returns[0] : code == 1 ? d.returns[1] : d.returns[2];
+        }
       }
     }
   }
 }
 
+// NG > 0: the number of gambles is the compile-time constant NG (every loop
+// unrolls, the per-gamble arrays live in registers); NG == 0: read from the desc.
+// The dice_sh family has one gamble but a 6-word state and a 7-word risk vector.
+template <int NG> struct EnvDims {
+  static constexpr int G = NG > 0 ? NG : ENV_MAX_GAMBLES;          // gamble slots
+  static constexpr int S = NG == 1 ? 6 : 4 + G;                    // state slots
+  static constexpr int A = NG == 1 ? 4 : 2 + G;                    // action slots
+  static constexpr int R = NG == 1 ? 7 : 6 + G;                    // risk slots
+};
+
+template <int NG = 0>
 struct EnvStep {
   double w;        // wealth after the step
   double reward;
   bool done, learn_done;
-  double ns[ENV_MAX_STATE];   // next state (normalised), S entries
-  double rk[ENV_MAX_RISK];    // risk vector, R entries
+  double ns[EnvDims<NG>::S];   // next state (normalised), S entries
+  double rk[EnvDims<NG>::R];   // risk vector, R entries
 };
 
+// dst[i] = src[i] for i < count, fully unrolled over MAXC slots (register arrays stay registers)
+template <int MAXC, typename D, typename S>
+__device__ __forceinline__ void copy_n(D* __restrict__ dst, const S* __restrict__ src, int count) {
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+    if (i < count) dst[i] = (D)src[i];
+}
+
 // One step from wealth w0 at env time t with action a[A] and returns r[n].
+template <int NG>
 __device__ __forceinline__ void env_step_core(const b200_env_desc& d, const double* __restrict__ a,
-                                              const double (&r)[ENV_MAX_GAMBLES], double w0, int t, EnvStep& o) {
-  const bool sh = d.family == B200_ENV_DICE_SH;
+                                              const double (&r)[EnvDims<NG>::G], double w0, int t, EnvStep<NG>& o) {
+  constexpr int GS = EnvDims<NG>::G;
+  const bool sh = NG <= 1 && d.family == B200_ENV_DICE_SH;
   const bool gbm = d.family == B200_ENV_GBM;
-  const int n = sh ? 1 : d.n_gambles;
+  const int n = NG > 0 ? NG : (sh ? 1 : d.n_gambles);
   // ---- actions -> leverages, stop-loss, retention
   const int off = sh ? (d.investor == B200_INV_INSURED ? 0 : d.investor) : d.investor;  // A 0, B 1, C 2
-  double lev[ENV_MAX_GAMBLES];
+  // a[off + i] with compile-time indices (an action held in registers stays there)
+  auto act = [&](int i) { return off == 0 ? a[i] : off == 1 ? a[i + 1] : a[i + 2]; };
+  double lev[GS];
   double lev_sh = 0.0, r_sh = 0.0;
   double stop = 0.0, retention = 0.0;
   const bool has_stop = d.investor == B200_INV_B || d.investor == B200_INV_C;
@@ -79,14 +110,16 @@ __device__ __forceinline__ void env_step_core(const b200_env_desc& d, const doub
       lev[0] = a[0] * d.i_lev_factor;
       lev_sh = 1 - lev[0];
     } else {
-      lev[0] = a[off] * d.lev_factor;
-      lev_sh = (a[off + 1] + d.max_abs_action) / 2 * d.sh_lev_factor;
+      lev[0] = act(0) * d.lev_factor;
+      lev_sh = (act(1) + d.max_abs_action) / 2 * d.sh_lev_factor;
     }
     step_return = clampd(lev[0] * r[0] + lev_sh * r_sh, d.min_return, d.max_return);
     factor = 1 + step_return;
   } else {
-    for (int i = 0; i < n; ++i) lev[i] = a[off + i] * d.lev_factor;
-    const double total = np_sum(n, [&](int i) { return lev[i] * r[i]; });   // np.sum(lev * r)
+#pragma unroll
+    for (int i = 0; i < GS; ++i)
+      if (i < n) lev[i] = act(i) * d.lev_factor;
+    const double total = np_sum<NG>(n, [&](int i) { return lev[i] * r[i]; });   // np.sum(lev * r)
     if (gbm) {
       step_return = fmax(total, d.min_return);
       factor = fmin(exp(step_return), 1 + d.max_return);
@@ -122,19 +155,25 @@ __device__ __forceinline__ void env_step_core(const b200_env_desc& d, const doub
     ns[4] = q0; ns[5] = q1;
     done_state = done_state || q0 >= 1.0 || q1 >= 1.0;
   } else {
-    for (int i = 0; i < n; ++i) {
-      const double q = r[i] / d.max_value;
-      ns[4 + i] = q;
-      done_state = done_state || q >= 1.0;
+#pragma unroll
+    for (int i = 0; i < GS; ++i) {
+      if (i < n) {
+        const double q = r[i] / d.max_value;
+        ns[4 + i] = q;
+        done_state = done_state || q >= 1.0;
+      }
     }
   }
   const double lev_cap = d.max_abs_action * d.lev_factor;
   bool any_max = false, all_max = true, all_min = true;
-  for (int i = 0; i < n; ++i) {
-    const double al = fabs(lev[i]);
-    any_max = any_max || (al == lev_cap);
-    all_max = all_max && (al == lev_cap);
-    all_min = all_min && (al < d.min_weight);
+#pragma unroll
+  for (int i = 0; i < GS; ++i) {
+    if (i < n) {
+      const double al = fabs(lev[i]);
+      any_max = any_max || (al == lev_cap);
+      all_max = all_max && (al == lev_cap);
+      all_min = all_min && (al < d.min_weight);
+    }
   }
   bool done = (w == wmin) || (rew < d.min_reward) || (step_return == d.min_return) || (gbm ? all_max : any_max) ||
               all_min || done_state;
@@ -153,16 +192,41 @@ __device__ __forceinline__ void env_step_core(const b200_env_desc& d, const doub
     rk[5] = has_ret ? retention : qnan;
     rk[6] = lev_sh;
   } else {
-    rk[3] = np_sum(n, [&](int i) { return lev[i]; }) / (double)n;           // np.mean(lev)
-    int c = 4;
-    if (has_stop) rk[c++] = stop;
-    if (has_ret) rk[c++] = retention;
-    if (n > 1)
-      for (int i = 0; i < n; ++i) rk[c++] = lev[i];
+    rk[3] = np_sum<NG>(n, [&](int i) { return lev[i]; }) / (double)n;           // np.mean(lev)
+    // stop / retention / per-gamble leverages follow without gaps; written with
+    // compile-time indices (a running index would put rk[] in local memory)
+    const int base = 4 + (has_stop ? 1 : 0) + (has_ret ? 1 : 0);
+    if (has_stop) rk[4] = stop;
+    if (has_ret) rk[5] = retention;
+    if (n > 1) {
+#pragma unroll
+      for (int i = 0; i < GS; ++i) {
+        if (i < n) {
+          const double v = lev[i];
+          if (base == 4) rk[4 + i] = v;
+          else if (base == 5) rk[5 + i] = v;
+          else rk[6 + i] = v;
+        }
+      }
+    }
   }
 
   o.w = w;
 }
+
+// Kernel instantiation for a desc: its number of gambles when a specialisation
+// exists (1, 2, 3; dice_sh is the one-gamble layout), else 0 = generic.
+__host__ __device__ __forceinline__ int env_ng(const b200_env_desc& d) {
+  if (d.family == B200_ENV_DICE_SH) return 1;
+  return d.n_gambles <= 3 ? d.n_gambles : 0;
+}
+#define B200_ENV_DISPATCH(ng, CALL)                 \
+  switch (ng) {                                     \
+    case 1: { constexpr int NG = 1; CALL; } break;  \
+    case 2: { constexpr int NG = 2; CALL; } break;  \
+    case 3: { constexpr int NG = 3; CALL; } break;  \
+    default: { constexpr int NG = 0; CALL; } break; \
+  }
 
 // State / risk vector lengths (env_dims on the host computes the same).
 __device__ __forceinline__ void env_dims_dev(const b200_env_desc& d, int& S, int& A, int& R) {

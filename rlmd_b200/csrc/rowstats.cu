@@ -13,13 +13,20 @@
 // are accumulated directly over {w > thr} and {w < thr} plus the tie share of
 // thr itself (never as all-minus-top: the top-K hold most of the mass).
 //
-// Five passes over the data, each HBM-bound (4 B per element per pass):
-//   pass 0: sum, level-1 histogram          pass 3: sums/counts above, below thr
-//   pass 1: |w-mean|, (w-mean)^2, level 2   pass 4: deviations of top / adj
-//   pass 2: level 3
+// Four passes over the data, each an HBM stream (4 B per element per pass):
+//   pass 0: sum, level-1 histogram
+//   pass 1: |w-mean|, (w-mean)^2, level-2 histograms
+//   pass 2: level-3 histograms + sums/counts of the elements whose 22-bit prefix is
+//           above / below thr's (the elements that share thr's prefix all sit in
+//           thr's level-3 histogram, and a level-3 bin IS one fp32 value, so the
+//           resolve step finishes the top / adj split exactly from the bin counts)
+//   pass 3: deviations of top / adj about their own means
 // Between passes a one-block-per-row "resolve" kernel turns histograms into
 // prefixes/ranks.  Every cross-block quantity lives in the caller's workspace as
 // 8-byte words so that a multi-GPU caller can all-reduce it between passes.
+#include <algorithm>
+#include <cstddef>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -34,19 +41,18 @@ struct RowWS {
   double sum_all;      // pass 0
   double absdev_all;   // pass 1
   double sqdev_all;    // pass 1
-  double sum_gt;       // pass 3: sum of w with key > key(thr)
-  double sum_lt;       // pass 3
-  double absdev_gt;    // pass 4 (about mean_top)
+  double sum_gt;       // pass 2: sum of w whose 22-bit key prefix is above thr's
+  double sum_lt;       // pass 2: ... below thr's
+  double absdev_gt;    // pass 3 (about mean_top), over key > key(thr)
   double sqdev_gt;
-  double absdev_lt;    // pass 4 (about mean_adj)
+  double absdev_lt;    // pass 3 (about mean_adj), over key < key(thr)
   double sqdev_lt;
   double pad_d[7];
   // ---- integers (exchange region I) ------------------------------------
-  long long cnt_gt;    // pass 3
-  long long cnt_lt;    // pass 3
-  long long pad_i[6];
   long long hist1[L1_BINS];          // pass 0
   long long hist2[NT][L2_BINS];      // pass 1
+  long long cnt_gt;                  // pass 2 (the count that goes with sum_gt)
+  long long pad_i[7];
   long long hist3[NT][L3_BINS];      // pass 2
   // ---- resolved by the row-resolve kernels (identical on every rank) ---
   long long rank[NT];       // remaining rank inside the current prefix
@@ -56,45 +62,72 @@ struct RowWS {
   long long ties_top, ties_adj;
   long long nonfinite[3];   // all / top / adj group holds +-inf or NaN (torch.std_mean -> nan)
   long long has_nan[3];     // all / top / adj group holds a NaN (torch.median -> nan)
-  long long pad_r[2];
+  long long key_mode;       // KEY_FULL / KEY_NO_NAN / KEY_POSITIVE for passes 1..3 (from hist1)
+  long long pad_r[1];
 };
 static_assert(sizeof(RowWS) % 8 == 0, "8-byte words");
+static_assert(offsetof(RowWS, hist1) == 16 * 8 && offsetof(RowWS, cnt_gt) == (16 + L1_BINS + NT * L2_BINS) * 8 &&
+                  offsetof(RowWS, hist3) == offsetof(RowWS, cnt_gt) + 64,
+              "exchange offsets follow the struct");
 
 constexpr int64_t D_WORDS = 16;  // doubles at the head
-constexpr int64_t OFF_CNT = D_WORDS;
-constexpr int64_t OFF_H1 = OFF_CNT + 8;
+constexpr int64_t OFF_H1 = D_WORDS;
 constexpr int64_t OFF_H2 = OFF_H1 + L1_BINS;
-constexpr int64_t OFF_H3 = OFF_H2 + (int64_t)NT * L2_BINS;
+constexpr int64_t OFF_CNT = OFF_H2 + (int64_t)NT * L2_BINS;
+constexpr int64_t OFF_H3 = OFF_CNT + 8;
 constexpr int64_t OFF_RES = OFF_H3 + (int64_t)NT * L3_BINS;
 constexpr int64_t ROW_WORDS = sizeof(RowWS) / 8;
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 16;  // elements per thread per block-slice iteration
 
+// Key modes.  Pass 0 must use the full map (float_key of common.cuh: sign-dependent
+// flip, every NaN to the top: four instructions).  Its level-1 histogram tells
+// whether the row holds a NaN or anything with the sign bit set; the later passes
+// of a NaN-free row skip the NaN test (two instructions), and those of an
+// all-positive row - every wealth row - order by the raw bit pattern: there
+// key = bits | 0x80000000, so the kernel compares raw bits against constants
+// with the top bit removed and spends nothing on the key.
+enum { KEY_FULL = 0, KEY_NO_NAN = 1, KEY_POSITIVE = 2 };
+template <int MODE>
+__device__ __forceinline__ uint32_t float_key_fast(float f) {
+  const uint32_t b = __float_as_uint(f);
+  if (MODE == KEY_POSITIVE) return b;
+  const uint32_t k = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+  return (MODE == KEY_FULL && f != f) ? 0xffffffffu : k;
+}
+// a key-space constant (shifted right by SH) in the units float_key_fast<MODE> returns
+template <int MODE>
+__device__ __forceinline__ uint32_t key_const(uint32_t v, int sh) {
+  return MODE == KEY_POSITIVE ? v ^ (0x80000000u >> sh) : v;
+}
+
 __device__ __forceinline__ void atomic_add_f64(double* p, double v) { atomicAdd(p, v); }
 __device__ __forceinline__ void atomic_add_i64(long long* p, long long v) {
   atomicAdd((unsigned long long*)p, (unsigned long long)v);
 }
 
-// grid = (slices, rows).  Each block walks its slice of one row.
-template <int PASS>
-__global__ void __launch_bounds__(RS_THREADS)
-rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, RowWS* __restrict__ ws) {
-  extern __shared__ unsigned int smem_hist[];
+// One block walks its slice of one row.  Per-element work is kept to a dozen
+// instructions so that every pass stays an HBM stream: the ALU pipe issues 2 warp
+// instructions per clock per SM, i.e. ~11 ALU instructions per element at the
+// measured HBM rate.
+template <int PASS, int MODE>
+__device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, int64_t n, RowWS* __restrict__ w,
+                                                   unsigned int* smem_hist) {
   __shared__ double red_d[32];
   __shared__ long long red_i[32];
 
-  const int64_t row = blockIdx.y;
-  const float* __restrict__ v = values + row * ld;
-  RowWS* w = ws + row;
-
   constexpr int HBINS = PASS == 0 ? L1_BINS : PASS == 1 ? NT * L2_BINS : PASS == 2 ? NT * L3_BINS : 0;
   for (int i = threadIdx.x; i < HBINS; i += RS_THREADS) smem_hist[i] = 0;
+  // pass 1: level-1 bin -> byte offset of the level-2 histogram that counts it (-1: none)
+  int* lut = reinterpret_cast<int*>(smem_hist + HBINS);
+  if (PASS == 1)
+    for (int i = threadIdx.x; i < L1_BINS; i += RS_THREADS) lut[i] = -1;
 
   // Targets that fell into the same bin so far need the same histogram: only the
   // first of them (its representative) counts, the others copy it at the flush.
   // cmp[j] is the bin prefix a key must show to be counted for target j; a
-  // duplicate gets a prefix no key can have.
+  // duplicate gets a prefix no key can have, so a key matches at most one target.
   __shared__ int rep_s[NT];
   uint32_t cmp[NT];
   double mean_a = 0, mean_t = 0, mean_j = 0;
@@ -109,43 +142,61 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
       for (int jj = NT - 1; jj >= 0; --jj)
         if (jj < j && ((uint32_t)w->prefix[jj] >> SH) == cmp[j]) rep = jj;
       if (threadIdx.x == 0) rep_s[j] = rep;
-      if (rep != j) cmp[j] = 0xffffffffu;
+      cmp[j] = rep != j ? 0xffffffffu : key_const<MODE>(cmp[j], SH);
     }
   }
-  if (PASS == 1) mean_a = w->mean_all;
-  if (PASS >= 3) thr_key = (uint32_t)w->prefix[1];
-  if (PASS == 4) { mean_t = w->mean_top; mean_j = w->mean_adj; }
+  if (PASS == 1) {
+    mean_a = w->mean_all;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        if (cmp[j] != 0xffffffffu) lut[cmp[j]] = j * L2_BINS * 4;
+    }
+  }
+  if (PASS == 2) thr_key = key_const<MODE>((uint32_t)w->prefix[1] >> L3_BITS, L3_BITS);   // thr's 22-bit prefix
+  if (PASS == 3) {
+    thr_key = key_const<MODE>((uint32_t)w->prefix[1], 0);
+    mean_t = w->mean_top;
+    mean_j = w->mean_adj;
+  }
   __syncthreads();
 
   double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-  long long c0 = 0, c1 = 0;
+  unsigned int c0 = 0;  // per-thread count: a thread sees far fewer than 2^32 elements
 
   auto process = [&](const float x) {
-    const uint32_t k = float_key(x);
+    const uint32_t k = float_key_fast<MODE>(x);
     if (PASS == 0) {
       a0 += (double)x;
       atomicAdd(&smem_hist[k >> (32 - L1_BITS)], 1u);
     } else if (PASS == 1) {
       const double d = (double)x - mean_a;
       a0 += fabs(d);
-      a1 += d * d;
-      const uint32_t top = k >> (32 - L1_BITS);
-      const uint32_t mid = (k >> L3_BITS) & (L2_BINS - 1);
-#pragma unroll
-      for (int j = 0; j < NT; ++j)
-        if (top == cmp[j]) atomicAdd(&smem_hist[j * L2_BINS + mid], 1u);
+      a1 = __fma_rn(d, d, a1);
+      const int off = lut[k >> (32 - L1_BITS)];
+      if (off >= 0)
+        atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(smem_hist) + off +
+                                                  ((k >> (L3_BITS - 2)) & ((L2_BINS - 1) << 2))), 1u);
     } else if (PASS == 2) {
+      // Sums on either side of thr's 22-bit prefix (the count below it follows
+      // from the total at the resolve step).  Nearly every element lies below
+      // thr (the top group is small) and outside the targets' 22-bit prefixes:
+      // its whole cost is the key, three compares and one predicated fp64 add;
+      // everything else sits behind one rarely taken branch.  (med_top's prefix
+      // is never below thr's, so "not below thr" covers targets 1 and 2.)
       const uint32_t hi = k >> L3_BITS;
-      const uint32_t lo = k & (L3_BINS - 1);
-#pragma unroll
-      for (int j = 0; j < NT; ++j)
-        if (hi == cmp[j]) atomicAdd(&smem_hist[j * L3_BINS + lo], 1u);
-    } else if (PASS == 3) {
-      if (k > thr_key) { a0 += (double)x; ++c0; }
-      else if (k < thr_key) { a1 += (double)x; ++c1; }
+      a1 += (double)(hi < thr_key ? x : 0.0f);   // one fp32 select, not two on the fp64 sum
+      if ((hi >= thr_key) | (hi == cmp[0]) | (hi == cmp[3])) {
+        if (hi > thr_key) { a0 += (double)x; ++c0; }
+        if ((hi == cmp[0]) | (hi == cmp[1]) | (hi == cmp[2]) | (hi == cmp[3])) {
+          const uint32_t j = hi == cmp[0] ? 0u : hi == cmp[1] ? 1u : hi == cmp[2] ? 2u : 3u;
+          atomicAdd(&smem_hist[j * L3_BINS + (k & (L3_BINS - 1))], 1u);
+        }
+      }
     } else {
-      if (k > thr_key) { const double d = (double)x - mean_t; a0 += fabs(d); a1 += d * d; }
-      else if (k < thr_key) { const double d = (double)x - mean_j; a2 += fabs(d); a3 += d * d; }
+      if (k < thr_key) { const double d = (double)x - mean_j; a2 += fabs(d); a3 = __fma_rn(d, d, a3); }
+      else if (k > thr_key) { const double d = (double)x - mean_t; a0 += fabs(d); a1 = __fma_rn(d, d, a1); }
     }
   };
 
@@ -163,15 +214,10 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
 #pragma unroll
       for (int u = 0; u < RS_ITEMS / 4; ++u) { process(t[u].x); process(t[u].y); process(t[u].z); process(t[u].w); }
     } else {
-      float t[RS_ITEMS];
-#pragma unroll
       for (int u = 0; u < RS_ITEMS; ++u) {
         const int64_t i = base + (int64_t)u * RS_THREADS + threadIdx.x;
-        t[u] = i < n ? __ldcs(v + i) : 0.0f;
+        if (i < n) process(__ldcs(v + i));
       }
-#pragma unroll
-      for (int u = 0; u < RS_ITEMS; ++u)
-        if (base + (int64_t)u * RS_THREADS + threadIdx.x < n) process(t[u]);
     }
   }
 
@@ -182,14 +228,14 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
   } else if (PASS == 1) {
     double s0 = block_sum(a0, red_d), s1 = block_sum(a1, red_d);
     if (threadIdx.x == 0) { atomic_add_f64(&w->absdev_all, s0); atomic_add_f64(&w->sqdev_all, s1); }
-  } else if (PASS == 3) {
+  } else if (PASS == 2) {
     double s0 = block_sum(a0, red_d), s1 = block_sum(a1, red_d);
-    long long n0 = block_sum(c0, red_i), n1 = block_sum(c1, red_i);
+    long long n0 = block_sum((long long)c0, red_i);
     if (threadIdx.x == 0) {
-      atomic_add_f64(&w->sum_gt, s0); atomic_add_f64(&w->sum_lt, s1);
-      atomic_add_i64(&w->cnt_gt, n0); atomic_add_i64(&w->cnt_lt, n1);
+      if (n0) { atomic_add_f64(&w->sum_gt, s0); atomic_add_i64(&w->cnt_gt, n0); }
+      atomic_add_f64(&w->sum_lt, s1);
     }
-  } else if (PASS == 4) {
+  } else if (PASS == 3) {
     double s0 = block_sum(a0, red_d), s1 = block_sum(a1, red_d);
     double s2 = block_sum(a2, red_d), s3 = block_sum(a3, red_d);
     if (threadIdx.x == 0) {
@@ -208,6 +254,20 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
       if (c) atomic_add_i64(gh + i, (long long)c);
     }
   }
+}
+
+// grid = (slices, rows)
+template <int PASS>
+__global__ void __launch_bounds__(RS_THREADS)
+rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, RowWS* __restrict__ ws) {
+  extern __shared__ unsigned int smem_hist[];
+  const int64_t row = blockIdx.y;
+  const float* __restrict__ v = values + row * ld;
+  RowWS* w = ws + row;
+  const long long mode = PASS == 0 ? (long long)KEY_FULL : w->key_mode;   // block-uniform
+  if (mode == KEY_POSITIVE) rowstats_pass_body<PASS, KEY_POSITIVE>(v, n, w, smem_hist);
+  else if (mode == KEY_NO_NAN) rowstats_pass_body<PASS, KEY_NO_NAN>(v, n, w, smem_hist);
+  else rowstats_pass_body<PASS, KEY_FULL>(v, n, w, smem_hist);
 }
 
 // One block per row: walk a histogram to find the bin that holds `rank`.
@@ -255,12 +315,14 @@ __device__ void find_bin(const long long* __restrict__ hist, int bins, long long
   __syncthreads();
 }
 
-// STEP 0: after pass 0   STEP 1: after pass 1   STEP 2: after pass 2
-// STEP 3: after pass 3   STEP 4: after pass 4 (writes stats)
+// STEP 0: after pass 0   STEP 1: after pass 1   STEP 2: after pass 2 (order
+// statistics, top / adj split and means)   STEP 3: after pass 3 (writes stats)
 template <int STEP>
 __global__ void __launch_bounds__(256)
 rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, double* __restrict__ stats) {
   __shared__ long long scratch[256];
+  __shared__ double red_d[32];
+  __shared__ long long red_i[32];
   __shared__ int bin_s;
   __shared__ long long rem_s;
   RowWS* w = ws + blockIdx.x;
@@ -276,7 +338,12 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
       }
       __syncthreads();
     }
+    // anything with the sign bit set (level-1 bins 0..1023)?  4 bins per thread
+    int neg = 0;
+    for (int i = 0; i < 4; ++i) neg |= w->hist1[threadIdx.x * 4 + i] != 0;
+    neg = __syncthreads_or(neg);
     if (threadIdx.x == 0) {
+      w->key_mode = w->hist1[2047] > 0 ? KEY_FULL : neg ? KEY_NO_NAN : KEY_POSITIVE;
       w->mean_all = w->sum_all / (double)n;
       // key bins that can only hold non-finite values: 3 = -inf, 2044 = +inf, 2047 = NaN
       const long long ninf = w->hist1[3], pinf = w->hist1[2044], nan = w->hist1[2047];
@@ -307,16 +374,33 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
       }
       __syncthreads();
     }
-  } else if (STEP == 3) {
+    // The elements that share thr's 22-bit prefix: bin `lo` of thr's level-3
+    // histogram holds c copies of the one fp32 value with key (prefix22 | lo).
+    const uint32_t thr_key = (uint32_t)w->prefix[1];
+    const uint32_t thr_lo = thr_key & (L3_BINS - 1), base = thr_key & ~(uint32_t)(L3_BINS - 1);
+    double s_gt = 0, s_lt = 0;
+    long long c_gt = 0, c_lt = 0, c_all = 0;
+    for (uint32_t lo = threadIdx.x; lo < (uint32_t)L3_BINS; lo += blockDim.x) {
+      const long long c = w->hist3[1][lo];
+      c_all += c;
+      if (c == 0 || lo == thr_lo) continue;   // an empty bin must not contribute 0 * inf
+      const double v = (double)c * (double)key_float(base | lo);
+      if (lo > thr_lo) { s_gt += v; c_gt += c; } else { s_lt += v; c_lt += c; }
+    }
+    s_gt = block_sum(s_gt, red_d); s_lt = block_sum(s_lt, red_d);
+    c_gt = block_sum(c_gt, red_i); c_lt = block_sum(c_lt, red_i); c_all = block_sum(c_all, red_i);
     if (threadIdx.x == 0) {
       const double thr = w->value[1];
-      const long long n_eq = n - w->cnt_gt - w->cnt_lt;
-      const long long tt = K - w->cnt_gt;  // ties that belong to the top group
+      // below thr's prefix = everything that is neither above it nor inside it
+      const long long n_gt = w->cnt_gt + c_gt, n_lt = (n - w->cnt_gt - c_all) + c_lt;
+      const double sum_gt = c_gt ? w->sum_gt + s_gt : w->sum_gt, sum_lt = c_lt ? w->sum_lt + s_lt : w->sum_lt;
+      const long long n_eq = n - n_gt - n_lt;
+      const long long tt = K - n_gt;  // ties that belong to the top group
       w->ties_top = tt;
       w->ties_adj = n_eq - tt;
       // a tie share of zero must not contribute 0 * inf
-      w->mean_top = (w->sum_gt + (tt > 0 ? (double)tt * thr : 0.0)) / (double)K;
-      w->mean_adj = (w->sum_lt + (n_eq - tt > 0 ? (double)(n_eq - tt) * thr : 0.0)) / (double)(n - K);
+      w->mean_top = (sum_gt + (tt > 0 ? (double)tt * thr : 0.0)) / (double)K;
+      w->mean_adj = (sum_lt + (n_eq - tt > 0 ? (double)(n_eq - tt) * thr : 0.0)) / (double)(n - K);
     }
   } else {
     if (threadIdx.x == 0) {
@@ -337,8 +421,12 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
       // torch semantics: Welford's std_mean turns any non-finite member into
       // nan mean/std (hence nan MAD); median propagates NaN
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      // ... except that a ONE-element group's mean is the element itself (Welford's
+      // first update is exact: mean = +-inf, then std = MAD = nan)
+      const long long size[3] = {n, K, n - K};
+      const double single[3] = {qnan, w->value[1], w->value[3]};   // top = {thr}, adj = {its median}
       for (int j = 0; j < 3; ++j) {
-        if (w->nonfinite[j]) { s[0 + j] = qnan; s[3 + j] = qnan; s[6 + j] = qnan; }
+        if (w->nonfinite[j]) { s[0 + j] = size[j] == 1 ? single[j] : qnan; s[3 + j] = qnan; s[6 + j] = qnan; }
         if (w->has_nan[j]) s[9 + j] = qnan;
       }
     }
@@ -348,21 +436,22 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
 static int launch_pass(int pass, const float* values, int64_t rows, int64_t n, int64_t ld, RowWS* ws,
                        cudaStream_t st) {
   if (n <= 0 || rows <= 0) return 0;
-  // enough blocks to fill the machine several times over, bounded per row
+  // Several waves of blocks (the last, partly filled wave then costs little), but
+  // at least four tiles of work per block so that flushing its shared-memory
+  // histogram stays a small share of its time.
   const int sms = sm_count();
-  int64_t want = ((int64_t)sms * 8 + rows - 1) / rows;
-  int64_t max_slices = (n + (int64_t)RS_THREADS * RS_ITEMS - 1) / ((int64_t)RS_THREADS * RS_ITEMS);
-  int64_t slices = want < 1 ? 1 : want;
+  const int64_t tile = (int64_t)RS_THREADS * RS_ITEMS;
+  int64_t slices = ((int64_t)sms * 32 + rows - 1) / rows;
+  const int64_t max_slices = std::max<int64_t>(1, n / (4 * tile));
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
   if (rows > 65535) return set_error(B200_ELIMIT, "rowstats: rows=%lld > 65535 per call", (long long)rows);
   dim3 grid((unsigned)slices, (unsigned)rows);
   switch (pass) {
     case 0: rowstats_pass_kernel<0><<<grid, RS_THREADS, L1_BINS * 4, st>>>(values, n, ld, ws); break;
-    case 1: rowstats_pass_kernel<1><<<grid, RS_THREADS, NT * L2_BINS * 4, st>>>(values, n, ld, ws); break;
+    case 1: rowstats_pass_kernel<1><<<grid, RS_THREADS, NT * L2_BINS * 4 + L1_BINS * 4, st>>>(values, n, ld, ws); break;
     case 2: rowstats_pass_kernel<2><<<grid, RS_THREADS, NT * L3_BINS * 4, st>>>(values, n, ld, ws); break;
     case 3: rowstats_pass_kernel<3><<<grid, RS_THREADS, 0, st>>>(values, n, ld, ws); break;
-    case 4: rowstats_pass_kernel<4><<<grid, RS_THREADS, 0, st>>>(values, n, ld, ws); break;
   }
   return check_cuda(cudaGetLastError(), "rowstats pass launch");
 }
@@ -374,7 +463,6 @@ static int launch_resolve(int step, int64_t rows, int64_t n_total, int64_t top, 
     case 1: rowstats_resolve_kernel<1><<<(unsigned)rows, 256, 0, st>>>(ws, n_total, top, stats); break;
     case 2: rowstats_resolve_kernel<2><<<(unsigned)rows, 256, 0, st>>>(ws, n_total, top, stats); break;
     case 3: rowstats_resolve_kernel<3><<<(unsigned)rows, 256, 0, st>>>(ws, n_total, top, stats); break;
-    case 4: rowstats_resolve_kernel<4><<<(unsigned)rows, 256, 0, st>>>(ws, n_total, top, stats); break;
   }
   return check_cuda(cudaGetLastError(), "rowstats resolve launch");
 }
@@ -390,10 +478,9 @@ extern "C" int64_t b200_rowstats_workspace_bytes(int64_t rows) {
 // Phases for a multi-GPU caller:
 //   phase 0: clear + pass 0                      -> exchange D[0..1) and hist1
 //   phase 1: resolve 0 + pass 1                  -> exchange D[1..3) and hist2
-//   phase 2: resolve 1 + pass 2                  -> exchange hist3
-//   phase 3: resolve 2 + pass 3                  -> exchange D[3..5) and cnt
-//   phase 4: resolve 3 + pass 4                  -> exchange D[5..9)
-//   phase 5: resolve 4 (writes stats)
+//   phase 2: resolve 1 + pass 2                  -> exchange D[3..5), cnt and hist3
+//   phase 3: resolve 2 + pass 3                  -> exchange D[5..9)
+//   phase 4: resolve 3 (writes stats)
 // The workspace is laid out row-major, so an exchange region is strided by
 // ROW_WORDS; callers reduce the whole typed slab view instead (see
 // b200_rowstats_exchange): the slabs below are contiguous PER ROW only, hence
@@ -410,9 +497,9 @@ extern "C" int b200_rowstats(const float* values, int64_t rows, int64_t n, int64
                (long long)n, (long long)n_total);
   B200_REQUIRE(top >= 1 && top < n_total, "rowstats: need 1 <= top < n_total (top=%lld)", (long long)top);
   B200_REQUIRE(ld >= n, "rowstats: ld < n");
-  B200_REQUIRE(phase >= -1 && phase <= 5, "rowstats: phase out of range");
+  B200_REQUIRE(phase >= -1 && phase <= 4, "rowstats: phase out of range");
   RowWS* ws = (RowWS*)workspace;
-  const int first = phase < 0 ? 0 : phase, last = phase < 0 ? 5 : phase;
+  const int first = phase < 0 ? 0 : phase, last = phase < 0 ? 4 : phase;
   for (int p = first; p <= last; ++p) {
     int rc = 0;
     if (p == 0) {
@@ -421,7 +508,7 @@ extern "C" int b200_rowstats(const float* values, int64_t rows, int64_t n, int64
       rc = launch_resolve(p - 1, rows, n_total, top, ws, stats, st);
       if (rc) return rc;
     }
-    if (p <= 4) {
+    if (p <= 3) {
       rc = launch_pass(p, values, rows, n, ld, ws, st);
       if (rc) return rc;
     }
@@ -437,9 +524,8 @@ extern "C" int b200_rowstats_exchange(int32_t phase, int64_t out[5]) {
   switch (phase) {
     case 0: io = OFF_H1; ic = L1_BINS; d_o = 0; dc = 1; break;
     case 1: io = OFF_H2; ic = (int64_t)NT * L2_BINS; d_o = 1; dc = 2; break;
-    case 2: io = OFF_H3; ic = (int64_t)NT * L3_BINS; break;
-    case 3: io = OFF_CNT; ic = 2; d_o = 3; dc = 2; break;
-    case 4: d_o = 5; dc = 4; break;
+    case 2: io = OFF_CNT; ic = 8 + (int64_t)NT * L3_BINS; d_o = 3; dc = 2; break;  // cnt words, then hist3
+    case 3: d_o = 5; dc = 4; break;
     default: break;
   }
   out[0] = io; out[1] = ic; out[2] = d_o; out[3] = dc; out[4] = ROW_WORDS;

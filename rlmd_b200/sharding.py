@@ -18,7 +18,7 @@ import torch
 
 from ._lib import check, lib
 
-N_PHASES = 6
+N_PHASES = 5
 
 
 def shard_range(n_total: int, world: int, rank: int) -> Tuple[int, int]:

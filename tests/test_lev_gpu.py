@@ -262,6 +262,56 @@ def test_rowstats_inf_and_nan_follow_torch(eng):
             assert (np.isnan(got[idx]) and np.isnan(w)) or got[idx] == pytest.approx(w, rel=1e-6), (idx, got[idx], w)
 
 
+def _torch_stats(v: np.ndarray, top: int) -> np.ndarray:
+    """The reference block (lev/lev_exp.py:177-192) itself, on torch CPU."""
+    t = torch.from_numpy(v)
+    s = t.sort(descending=True)[0]
+    out = np.zeros(12)
+    for j, grp in enumerate((t, s[:top], s[top:])):
+        std, mean = torch.std_mean(grp, unbiased=False)
+        out[0 + j], out[6 + j] = float(mean), float(std)
+        out[3 + j] = float((grp - mean).abs().mean())
+        out[9 + j] = float(grp.median())
+    return out
+
+
+@pytest.mark.parametrize("top", [1, 3, 8, 15])
+def test_rowstats_rows_in_every_key_mode_in_one_launch(eng, top):
+    """
+    Passes 1..3 pick a key mode per row from pass 0's histogram: raw bits for an
+    all-positive row, the sign flip for a row with the sign bit set somewhere
+    (-0.0 included), the full map for a row with NaNs (either sign bit).
+    """
+    rs = np.random.RandomState(top)
+    n = 29
+    rows = [rs.lognormal(0, 2, n), rs.standard_normal(n), rs.lognormal(0, 1, n), rs.lognormal(0, 1, n),
+            rs.standard_normal(n), np.abs(rs.standard_normal(n))]
+    v = np.stack(rows).astype(np.float32)
+    v[2, 5] = np.float32(-0.0)                                   # sign bit, value zero
+    v[3, [1, 7]] = np.float32(np.nan)
+    v[4, [0, 9, 20]] = np.array([0xFFC00000, 0x7FC00000, 0xFF800001], dtype=np.uint32).view(np.float32)  # -NaN, NaN, -sNaN
+    v[5, [2, 3]] = np.float32(np.inf)
+    got = eng.rowstats(torch.from_numpy(v).cuda(), top).cpu().numpy()
+    for r in range(v.shape[0]):
+        want = _torch_stats(v[r], top)
+        for idx in range(12):
+            assert (np.isnan(got[r, idx]) and np.isnan(want[idx])) or got[r, idx] == pytest.approx(want[idx], rel=2e-6, abs=1e-7), \
+                (r, idx, got[r], want)
+        ok = ~np.isnan(want[9:12])
+        assert np.array_equal(got[r, 9:12][ok], want[9:12][ok]), "order statistics are exact"
+
+
+def test_rowstats_large_top_group(eng):
+    """top ~ n/2: the 'above thr' side is no longer rare (it sits behind the branch pass 2 takes seldom)."""
+    rs = np.random.RandomState(3)
+    v = rs.lognormal(1, 1.5, size=(2, 50_001)).astype(np.float32)
+    for top in (25_000, 50_000):
+        got = eng.rowstats(torch.from_numpy(v).cuda(), top).cpu().numpy()
+        want = np.stack([lo.summary_stats(v[r], top) for r in range(2)])
+        assert np.array_equal(got[:, 9:12], want[:, 9:12])
+        assert np.allclose(got[:, :9], want[:, :9], rtol=1e-11)
+
+
 def test_rowstats_strided_rows(eng):
     rs = np.random.RandomState(0)
     buf = torch.from_numpy(rs.lognormal(size=(4, 1000)).astype(np.float32)).cuda()

@@ -45,8 +45,8 @@ def _worker(rank, world, port, top, out_dir):
         assert sharding.global_count(cnt, dist.group.WORLD, "cpu") == n_total
         io1, ic1, _, _, words = sharding.exchange_words(0)
         io2 = sharding.exchange_words(1)[0]
-        io3 = sharding.exchange_words(2)[0]
-        ioc = sharding.exchange_words(3)[0]
+        ioc = sharding.exchange_words(2)[0]      # phase 2 exchanges the 8 count words, then hist3
+        io3 = ioc + 8
         ws = torch.zeros((rows, words), dtype=torch.int64)
         passes = rp.RowStatsPasses(v[:, off:off + cnt], n_total, top, ws.numpy(),
                                    {"h1": io1, "h2": io2, "h3": io3, "cnt": ioc})

@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--h", type=int, default=2048)
+    ap.add_argument("--series-h", type=int, default=64,
+                    help="steps of the series run (chunks of 32 steps; early chunks are tie-heavy: with a long run, "
+                         "point ncu at late chunks with --launch-skip)")
     a = ap.parse_args()
     only = set(filter(None, a.only.split(",")))
     n, h = a.n, a.h
@@ -64,7 +67,7 @@ def main():
                          mode="log", out_data_T=outp)
     if on("series"):
         f3 = lev_exp.dice_factor_table(lev10, 0.5, -0.5, 0.05)
-        oc = engine.lev_draw("discrete", n, 64, seed=420, probs=(1 / 6, 1 / 6, 2 / 3))
+        oc = engine.lev_draw("discrete", n, a.series_h, seed=420, probs=(1 / 6, 1 / 6, 2 / 3))
         engine.lev_series("discrete", f3, lev10, 100.0, max(1, n // 10000), outcomes=oc)
         del oc
     if on("bigbrain"):
