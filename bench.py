@@ -9,6 +9,9 @@ param_range(0.05, 1.00, 0.05) = 20 leverages, top = 100.  One "step" is one
 pass of the `dice_fixed_final_lev` hot path over one synthetic outcome array:
     sweep (log-domain count kernel) -> data_T[20, N] -> 12 summary statistics
     per leverage (exact order statistics by radix select).
+The outcome array is resident in HBM in the engine's packed format (2 bits per
+roll, `--format packed2`, the default; `--format u8` = one byte per roll): the
+sweep is bound by the one read of that array, so its size is the cost.
 With N GPUs (one process per GPU, torchrun) every rank owns its own 1e6
 investors (weak scaling); the only cross-GPU traffic is the all-reduce of the
 per-leverage partial sums and radix histograms inside the statistics.
@@ -281,7 +284,11 @@ def run_gpu(args):
 
     # synthetic outcomes of this rank's investors, resident in HBM (10 GB >> 126 MB L2:
     # every step streams the whole array from DRAM again)
-    outcomes = engine.lev_draw("discrete", n, h, seed=420, investor_offset=rank * n, probs=PROBS, device=dev)
+    packed = args.format == "packed2"
+    outcomes = engine.lev_draw("discrete", n, h, seed=420, investor_offset=rank * n, probs=PROBS, device=dev,
+                               packed=packed)
+    row_bytes = (h + 3) // 4 if packed else h            # algorithmic bytes per investor row
+    resident = outcomes.data if packed else outcomes
     data_T = torch.empty((g, n), dtype=torch.float32, device=dev)
     ws = engine.rowstats_workspace(g, dev)
     stats_holder = {}
@@ -321,37 +328,46 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed, sweep_s = float(t[0]), float(t[1])
     value = n_total * h * args.steps / elapsed
-    launches_per_step = 1 + 10  # sweep + 5 statistic passes + 5 row-resolve kernels
+    # sweep + 4 statistic passes + 4 row-resolve kernels (+ pack / unpack around each of the 4 exchanges)
+    launches_per_step = 1 + 8 + (8 if world > 1 else 0)
 
     # ---- end to end: pinned host outcomes -> H2D (overlapped with the sweep) -> statistics -> host
-    e2e = None
-    if not args.no_e2e:
+    def measure_e2e(as_packed):
+        """Pinned host outcomes -> lev_final_host (H2D inside) -> statistics on the host, CUDA-event timed."""
         n_host = n
-        while True:   # 10 GB of pinned memory per rank; halve the e2e sample if the host refuses to pin that much
+        width = (h + 3) // 4 if as_packed else h
+        while True:   # halve the e2e sample if the host refuses to pin that much
             try:
-                host = torch.empty((n_host, h), dtype=torch.uint8, pin_memory=True)
+                host = torch.empty((n_host, width), dtype=torch.uint8, pin_memory=True)
                 break
             except RuntimeError:
                 n_host //= 2
                 if n_host < 1000:
                     raise
-        host.copy_(outcomes[:n_host])
-        torch.cuda.synchronize()
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
         if world > 1:   # every rank must run the same sample size (the statistics are collective)
             t = torch.tensor([n_host], dtype=torch.int64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             n_host = int(t[0])
             host = host[:n_host]
+        if as_packed == packed:
+            host.copy_(resident[:n_host, :width])
+        elif as_packed:
+            host.copy_(engine.pack_codes(outcomes[:n_host]).data[:, :width])
+        else:
+            host.copy_(outcomes.unpack()[:n_host] if n_host == n else
+                       engine.PackedCodes(outcomes.data[:n_host], h).unpack())
+        torch.cuda.synchronize()
+        src = engine.PackedCodes(host, h) if as_packed else host
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
         kw = dict(mode="log", device=dev, group=group, n_total=n_host * world)
-        engine.lev_final_host("discrete", table, V0, top_total, host, **kw)  # warm-up
+        engine.lev_final_host("discrete", table, V0, top_total, src, **kw)  # warm-up
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_start.record()
         for _ in range(e2e_steps):
-            st = engine.lev_final_host("discrete", table, V0, top_total, host, **kw)   # ends with the D2H read
+            st = engine.lev_final_host("discrete", table, V0, top_total, src, **kw)   # ends with the D2H read
         e_end.record()
         torch.cuda.synchronize()
         dt = e_start.elapsed_time(e_end) * 1e-3
@@ -359,14 +375,21 @@ def run_gpu(args):
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t[0])
-        e2e = {
-            "value": n_host * world * h * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_host * h,
-            "investors_per_gpu": n_host,
-            "d2h_bytes_per_step": int(st.nbytes), "steps": e2e_steps,
-            "note": "per-rank pinned uint8 outcomes copied H2D in 256 MiB row chunks overlapped with the sweep; "
-                    "statistics read back to the host every step",
+        return {
+            "value": n_host * world * h * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_host * width,
+            "investors_per_gpu": n_host, "d2h_bytes_per_step": int(st.nbytes), "steps": e2e_steps,
+            "host_format": "2-bit packed codes" if as_packed else "uint8 codes",
+            "note": "per-rank pinned host outcomes copied H2D in 256 MiB row chunks overlapped with the sweep; "
+                    "statistics read back to the host every step (PCIe-bound)",
         }
-        del host
+
+    # ---- end to end: pinned host outcomes -> H2D (overlapped with the sweep) -> statistics -> host
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(packed)
+        if packed:   # the same call on one-byte-per-roll host outcomes, for comparison (4x the PCIe bytes)
+            other = measure_e2e(False)
+            e2e["uint8_host_codes"] = {k: other[k] for k in ("value", "h2d_bytes_per_step", "investors_per_gpu")}
 
     secondary = None if args.no_secondary else run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world)
 
@@ -376,19 +399,22 @@ def run_gpu(args):
         return 0
 
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = n * h * 1.0 / sweep_s / 1e9  # 1 byte per investor-step, per GPU, per launch
+    # algorithmic bytes: one read of this GPU's outcome array per launch (1/4 B per investor-step packed, 1 B as uint8)
+    kernel = "log_discrete_packed_kernel" if packed else "log_discrete_stream_kernel"
+    achieved = n * row_bytes / sweep_s / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and n == N_INVESTORS:
         try:
-            traffic = json.load(open(tpath)).get("log_discrete_stream_kernel", {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get(kernel, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "log_discrete_stream_kernel<3>", "achieved": achieved, "peak": hbm_peak,
+        "bound": "hbm", "kernel": kernel + "<3>", "achieved": achieved, "peak": hbm_peak,
         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-        "algorithmic_bytes_per_launch": n * h, "avg_launch_ms": sweep_s * 1e3,
+        "algorithmic_bytes_per_launch": n * row_bytes, "bytes_per_investor_step": row_bytes / h,
+        "avg_launch_ms": sweep_s * 1e3,
     }
 
     cpu = None
@@ -405,12 +431,14 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8 codes, int32 counts, f64 log-wealth",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": ("2-bit codes" if packed else "u8 codes") + ", int32 counts, f64 log-wealth",
         "data": "synthetic (on-device Philox4x32-10 die rolls, seed 420)",
         "config": {
             "workload": WORKLOAD, "investors_per_gpu": n, "horizon": h, "leverages": g, "top": top_total,
             "mode": "log-domain final sweep + exact row statistics", "sharding": f"investors x{world}",
-            "l2": "inputs (10 GB per GPU) exceed the 126 MB L2; no explicit flush",
+            "outcome_format": "packed 2-bit codes (2.5 GB per GPU)" if packed else "uint8 codes (10 GB per GPU)",
+            "l2": f"inputs ({n * row_bytes / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no explicit flush",
         },
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
@@ -430,6 +458,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--investors", type=int, default=N_INVESTORS, help="investors per GPU")
+    ap.add_argument("--format", default="packed2", choices=["packed2", "u8"],
+                    help="resident outcome format: 2-bit packed codes (default) or one uint8 per roll")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -89,11 +89,19 @@ typedef struct b200_lev_desc {
   uint32_t thresholds[B200_MAX_OUTCOMES]; /* discrete Philox: outcome =
                               #{k : draw >= thresholds[k]}, k < K-1, draw a
                               uniform uint32; thresholds ascending            */
+  int32_t outcome_bits;    /* discrete STREAM outcomes: 0 or 8 = one uint8 code
+                              per outcome; 2 = PACKED, four 2-bit codes per byte
+                              (step t in byte t>>2, bits 2*(t&3)..+1), row
+                              stride ld_outcomes in BYTES (>= ceil(H/4)).  A
+                              fair die carries 1.25 bits per roll: the packed
+                              array is a quarter of the HBM traffic of the LOG
+                              sweep (the CHAIN kernels take uint8 codes)      */
+  int32_t reserved;        /* 0 */
 } b200_lev_desc;
 
 /*
- * outcomes : STREAM: uint8 [N,ld] (discrete, codes < K) or float [N,ld] (GBM);
- *            PHILOX: NULL.
+ * outcomes : STREAM: uint8 [N,ld] (discrete, codes < K; or packed 2-bit codes,
+ *            see outcome_bits) or float [N,ld] (GBM); PHILOX: NULL.
  * factors_host : HOST pointer (the table is tiny and travels as a kernel
  *            parameter).  Discrete: float [G,K] row-major, computed by the
  *            caller with the reference's own fp32 expressions; GBM: float lev[G].
@@ -126,9 +134,15 @@ int b200_lev_chunk(const b200_lev_desc* desc, const void* outcomes,
                    void* state, float* dump, void* stream);
 
 /* Materialises the outcomes a PHILOX sweep with `desc` consumes into
- * out[N,ld] (uint8 codes or float x): lets a streamed run and the CPU oracle
- * see the identical pre-drawn array. */
+ * out[N,ld] (uint8 codes, packed 2-bit codes when desc->outcome_bits == 2 - then
+ * ld_outcomes is in bytes and a multiple of 4 - or float x): lets a streamed run
+ * and the CPU oracle see the identical pre-drawn array. */
 int b200_lev_draw(const b200_lev_desc* desc, void* out, void* stream);
+
+/* uint8 codes [N, ld_codes] -> packed 2-bit codes [N, ld_packed bytes]
+ * (ld_packed >= ceil(H/4); codes are taken modulo 4, pad bits are written 0). */
+int b200_lev_pack(const uint8_t* codes, int64_t n_investors, int32_t horizon,
+                  int64_t ld_codes, uint8_t* packed, int64_t ld_packed, void* stream);
 
 /* ------------------------------------------------------------------ *
  * Row statistics (the reference's summary-statistic block)

@@ -176,6 +176,32 @@ def valid_count(data_T: np.ndarray) -> np.ndarray:
     return (np.isfinite(data_T) & (data_T > 0)).sum(axis=-1).astype(np.int64)
 
 
+# ------------------------------------------------- packed outcomes (engine format)
+def pack_codes(codes: np.ndarray, ld: int = 0) -> np.ndarray:
+    """
+    [N,H] codes < 4 -> uint8 [N, ld]: four 2-bit codes per byte, step t in byte
+    t >> 2 at bits 2*(t&3)..+1, pad bits zero (include/rlmd_b200.h, outcome_bits = 2).
+    The reference has no such format; this restates the engine's layout so that
+    the packed sweep can be checked against the reference-pinned counts.
+    """
+    c = np.asarray(codes).astype(np.uint8) & 3
+    n, h = c.shape
+    nb = (h + 3) // 4
+    ld = max(int(ld), nb)
+    pad = np.zeros((n, nb * 4), dtype=np.uint8)
+    pad[:, :h] = c
+    q = pad.reshape(n, nb, 4)
+    out = np.zeros((n, ld), dtype=np.uint8)
+    out[:, :nb] = q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)
+    return out
+
+
+def unpack_codes(packed: np.ndarray, horizon: int) -> np.ndarray:
+    p = np.asarray(packed, dtype=np.uint8)
+    c = np.stack([(p >> s) & 3 for s in (0, 2, 4, 6)], axis=-1)
+    return c.reshape(p.shape[0], -1)[:, :horizon]
+
+
 # --------------------------------------------------------------------- statistics
 def lower_median(v: np.ndarray) -> float:
     """torch.median: ascending order statistic at 0-based index (n-1)//2."""

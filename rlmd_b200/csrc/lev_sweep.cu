@@ -43,6 +43,74 @@ draw_discrete_kernel(const __grid_constant__ Thresholds th, uint64_t seed, int64
   }
 }
 
+// Packed outcomes: four 2-bit codes per byte (step t in byte t>>2, bits 2*(t&3)..+1).
+// One thread per (investor, 32-bit word = 16 steps = 4 Philox blocks): the same
+// draws as draw_discrete_kernel, packed; steps >= H are written as code 0.
+template <int K>
+__global__ void __launch_bounds__(128)
+draw_discrete_packed_kernel(const __grid_constant__ Thresholds th, uint64_t seed, int64_t investor_offset, int32_t H,
+                            int64_t N, int64_t ldb, uint8_t* __restrict__ out) {
+  const int nwords = (H + 15) >> 4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * nwords) return;
+  const int64_t row = idx / nwords;
+  const int w = (int)(idx - row * nwords);
+  const uint64_t id = (uint64_t)(row + investor_offset);
+  uint32_t word = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = w * 4 + q;
+    if (j * 4 >= H) break;
+    const Philox4 r = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)j, PHILOX_TAG_LEV,
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (j * 4 + b < H) word |= (uint32_t)draw_code<K>(u[b], th) << (2 * (q * 4 + b));
+  }
+  uint8_t* dst = out + row * ldb + (int64_t)w * 4;
+  if (w * 4 + 4 <= ldb && (((uintptr_t)dst) & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(dst) = word;
+  } else {
+    for (int b = 0; b < 4 && w * 4 + b < ldb; ++b) dst[b] = (uint8_t)(word >> (8 * b));
+  }
+}
+
+// uint8 codes -> packed: one thread per output byte quad (16 codes)
+__global__ void __launch_bounds__(256)
+pack_codes_kernel(const uint8_t* __restrict__ codes, int64_t ld, int32_t H, int64_t N, uint8_t* __restrict__ packed,
+                  int64_t ldb) {
+  const int nwords = (int)((ldb + 3) >> 2);   // the pad bytes of a row are written too (zero)
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * nwords) return;
+  const int64_t row = idx / nwords;
+  const int w = (int)(idx - row * nwords);
+  const uint8_t* __restrict__ src = codes + row * ld + (int64_t)w * 16;
+  uint32_t word = 0;
+  if (w * 16 + 16 <= H && (((uintptr_t)src) & 15) == 0) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src));
+    const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // four codes, one per byte -> 8 bits
+      const uint32_t c = q[i] & 0x03030303u;
+      const uint32_t b = (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu;
+      word |= b << (8 * i);
+    }
+  } else {
+    for (int i = 0; i < 16; ++i) {
+      const int t = w * 16 + i;
+      if (t < H) word |= (uint32_t)(src[i] & 3u) << (2 * i);
+    }
+  }
+  uint8_t* dst = packed + row * ldb + (int64_t)w * 4;
+  if (w * 4 + 4 <= ldb && (((uintptr_t)dst) & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(dst) = word;
+  } else {
+    for (int b = 0; b < 4 && w * 4 + b < ldb; ++b) dst[b] = (uint8_t)(word >> (8 * b));
+  }
+}
+
 // ------------------------------------------------ LOG, discrete: counting
 // One warp per investor row; lanes stride over 16-byte chunks (coalesced 512 B
 // per warp instruction).  Codes 0..3 are counted with dp4a on bit-planes:
@@ -116,6 +184,122 @@ log_discrete_stream_kernel(const uint8_t* __restrict__ outcomes, int64_t ld, int
 #pragma unroll
       for (int k = 0; k < K; ++k)
         if (n[k] > 0) lw += (double)n[k] * lf.lm[k][g];
+      if (log_w != nullptr) log_w[(int64_t)g * ldT + row] = lw;
+      if (data_T != nullptr) data_T[(int64_t)g * ldT + row] = (float)exp(lw);
+    }
+  }
+}
+
+// ------------------------------------------ LOG, discrete: packed 2-bit codes
+// Same contract as log_discrete_stream_kernel on a quarter of the bytes.  The
+// masks of a code's low / high bit occupy the even bit positions only, so the
+// masks of TWO words share one popc: per 32 codes 2 shifts, 2 LOP3, 2 POPC and
+// 2 adds (POPC issues at 16 lanes/clk/SM: ~1/3 of its rate at the HBM rate).
+template <int K>
+__device__ __forceinline__ void count_pair(uint32_t a, uint32_t b, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+  constexpr uint32_t EVEN = 0x55555555u, ODD = 0xaaaaaaaau;
+  s1 += __popc((a & EVEN) | ((b << 1) & ODD));
+  if (K >= 3) s2 += __popc(((a >> 1) & EVEN) | (b & ODD));
+  if (K >= 4) s3 += __popc((a & (a >> 1) & EVEN) | ((b & (b << 1)) & ODD));
+}
+
+// Rows that start on a 16-byte boundary (every row of pack_codes / lev_draw) are
+// read as whole 16-byte vectors, PACKED_U per lane per iteration, all issued
+// before the first is consumed: a 1e4-step row (2500 bytes) is ONE round trip to
+// DRAM per warp.  The last vector may reach into the row's pad bytes (ld is a
+// multiple of 16 there): the lane that holds it masks the codes of steps >= H.
+constexpr int PACKED_U = 6;
+
+__device__ __forceinline__ void mask_last_vector(uint4& v, int valid /* codes of this vector that are steps < H */) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int vj = min(max(valid - 16 * j, 0), 16);
+    w[j] &= vj >= 16 ? 0xffffffffu : ((1u << (2 * vj)) - 1u);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(COUNT_WARPS * 32)
+log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, int32_t H, int64_t N, int32_t G,
+                           const __grid_constant__ LogFactorTable lf, double logV0, float* __restrict__ data_T,
+                           double* __restrict__ log_w, int32_t* __restrict__ counts, int64_t ldT) {
+  // log-factor table in shared memory: the epilogue indexes it by lane (a per-lane
+  // index into the constant bank would be replayed once per distinct address)
+  __shared__ double slm[K][B200_MAX_GRID];
+  for (int i = threadIdx.x; i < K * B200_MAX_GRID; i += COUNT_WARPS * 32)
+    slm[i / B200_MAX_GRID][i % B200_MAX_GRID] = lf.lm[i / B200_MAX_GRID][i % B200_MAX_GRID];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * COUNT_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * COUNT_WARPS;
+  const int nbytes = (H + 3) >> 2;          // bytes that hold codes
+  const int full = H >> 2;                  // bytes whose four codes are all steps < H
+  const int nvec = (nbytes + 15) >> 4;      // 16-byte vectors that hold codes
+  const bool vec_rows = (ldb & 15) == 0 && ldb >= (int64_t)nvec * 16;
+  auto count_byte = [&](int t, uint32_t& s1, uint32_t& s2, uint32_t& s3, const uint8_t* __restrict__ p) {
+    uint32_t c = p[t];
+    if (t >= full) c &= (1u << (2 * (H & 3))) - 1u;   // the last, partly filled byte
+    s1 += __popc(c & 0x55u);
+    if (K >= 3) s2 += __popc((c >> 1) & 0x55u);
+    if (K >= 4) s3 += __popc(c & (c >> 1) & 0x55u);
+  };
+  for (int64_t row = warp_global; row < N; row += nwarps) {
+    const uint8_t* __restrict__ p = outcomes + row * ldb;
+    uint32_t s1 = 0, s2 = 0, s3 = 0;
+    if (vec_rows && (((uintptr_t)p) & 15) == 0) {
+      const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p);
+      for (int base = 0; base < nvec; base += 32 * PACKED_U) {
+        uint4 v[PACKED_U];
+#pragma unroll
+        for (int u = 0; u < PACKED_U; ++u) {
+          const int idx = base + u * 32 + lane;
+          v[u] = idx < nvec ? __ldcs(q + idx) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (base + 32 * PACKED_U >= nvec) {          // the iteration that holds the row's last vector
+          const int last = nvec - 1 - base - lane;   // == u * 32 for the lane and slot that hold it
+#pragma unroll
+          for (int u = 0; u < PACKED_U; ++u)
+            if (last == u * 32) mask_last_vector(v[u], H - 64 * (nvec - 1));
+        }
+#pragma unroll
+        for (int u = 0; u < PACKED_U; ++u) {
+          count_pair<K>(v[u].x, v[u].y, s1, s2, s3);
+          count_pair<K>(v[u].z, v[u].w, s1, s2, s3);
+        }
+      }
+    } else {
+      // any alignment: head bytes up to 16-byte alignment, body in uint4 (full bytes only), tail bytes
+      const uintptr_t addr = (uintptr_t)p;
+      int head = (int)((16 - (addr & 15)) & 15);
+      if (head > full) head = full;
+      const int body = (full - head) >> 4;
+      const int tail0 = head + (body << 4);
+      for (int t = lane; t < head; t += 32) count_byte(t, s1, s2, s3, p);
+      const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p + head);
+      for (int i = lane; i < body; i += 32) {
+        const uint4 a = __ldcs(q + i);
+        count_pair<K>(a.x, a.y, s1, s2, s3); count_pair<K>(a.z, a.w, s1, s2, s3);
+      }
+      for (int t = tail0 + lane; t < nbytes; t += 32) count_byte(t, s1, s2, s3, p);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      if (K >= 3) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (K >= 4) s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    int n[4];
+    if (K == 2) { n[1] = (int)s1; n[0] = H - n[1]; n[2] = n[3] = 0; }
+    else if (K == 3) { n[1] = (int)s1; n[2] = (int)s2; n[0] = H - n[1] - n[2]; n[3] = 0; }
+    else { n[3] = (int)s3; n[1] = (int)(s1 - s3); n[2] = (int)(s2 - s3); n[0] = H - n[1] - n[2] - n[3]; }
+    if (counts != nullptr && lane < K) counts[row * K + lane] = n[lane];
+    for (int g = lane; g < G; g += 32) {
+      double lw = logV0;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (n[k] > 0) lw += (double)n[k] * slm[k][g];
       if (log_w != nullptr) log_w[(int64_t)g * ldT + row] = lw;
       if (data_T != nullptr) data_T[(int64_t)g * ldT + row] = (float)exp(lw);
     }
@@ -448,20 +632,23 @@ static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, con
   int64_t blocks = (N + COUNT_WARPS - 1) / COUNT_WARPS;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  switch (d.n_outcomes) {
-    case 2:
-      log_discrete_stream_kernel<2><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(
-          outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, logV0, data_T, log_w, counts, out_ld(d));
-      break;
-    case 3:
-      log_discrete_stream_kernel<3><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(
-          outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, logV0, data_T, log_w, counts, out_ld(d));
-      break;
-    default:
-      log_discrete_stream_kernel<4><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(
-          outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, logV0, data_T, log_w, counts, out_ld(d));
-      break;
+#define B200_LOG_LAUNCH(KERNEL, KK)                                                                             \
+  KERNEL<KK><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, \
+                                                            logV0, data_T, log_w, counts, out_ld(d))
+  if (d.outcome_bits == 2) {
+    switch (d.n_outcomes) {
+      case 2: B200_LOG_LAUNCH(log_discrete_packed_kernel, 2); break;
+      case 3: B200_LOG_LAUNCH(log_discrete_packed_kernel, 3); break;
+      default: B200_LOG_LAUNCH(log_discrete_packed_kernel, 4); break;
+    }
+  } else {
+    switch (d.n_outcomes) {
+      case 2: B200_LOG_LAUNCH(log_discrete_stream_kernel, 2); break;
+      case 3: B200_LOG_LAUNCH(log_discrete_stream_kernel, 3); break;
+      default: B200_LOG_LAUNCH(log_discrete_stream_kernel, 4); break;
+    }
   }
+#undef B200_LOG_LAUNCH
   return check_cuda(cudaGetLastError(), "log_discrete_stream launch");
 }
 
@@ -519,7 +706,14 @@ static int validate(const b200_lev_desc* d) {
       for (int k = 1; k < d->n_outcomes - 1; ++k)
         B200_REQUIRE(d->thresholds[k] >= d->thresholds[k - 1], "lev: thresholds must ascend");
   }
-  if (d->source == B200_SRC_STREAM) B200_REQUIRE(d->ld_outcomes >= d->horizon, "lev: ld_outcomes < horizon");
+  B200_REQUIRE(d->outcome_bits == 0 || d->outcome_bits == 8 || d->outcome_bits == 2,
+               "lev: outcome_bits must be 0/8 (uint8 codes) or 2 (packed)");
+  if (d->outcome_bits == 2) {
+    B200_REQUIRE(d->kind == B200_LEV_DISCRETE, "lev: packed outcomes are discrete codes");
+    B200_REQUIRE(d->ld_outcomes >= ((int64_t)d->horizon + 3) / 4, "lev: packed ld_outcomes (bytes) < ceil(horizon/4)");
+  } else if (d->source == B200_SRC_STREAM) {
+    B200_REQUIRE(d->ld_outcomes >= d->horizon, "lev: ld_outcomes < horizon");
+  }
   return 0;
 }
 
@@ -544,6 +738,8 @@ extern "C" int b200_lev_sweep(const b200_lev_desc* desc, const void* outcomes, c
   if (d.kind == B200_LEV_DISCRETE) {
     if (d.mode == B200_MODE_CHAIN) {
       B200_REQUIRE(data_T != nullptr, "lev_sweep: CHAIN mode needs data_T");
+      B200_REQUIRE(d.outcome_bits != 2 || d.source == B200_SRC_PHILOX,
+                   "lev_sweep: the CHAIN kernels take uint8 codes (packed outcomes feed the LOG sweep)");
       return run_chain_discrete(d, (const uint8_t*)outcomes, host_f, 0, d.horizon, nullptr, data_T, nullptr, out_ld(d), st);
     }
     if (d.mode == B200_MODE_LOG) {
@@ -564,8 +760,23 @@ extern "C" int b200_lev_draw(const b200_lev_desc* desc, void* out, void* stream)
   const b200_lev_desc& d = *desc;
   cudaStream_t st = (cudaStream_t)stream;
   B200_REQUIRE(out != nullptr || d.n_investors == 0, "lev_draw: out is NULL");
-  B200_REQUIRE(d.ld_outcomes >= d.horizon, "lev_draw: ld_outcomes < horizon");
   if (d.n_investors == 0) return 0;
+  if (d.outcome_bits == 2) {
+    const int64_t words = d.n_investors * (int64_t)((d.horizon + 15) >> 4);
+    const unsigned pb = (unsigned)((words + 127) / 128);
+    Thresholds th;
+    for (int k = 0; k < B200_MAX_OUTCOMES; ++k) th.t[k] = d.thresholds[k];
+    switch (d.n_outcomes) {
+      case 2: draw_discrete_packed_kernel<2><<<pb, 128, 0, st>>>(th, d.seed, d.investor_offset, d.horizon,
+                                                                 d.n_investors, d.ld_outcomes, (uint8_t*)out); break;
+      case 3: draw_discrete_packed_kernel<3><<<pb, 128, 0, st>>>(th, d.seed, d.investor_offset, d.horizon,
+                                                                 d.n_investors, d.ld_outcomes, (uint8_t*)out); break;
+      default: draw_discrete_packed_kernel<4><<<pb, 128, 0, st>>>(th, d.seed, d.investor_offset, d.horizon,
+                                                                  d.n_investors, d.ld_outcomes, (uint8_t*)out); break;
+    }
+    return check_cuda(cudaGetLastError(), "lev_draw (packed) launch");
+  }
+  B200_REQUIRE(d.ld_outcomes >= d.horizon, "lev_draw: ld_outcomes < horizon");
   const int64_t work = d.n_investors * (int64_t)((d.horizon + 3) >> 2);
   const unsigned blocks = (unsigned)((work + 127) / 128);
   if (d.kind == B200_LEV_GBM) {
@@ -586,6 +797,23 @@ extern "C" int b200_lev_draw(const b200_lev_desc* desc, void* out, void* stream)
   return check_cuda(cudaGetLastError(), "lev_draw launch");
 }
 
+extern "C" int b200_lev_pack(const uint8_t* codes, int64_t n_investors, int32_t horizon, int64_t ld_codes,
+                             uint8_t* packed, int64_t ld_packed, void* stream) {
+  B200_REQUIRE(n_investors >= 0 && horizon >= 1, "lev_pack: need n_investors >= 0 and horizon >= 1");
+  if (n_investors == 0) return 0;
+  B200_REQUIRE(codes != nullptr && packed != nullptr, "lev_pack: NULL buffer");
+  B200_REQUIRE(ld_codes >= horizon, "lev_pack: ld_codes < horizon");
+  B200_REQUIRE(ld_packed >= ((int64_t)horizon + 3) / 4, "lev_pack: ld_packed < ceil(horizon/4)");
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  const int64_t words = n_investors * ((ld_packed + 3) >> 2);
+  const int64_t blocks = (words + 255) / 256;
+  B200_REQUIRE(blocks <= 0x7fffffff, "lev_pack: too many rows for one launch");
+  pack_codes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, ld_codes, horizon, n_investors, packed,
+                                                                         ld_packed);
+  return check_cuda(cudaGetLastError(), "lev_pack launch");
+}
+
 extern "C" int b200_lev_chunk(const b200_lev_desc* desc, const void* outcomes, const float* factors, int32_t t_begin,
                               int32_t t_end, void* state, float* dump, void* stream) {
   int rc = validate(desc);
@@ -599,6 +827,7 @@ extern "C" int b200_lev_chunk(const b200_lev_desc* desc, const void* outcomes, c
   if (d.n_investors == 0) return 0;
   if (d.kind == B200_LEV_DISCRETE) {
     B200_REQUIRE(d.mode == B200_MODE_CHAIN, "lev_chunk: discrete chunks run in CHAIN mode");
+    B200_REQUIRE(d.outcome_bits != 2 || d.source == B200_SRC_PHILOX, "lev_chunk: the CHAIN kernels take uint8 codes");
     B200_REQUIRE(d.source != B200_SRC_PHILOX || (t_begin & 3) == 0, "lev_chunk: Philox chunks start at a multiple of 4");
     float* stf = (float*)state;
     return run_chain_discrete(d, (const uint8_t*)outcomes, factors, t_begin, t_end, t_begin > 0 ? stf : nullptr, stf,

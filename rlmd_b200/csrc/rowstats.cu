@@ -211,8 +211,32 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
       float4 t[RS_ITEMS / 4];
 #pragma unroll
       for (int u = 0; u < RS_ITEMS / 4; ++u) t[u] = __ldcs(v4 + u * RS_THREADS + threadIdx.x);
+      if (PASS == 1) {
+        // eight table lookups are issued before the first (dependent) histogram
+        // branch; two independent fp64 chains per sum (a dependent DADD/DFMA per
+        // element otherwise waits out the fp64 pipe latency)
+        const float* e = reinterpret_cast<const float*>(t);
 #pragma unroll
-      for (int u = 0; u < RS_ITEMS / 4; ++u) { process(t[u].x); process(t[u].y); process(t[u].z); process(t[u].w); }
+        for (int h = 0; h < RS_ITEMS; h += 8) {
+          int off[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) off[u] = lut[float_key_fast<MODE>(e[h + u]) >> (32 - L1_BITS)];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double d = (double)e[h + u] - mean_a;
+            if (u & 1) { a2 += fabs(d); a3 = __fma_rn(d, d, a3); }
+            else { a0 += fabs(d); a1 = __fma_rn(d, d, a1); }
+            if (off[u] >= 0) {
+              const uint32_t k = float_key_fast<MODE>(e[h + u]);
+              atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(smem_hist) + off[u] +
+                                                        ((k >> (L3_BITS - 2)) & ((L2_BINS - 1) << 2))), 1u);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < RS_ITEMS / 4; ++u) { process(t[u].x); process(t[u].y); process(t[u].z); process(t[u].w); }
+      }
     } else {
       for (int u = 0; u < RS_ITEMS; ++u) {
         const int64_t i = base + (int64_t)u * RS_THREADS + threadIdx.x;
@@ -226,7 +250,7 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
     double s = block_sum(a0, red_d);
     if (threadIdx.x == 0) atomic_add_f64(&w->sum_all, s);
   } else if (PASS == 1) {
-    double s0 = block_sum(a0, red_d), s1 = block_sum(a1, red_d);
+    double s0 = block_sum(a0 + a2, red_d), s1 = block_sum(a1 + a3, red_d);
     if (threadIdx.x == 0) { atomic_add_f64(&w->absdev_all, s0); atomic_add_f64(&w->sqdev_all, s1); }
   } else if (PASS == 2) {
     double s0 = block_sum(a0, red_d), s1 = block_sum(a1, red_d);

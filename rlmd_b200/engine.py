@@ -50,6 +50,49 @@ def encode_codes(outcomes, device="cuda") -> torch.Tensor:
     return buf[:, :h]
 
 
+class PackedCodes:
+    """
+    Discrete outcomes at two bits each: `data` is uint8 [N, ld] (CUDA, or pinned
+    host memory for lev_final_host), four codes per byte - step t of a row in byte
+    t >> 2, bits 2*(t&3)..+1 - with ld = ceil(H/4) rounded up to 16 bytes and zero
+    pad bits.  A die roll carries 1.25 bits: the LOG sweep, which is bound by the
+    read of the outcome array, moves a quarter of the bytes (the CHAIN kernels,
+    bound by instruction issue, take uint8 codes).
+    """
+
+    def __init__(self, data: torch.Tensor, horizon: int):
+        if data.dtype != torch.uint8 or data.dim() != 2 or (data.shape[0] > 1 and data.stride(1) != 1):
+            raise ValueError("packed outcomes are a uint8 [N, ld] tensor with unit inner stride")
+        if data.shape[1] * 4 < horizon:
+            raise ValueError("packed outcomes: fewer than ceil(horizon/4) bytes per row")
+        self.data, self.horizon = data, int(horizon)
+
+    @property
+    def shape(self):
+        return (self.data.shape[0], self.horizon)
+
+    def unpack(self) -> torch.Tensor:
+        """uint8 codes [N,H] (torch ops; for tests and one-off conversions)."""
+        d = self.data
+        sh = torch.arange(0, 8, 2, device=d.device, dtype=torch.uint8)
+        codes = (d.unsqueeze(-1) >> sh) & 3
+        return codes.reshape(d.shape[0], -1)[:, : self.horizon].contiguous()
+
+
+def pack_codes(codes: torch.Tensor) -> PackedCodes:
+    """uint8 codes [N,H] on the GPU (encode_codes / lev_draw) -> PackedCodes (b200_lev_pack)."""
+    require_cuda()
+    if not codes.is_cuda or codes.dtype != torch.uint8 or codes.dim() != 2 or codes.stride(1) != 1:
+        raise ValueError("codes must be a [N,H] uint8 CUDA tensor with unit inner stride")
+    n, h = codes.shape
+    ldb = _round_up((h + 3) // 4, 16)
+    out = torch.empty((n, ldb), dtype=torch.uint8, device=codes.device)
+    ld = codes.stride(0) if n > 1 else max(codes.stride(0), h)
+    with torch.cuda.device(codes.device):
+        check(lib.b200_lev_pack(ptr(codes), n, h, ld, ptr(out), ldb, stream_ptr()))
+    return PackedCodes(out, h)
+
+
 def encode_returns(x, device="cuda") -> torch.Tensor:
     """GBM log-returns -> fp32 [N, ld] on the GPU, ld a multiple of 4 (16 bytes)."""
     require_cuda()
@@ -97,7 +140,8 @@ def lev_sweep(
 
     kind      "discrete" (factors [G,K] fp32) or "gbm" (factors = lev[G] fp32)
     outcomes  CUDA tensor [N,H] uint8 (discrete) / float32 (gbm), row stride
-              arbitrary (unit inner stride); None -> Philox draws on device
+              arbitrary (unit inner stride), or PackedCodes (discrete, LOG mode);
+              None -> Philox draws on device
     mode      "chain" (exact fp32 product; discrete only) or "log"
     returns   {"data_T": [G,N] f32, "log_w": [G,N] f64, "counts": [N,K] i32}
     """
@@ -121,15 +165,16 @@ def lev_sweep(
             log_w = torch.empty((g, n), dtype=torch.float64, device=dev)
         if want_counts:
             counts = torch.empty((n, k), dtype=torch.int32, device=dev)
-        check(lib.b200_lev_sweep(C.byref(d), ptr(outcomes), f.ctypes.data_as(C.POINTER(C.c_float)),
+        oc = outcomes.data if isinstance(outcomes, PackedCodes) else outcomes
+        check(lib.b200_lev_sweep(C.byref(d), ptr(oc), f.ctypes.data_as(C.POINTER(C.c_float)),
                                  ptr(data_T), ptr(log_w), ptr(counts), stream_ptr()))
     res["data_T"], res["log_w"], res["counts"] = data_T, log_w, counts
     return res
 
 
 def lev_draw(kind: str, n_investors: int, horizon: int, *, seed: int = 0, investor_offset: int = 0,
-             probs=None, log_mean: float = 0.0, sigma: float = 0.0, device="cuda") -> torch.Tensor:
-    """The outcome array a Philox sweep with the same arguments consumes."""
+             probs=None, log_mean: float = 0.0, sigma: float = 0.0, device="cuda", packed: bool = False):
+    """The outcome array a Philox sweep with the same arguments consumes (packed=True: PackedCodes)."""
     require_cuda()
     d = LevDesc()
     d.n_investors, d.horizon = int(n_investors), int(horizon)
@@ -139,15 +184,23 @@ def lev_draw(kind: str, n_investors: int, horizon: int, *, seed: int = 0, invest
         d.kind, d.n_outcomes = _lib.LEV_DISCRETE, len(probs)
         for i, v in enumerate(philox_thresholds(probs)):
             d.thresholds[i] = v
-        ld = _round_up(horizon, 16)
+        if packed:
+            ld = _round_up((horizon + 3) // 4, 16)
+            d.outcome_bits = 2
+        else:
+            ld = _round_up(horizon, 16)
         out = torch.zeros((n_investors, ld), dtype=torch.uint8, device=device)
     else:
+        if packed:
+            raise ValueError("packed outcomes are discrete codes")
         d.kind, d.log_mean, d.sigma = _lib.LEV_GBM, float(log_mean), float(sigma)
         ld = _round_up(horizon, 4)
         out = torch.zeros((n_investors, ld), dtype=torch.float32, device=device)
     d.ld_outcomes = ld
     with torch.cuda.device(out.device):
         check(lib.b200_lev_draw(C.byref(d), ptr(out), stream_ptr()))
+    if packed:
+        return PackedCodes(out, horizon)
     return out[:, :horizon]
 
 
@@ -170,7 +223,16 @@ def _fill_desc(kind, f, value_0, outcomes, n_investors, horizon, mode, seed, inv
     d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     d.investor_offset = int(investor_offset)
     d.log_mean, d.sigma = float(log_mean), float(sigma)
-    if outcomes is not None:
+    if isinstance(outcomes, PackedCodes):
+        if kind != "discrete" or mode != "log":
+            raise ValueError("packed outcomes feed the discrete LOG sweep (the CHAIN kernels take uint8 codes)")
+        if not outcomes.data.is_cuda:
+            raise ValueError("outcomes must live on the GPU")
+        n, h = outcomes.shape
+        d.source, d.outcome_bits = _lib.SRC_STREAM, 2
+        d.ld_outcomes = outcomes.data.stride(0) if n > 1 else outcomes.data.shape[1]
+        dev = outcomes.data.device
+    elif outcomes is not None:
         if not outcomes.is_cuda:
             raise ValueError("outcomes must live on the GPU (see encode_codes / encode_returns)")
         want = torch.uint8 if kind == "discrete" else torch.float32
@@ -270,7 +332,7 @@ def lev_series(
     return data, data_T
 
 
-def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, outcomes_host: torch.Tensor, *,
+def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, outcomes_host, *,
                    mode: str = "log", chunk_rows: Optional[int] = None, variant: int = 0, device="cuda",
                    return_data_T: bool = False, group=None, n_total: Optional[int] = None):
     """
@@ -278,21 +340,28 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
     (pinned for overlap): investor rows are independent, so the array is walked
     in row chunks through two device staging buffers - the H2D copy of chunk i+1
     overlaps the sweep of chunk i - and the statistics come back to the host.
+    `outcomes_host`: uint8 codes / fp32 returns [N,H], or PackedCodes over a host
+    tensor (a quarter of the bytes over PCIe).
     Returns float64 [G,12] numpy (and data_T on the device when asked).
     """
     require_cuda()
-    if outcomes_host.is_cuda or outcomes_host.dim() != 2:
-        raise ValueError("outcomes_host must be a 2-D host tensor")
+    packed = isinstance(outcomes_host, PackedCodes)
+    host = outcomes_host.data if packed else outcomes_host
+    if host.is_cuda or host.dim() != 2:
+        raise ValueError("outcomes_host must be a 2-D host tensor (or PackedCodes over one)")
     want = torch.uint8 if kind == "discrete" else torch.float32
-    if outcomes_host.dtype != want:
+    if host.dtype != want:
         raise ValueError(f"outcomes_host must be {want}")
+    if packed and (kind != "discrete" or mode != "log"):
+        raise ValueError("packed outcomes feed the discrete LOG sweep")
     f = np.ascontiguousarray(factors, dtype=np.float32)
     g = f.shape[0]
     n, h = outcomes_host.shape
+    w = host.shape[1] if packed else h                      # row width in elements of `host`
     dev = torch.device(device)
-    ld = _round_up(h, 16 if kind == "discrete" else 4)
+    ld = _round_up(w, 16 if kind == "discrete" else 4)
     if chunk_rows is None:
-        chunk_rows = max(1024, (256 << 20) // (ld * outcomes_host.element_size()))
+        chunk_rows = max(1024, (256 << 20) // (ld * host.element_size()))
     chunk_rows = min(chunk_rows, max(n, 1))
     with torch.cuda.device(dev):
         data_T = torch.empty((g, n), dtype=torch.float32, device=dev)
@@ -308,11 +377,11 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
             if i >= 2:
                 copy.wait_event(done[i & 1])
             with torch.cuda.stream(copy):
-                b[:rows, :h].copy_(outcomes_host[r0:r0 + rows], non_blocking=True)
+                b[:rows, :w].copy_(host[r0:r0 + rows], non_blocking=True)
                 ready[i & 1].record(copy)
             comp.wait_event(ready[i & 1])
-            lev_sweep(kind, f, value_0, outcomes=b[:rows, :h], mode=mode, variant=variant,
-                      out_data_T=data_T[:, r0:r0 + rows])
+            oc = PackedCodes(b[:rows], h) if packed else b[:rows, :h]
+            lev_sweep(kind, f, value_0, outcomes=oc, mode=mode, variant=variant, out_data_T=data_T[:, r0:r0 + rows])
             done[i & 1].record(comp)
         stats = rowstats(data_T, top, n_total=n_total, group=group).cpu().numpy() if n > 0 else np.zeros((g, 12))
     return (stats, data_T) if return_data_T else stats

@@ -114,3 +114,14 @@ def test_percentile_type8_matches_numpy():
     for q in (0.05, 0.5, 0.95):
         want = np.percentile(v.astype(np.float64), q * 100, method="median_unbiased")
         assert abs(lo.percentile_type8(v, q) - want) <= 1e-12 * abs(want)
+
+
+def test_packed_code_layout_round_trips():
+    """Engine format with outcome_bits = 2: four codes per byte, little end first, zero pad bits."""
+    rs = np.random.RandomState(0)
+    for h in (1, 3, 4, 5, 16, 17, 63, 300):
+        c = rs.randint(0, 4, size=(7, h)).astype(np.uint8)
+        p = lo.pack_codes(c, ld=(h + 3) // 4 + 5)
+        assert p.shape == (7, (h + 3) // 4 + 5) and not p[:, (h + 3) // 4:].any()
+        assert np.array_equal(lo.unpack_codes(p, h), c)
+    assert lo.pack_codes(np.uint8([[1, 2, 3, 0, 2]])).tolist() == [[0b00111001, 0b00000010]]
