@@ -210,27 +210,25 @@ __device__ __forceinline__ void count_pair(uint32_t a, uint32_t b, uint32_t& s1,
 // multiple of 16 there): the lane that holds it masks the codes of steps >= H.
 constexpr int PACKED_U = 6;
 
-__device__ __forceinline__ void mask_last_vector(uint4& v, int valid /* codes of this vector that are steps < H */) {
-  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int vj = min(max(valid - 16 * j, 0), 16);
-    w[j] &= vj >= 16 ? 0xffffffffu : ((1u << (2 * vj)) - 1u);
-  }
+__device__ __forceinline__ uint32_t word_mask(int valid) {   // low 2*valid bits, valid clamped to 0..16
+  const int v = min(max(valid, 0), 16);
+  return v >= 16 ? 0xffffffffu : ((1u << (2 * v)) - 1u);
+}
+// mask of a vector whose first `valid` codes are steps < H
+__device__ __forceinline__ uint4 last_vector_mask(int valid) {
+  return make_uint4(word_mask(valid), word_mask(valid - 16), word_mask(valid - 32), word_mask(valid - 48));
 }
 
+// A warp takes 32 consecutive rows: it sweeps them one after the other (every
+// lane on the same row: coalesced), lane r keeps the counts of row r, and the
+// log-wealth / exp epilogue then runs once for the 32 rows with one row per lane
+// - 1/32 of the epilogue instructions per row, uniform (constant-bank) table
+// reads and 128-byte coalesced stores of data_T / log_w.
 template <int K>
-__global__ void __launch_bounds__(COUNT_WARPS * 32)
+__global__ void __launch_bounds__(COUNT_WARPS * 32, 4)   // 64 registers: 4 blocks per SM measured best (3: 0.86, 5: 0.83 of HBM)
 log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, int32_t H, int64_t N, int32_t G,
                            const __grid_constant__ LogFactorTable lf, double logV0, float* __restrict__ data_T,
                            double* __restrict__ log_w, int32_t* __restrict__ counts, int64_t ldT) {
-  // log-factor table in shared memory: the epilogue indexes it by lane (a per-lane
-  // index into the constant bank would be replayed once per distinct address)
-  __shared__ double slm[K][B200_MAX_GRID];
-  for (int i = threadIdx.x; i < K * B200_MAX_GRID; i += COUNT_WARPS * 32)
-    slm[i / B200_MAX_GRID][i % B200_MAX_GRID] = lf.lm[i / B200_MAX_GRID][i % B200_MAX_GRID];
-  __syncthreads();
-
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * COUNT_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * COUNT_WARPS;
@@ -238,6 +236,14 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
   const int full = H >> 2;                  // bytes whose four codes are all steps < H
   const int nvec = (nbytes + 15) >> 4;      // 16-byte vectors that hold codes
   const bool vec_rows = (ldb & 15) == 0 && ldb >= (int64_t)nvec * 16;
+  // row-invariant shape of the vector walk (see the row loop)
+  const int iters = (nvec + 32 * PACKED_U - 1) / (32 * PACKED_U);
+  const int rem = nvec - (iters - 1) * 32 * PACKED_U;            // vectors of the last iteration, 1..32*PACKED_U
+  const int tail_slots = (rem + 31) >> 5;                        // slots it uses
+  const int tail_lanes = rem - (tail_slots - 1) * 32;            // lanes of its last slot, 1..32
+  const bool in_tail = lane < tail_lanes;
+  // this lane's mask for the last slot: only the row's very last vector holds pad codes
+  const uint4 wm = lane == tail_lanes - 1 ? last_vector_mask(H - 64 * (nvec - 1)) : make_uint4(~0u, ~0u, ~0u, ~0u);
   auto count_byte = [&](int t, uint32_t& s1, uint32_t& s2, uint32_t& s3, const uint8_t* __restrict__ p) {
     uint32_t c = p[t];
     if (t >= full) c &= (1u << (2 * (H & 3))) - 1u;   // the last, partly filled byte
@@ -245,63 +251,93 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
     if (K >= 3) s2 += __popc((c >> 1) & 0x55u);
     if (K >= 4) s3 += __popc(c & (c >> 1) & 0x55u);
   };
-  for (int64_t row = warp_global; row < N; row += nwarps) {
-    const uint8_t* __restrict__ p = outcomes + row * ldb;
-    uint32_t s1 = 0, s2 = 0, s3 = 0;
-    if (vec_rows && (((uintptr_t)p) & 15) == 0) {
-      const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p);
-      for (int base = 0; base < nvec; base += 32 * PACKED_U) {
-        uint4 v[PACKED_U];
+  for (int64_t row0 = warp_global * 32; row0 < N; row0 += nwarps * 32) {
+    const int nr = (int)min((int64_t)32, N - row0);
+    uint32_t m1 = 0, m2 = 0, m3 = 0;   // sums of row (row0 + lane)
+    for (int r = 0; r < nr; ++r) {
+      const uint8_t* __restrict__ p = outcomes + (row0 + r) * ldb;
+      uint32_t s1 = 0, s2 = 0, s3 = 0;
+      // the next row's lines start their way from DRAM to L2 while this row is counted
+      if (r + 1 < nr)
+        for (int b = lane * 128; b < nbytes; b += 32 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ldb + b));
+      if (vec_rows && (((uintptr_t)p) & 15) == 0) {
+        const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p) + lane;
+        // full iterations: PACKED_U vectors per lane, no predicates
+        for (int it = 0; it + 1 < iters; ++it, q += 32 * PACKED_U) {
+          uint4 v[PACKED_U];
 #pragma unroll
-        for (int u = 0; u < PACKED_U; ++u) {
-          const int idx = base + u * 32 + lane;
-          v[u] = idx < nvec ? __ldcs(q + idx) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (base + 32 * PACKED_U >= nvec) {          // the iteration that holds the row's last vector
-          const int last = nvec - 1 - base - lane;   // == u * 32 for the lane and slot that hold it
+          for (int u = 0; u < PACKED_U; ++u) v[u] = __ldcs(q + u * 32);
 #pragma unroll
-          for (int u = 0; u < PACKED_U; ++u)
-            if (last == u * 32) mask_last_vector(v[u], H - 64 * (nvec - 1));
+          for (int u = 0; u < PACKED_U; ++u) {
+            count_pair<K>(v[u].x, v[u].y, s1, s2, s3);
+            count_pair<K>(v[u].z, v[u].w, s1, s2, s3);
+          }
         }
+        // the row's last `rem` vectors: slots below tail_slots-1 are full, slot
+        // tail_slots-1 ends at lane tail_lanes-1, whose vector reaches into the pad
+        // (everything here but the loaded data was worked out before the row loop)
+        uint4 vl = make_uint4(0u, 0u, 0u, 0u);   // the partly filled last slot, kept apart from the array
+        if (in_tail) vl = __ldcs(q + (tail_slots - 1) * 32);
+        uint4 v[PACKED_U - 1];
 #pragma unroll
-        for (int u = 0; u < PACKED_U; ++u) {
-          count_pair<K>(v[u].x, v[u].y, s1, s2, s3);
-          count_pair<K>(v[u].z, v[u].w, s1, s2, s3);
+        for (int u = 0; u < PACKED_U - 1; ++u)
+          if (u < tail_slots - 1) v[u] = __ldcs(q + u * 32);
+        vl.x &= wm.x; vl.y &= wm.y; vl.z &= wm.z; vl.w &= wm.w;
+        count_pair<K>(vl.x, vl.y, s1, s2, s3);
+        count_pair<K>(vl.z, vl.w, s1, s2, s3);
+#pragma unroll
+        for (int u = 0; u < PACKED_U - 1; ++u) {
+          if (u < tail_slots - 1) {
+            count_pair<K>(v[u].x, v[u].y, s1, s2, s3);
+            count_pair<K>(v[u].z, v[u].w, s1, s2, s3);
+          }
         }
+      } else {
+        // any alignment: head bytes up to 16-byte alignment, body in uint4 (full bytes only), tail bytes
+        const uintptr_t addr = (uintptr_t)p;
+        int head = (int)((16 - (addr & 15)) & 15);
+        if (head > full) head = full;
+        const int body = (full - head) >> 4;
+        const int tail0 = head + (body << 4);
+        for (int t = lane; t < head; t += 32) count_byte(t, s1, s2, s3, p);
+        const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p + head);
+        for (int i = lane; i < body; i += 32) {
+          const uint4 a = __ldcs(q + i);
+          count_pair<K>(a.x, a.y, s1, s2, s3); count_pair<K>(a.z, a.w, s1, s2, s3);
+        }
+        for (int t = tail0 + lane; t < nbytes; t += 32) count_byte(t, s1, s2, s3, p);
       }
-    } else {
-      // any alignment: head bytes up to 16-byte alignment, body in uint4 (full bytes only), tail bytes
-      const uintptr_t addr = (uintptr_t)p;
-      int head = (int)((16 - (addr & 15)) & 15);
-      if (head > full) head = full;
-      const int body = (full - head) >> 4;
-      const int tail0 = head + (body << 4);
-      for (int t = lane; t < head; t += 32) count_byte(t, s1, s2, s3, p);
-      const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p + head);
-      for (int i = lane; i < body; i += 32) {
-        const uint4 a = __ldcs(q + i);
-        count_pair<K>(a.x, a.y, s1, s2, s3); count_pair<K>(a.z, a.w, s1, s2, s3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        if (K >= 3) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        if (K >= 4) s3 += __shfl_xor_sync(0xffffffffu, s3, o);
       }
-      for (int t = tail0 + lane; t < nbytes; t += 32) count_byte(t, s1, s2, s3, p);
+      if (lane == r) { m1 = s1; m2 = s2; m3 = s3; }
     }
+    // ---- epilogue: one row per lane
+    if (lane < nr) {
+      const int64_t row = row0 + lane;
+      int n[4];
+      if (K == 2) { n[1] = (int)m1; n[0] = H - n[1]; n[2] = n[3] = 0; }
+      else if (K == 3) { n[1] = (int)m1; n[2] = (int)m2; n[0] = H - n[1] - n[2]; n[3] = 0; }
+      else { n[3] = (int)m3; n[1] = (int)(m1 - m3); n[2] = (int)(m2 - m3); n[0] = H - n[1] - n[2] - n[3]; }
+      if (counts != nullptr) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      if (K >= 3) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-      if (K >= 4) s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-    }
-    int n[4];
-    if (K == 2) { n[1] = (int)s1; n[0] = H - n[1]; n[2] = n[3] = 0; }
-    else if (K == 3) { n[1] = (int)s1; n[2] = (int)s2; n[0] = H - n[1] - n[2]; n[3] = 0; }
-    else { n[3] = (int)s3; n[1] = (int)(s1 - s3); n[2] = (int)(s2 - s3); n[0] = H - n[1] - n[2] - n[3]; }
-    if (counts != nullptr && lane < K) counts[row * K + lane] = n[lane];
-    for (int g = lane; g < G; g += 32) {
-      double lw = logV0;
+        for (int k = 0; k < K; ++k) counts[row * K + k] = n[k];
+      }
+      double nd[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (n[k] > 0) lw += (double)n[k] * slm[k][g];
-      if (log_w != nullptr) log_w[(int64_t)g * ldT + row] = lw;
-      if (data_T != nullptr) data_T[(int64_t)g * ldT + row] = (float)exp(lw);
+      for (int k = 0; k < K; ++k) nd[k] = (double)n[k];
+      for (int g = 0; g < G; ++g) {
+        double lw = logV0;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (n[k] > 0) lw += nd[k] * lf.lm[k][g];
+        if (log_w != nullptr) log_w[(int64_t)g * ldT + row] = lw;
+        if (data_T != nullptr) data_T[(int64_t)g * ldT + row] = (float)exp(lw);
+      }
     }
   }
 }
@@ -629,12 +665,16 @@ static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, con
     }
   const double logV0 = log((double)d.value_0);
   const int64_t N = d.n_investors;
-  int64_t blocks = (N + COUNT_WARPS - 1) / COUNT_WARPS;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  // a warp per row (uint8 codes) / per 32 rows (packed)
+  const int64_t warps = d.outcome_bits == 2 ? (N + 31) / 32 : N;
+  int64_t blocks = (warps + COUNT_WARPS - 1) / COUNT_WARPS;
+  // packed: one 32-row task per warp, handed out by the block scheduler (a capped
+  // grid would give each warp 3.3 tasks at 1e6 rows: a fifth of the run spent in the tail)
+  const int64_t cap = d.outcome_bits == 2 ? (int64_t)0x7fffffff : (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-#define B200_LOG_LAUNCH(KERNEL, KK)                                                                             \
-  KERNEL<KK><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, \
-                                                            logV0, data_T, log_w, counts, out_ld(d))
+#define B200_LOG_LAUNCH(KERNEL, ...)                                                                                     \
+  KERNEL<__VA_ARGS__><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, \
+                                                                     logV0, data_T, log_w, counts, out_ld(d))
   if (d.outcome_bits == 2) {
     switch (d.n_outcomes) {
       case 2: B200_LOG_LAUNCH(log_discrete_packed_kernel, 2); break;
