@@ -328,8 +328,10 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed, sweep_s = float(t[0]), float(t[1])
     value = n_total * h * args.steps / elapsed
-    # sweep + 4 statistic passes + 4 row-resolve kernels (+ pack / unpack around each of the 4 exchanges)
-    launches_per_step = 1 + 8 + (8 if world > 1 else 0)
+    # sweep + 4 statistic passes + 4 row-resolve kernels; multi-GPU: + 4 flag kernels (peer-memory exchange,
+    # the default) or + pack / unpack around each of the 4 all-reduces (RLMD_B200_EXCHANGE=nccl)
+    exchange = os.environ.get("RLMD_B200_EXCHANGE", "p2p") if world > 1 else None
+    launches_per_step = 1 + 8 + (0 if world == 1 else 4 if exchange == "p2p" else 8)
 
     # ---- end to end: pinned host outcomes -> H2D (overlapped with the sweep) -> statistics -> host
     def measure_e2e(as_packed):
@@ -437,6 +439,8 @@ def run_gpu(args):
         "config": {
             "workload": WORKLOAD, "investors_per_gpu": n, "horizon": h, "leverages": g, "top": top_total,
             "mode": "log-domain final sweep + exact row statistics", "sharding": f"investors x{world}",
+            "statistics_exchange": {None: "none (one GPU)", "p2p": "resolve kernels sum the peers' histograms over "
+                                    "NVLink peer memory", "nccl": "packed NCCL all-reduce per pass"}[exchange],
             "outcome_format": "packed 2-bit codes (2.5 GB per GPU)" if packed else "uint8 codes (10 GB per GPU)",
             "l2": f"inputs ({n * row_bytes / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no explicit flush",
         },

@@ -410,6 +410,32 @@ int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealt
  * buffer staging[rows, int_count + dbl_count] (counts are < 2^53: exact), the
  * caller all-reduces it (one NCCL call per phase), unpack scatters it back.
  * ------------------------------------------------------------------ */
+/* The same exchange WITHOUT a collective library, for the GPUs of one node: the
+ * ranks' workspaces (and small flag blocks) live in memory every process has
+ * mapped (CUDA IPC / torch symmetric memory).  A rank flags each finished pass
+ * in its peers' flag blocks; the resolve kernel that follows waits for the
+ * world's flags and sums the peers' partial histograms straight out of their
+ * memory over NVLink (system-scope loads), every rank in the same order.
+ *   workspace[r] : rank r's rowstats workspace as mapped HERE (>= workspace_bytes(rows))
+ *   flags[r]     : rank r's flag block, uint32 [B200_MAX_PEERS * 4 + 1], zeroed once;
+ *                  word B200_MAX_PEERS*4 of the own block is set when a peer's flag
+ *                  did not arrive within ~10 s (the statistics are then NaN)
+ *   epoch        : 1, 2, 3, ... - one more per call, the same on every rank; successive
+ *                  calls must alternate between two workspaces (a peer may still be
+ *                  reading the previous call's sums)
+ * Runs the whole statistic block (all passes) on `stream`. */
+#define B200_MAX_PEERS 8
+typedef struct b200_peer_set {
+  void* workspace[B200_MAX_PEERS];
+  uint32_t* flags[B200_MAX_PEERS];
+  int32_t world, rank;
+  uint32_t epoch;
+  uint32_t reserved;
+} b200_peer_set;
+int b200_rowstats_p2p(const float* values, int64_t rows, int64_t n, int64_t ld,
+                      int64_t n_total, int64_t top, const b200_peer_set* peers,
+                      double* stats, void* stream);
+
 int b200_exchange_pack(const void* workspace, int64_t words_per_row, int64_t rows,
                        int64_t int_offset, int64_t int_count, int64_t dbl_offset,
                        int64_t dbl_count, double* staging, void* stream);

@@ -41,6 +41,20 @@ class LevDesc(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+
+
+class PeerSet(C.Structure):
+    _fields_ = [
+        ("workspace", C.c_void_p * MAX_PEERS),
+        ("flags", C.c_void_p * MAX_PEERS),
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("epoch", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
 ENV_COIN, ENV_DICE, ENV_GBM, ENV_DICE_SH = 0, 1, 2, 3
 INV_A, INV_B, INV_C, INV_INSURED = 0, 1, 2, 3
 ENV_MAX_GAMBLES = 8
@@ -190,6 +204,7 @@ _SIGNATURES = {
     "b200_rowstats_workspace_bytes": (_i64, [_i64]),
     "b200_rowstats": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "b200_rowstats_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),
+    "b200_rowstats_p2p": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, C.POINTER(PeerSet), _vp, _vp]),
 }
 # extended below as entry points are added; tests/test_cabi.py checks that every
 # symbol declared in include/rlmd_b200.h is listed here and exported.

@@ -26,6 +26,7 @@
 // 8-byte words so that a multi-GPU caller can all-reduce it between passes.
 #include <algorithm>
 #include <cstddef>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -294,6 +295,90 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
   else rowstats_pass_body<PASS, KEY_FULL>(v, n, w, smem_hist);
 }
 
+// ----------------------------------------------------------------------------
+// Multi-GPU without a collective library: every rank's workspace is mapped into
+// every process (CUDA IPC / symmetric memory), a rank raises a flag in each
+// peer's flag block when one of its passes is complete, and the resolve kernel
+// that follows waits for the world's flags and then SUMS the peers' partial
+// histograms and sums straight out of their memory over NVLink - the all-reduce
+// is fused into the kernel that consumes it.  Every rank adds the ranks in the
+// same order, so all of them resolve bit-identical thresholds and means.
+struct PeerSet {
+  RowWS* ws[B200_MAX_PEERS];            // [rank] is this rank's own workspace
+  uint32_t* flags[B200_MAX_PEERS];      // flag blocks: uint32 [B200_MAX_PEERS][4] + 1 error word
+  int32_t world, rank;
+  uint32_t epoch;
+};
+constexpr int FLAG_ERROR_WORD = B200_MAX_PEERS * 4;
+
+__device__ __forceinline__ long long ld_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_sys(const double* p) {
+  return __longlong_as_double(ld_sys(reinterpret_cast<const long long*>(p)));
+}
+
+// One warp: tells every peer that this rank's pass `phase` of call `epoch` is in memory.
+__global__ void rowstats_signal_kernel(const __grid_constant__ PeerSet P, int phase) {
+  const int r = threadIdx.x;
+  if (r >= P.world || r == P.rank) return;
+  __threadfence_system();
+  uint32_t* f = P.flags[r] + P.rank * 4 + phase;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(P.epoch) : "memory");
+}
+
+// Block-wide wait for the peers' flags of `phase`; false after ~10 s (a peer died):
+// the caller then writes NaN statistics instead of hanging the device.
+__device__ bool wait_peers(const PeerSet& P, int phase) {
+  __shared__ int ok_s;
+  if (threadIdx.x == 0) {
+    int ok = 1;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int r = 0; r < P.world && ok; ++r) {
+      if (r == P.rank) continue;
+      const uint32_t* f = P.flags[P.rank] + r * 4 + phase;
+      for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int32_t)(v - P.epoch) >= 0) break;
+        __nanosleep(200);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) { ok = 0; break; }
+      }
+    }
+    if (!ok) P.flags[P.rank][FLAG_ERROR_WORD] = 1u;
+    ok_s = ok;
+  }
+  __syncthreads();
+  return ok_s != 0;
+}
+
+// sum over the world of `count` integer words at `offset` (8-byte words) of row `row`
+__device__ __forceinline__ void gather_i64(const PeerSet& P, int64_t row, int64_t offset, int count, long long* dst) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    long long acc = 0;
+    for (int r = 0; r < P.world; ++r) acc += ld_sys(reinterpret_cast<const long long*>(P.ws[r] + row) + offset + i);
+    dst[i] = acc;
+  }
+}
+__device__ __forceinline__ double gather_f64(const PeerSet& P, int64_t row, int64_t word) {
+  double acc = 0.0;
+  for (int r = 0; r < P.world; ++r) {
+    const double v = ld_sys(reinterpret_cast<const double*>(P.ws[r] + row) + word);
+    acc = r == 0 ? v : acc + v;
+  }
+  return acc;
+}
+__device__ __forceinline__ long long gather_i64_word(const PeerSet& P, int64_t row, int64_t word) {
+  long long acc = 0;
+  for (int r = 0; r < P.world; ++r) acc += ld_sys(reinterpret_cast<const long long*>(P.ws[r] + row) + word);
+  return acc;
+}
+
 // One block per row: walk a histogram to find the bin that holds `rank`.
 // blockDim.x == 256: each thread sums a contiguous run of bins, a block-wide
 // inclusive scan of the 256 partials (warp shuffles + 8 warp totals) names the
@@ -341,21 +426,33 @@ __device__ void find_bin(const long long* __restrict__ hist, int bins, long long
 
 // STEP 0: after pass 0   STEP 1: after pass 1   STEP 2: after pass 2 (order
 // statistics, top / adj split and means)   STEP 3: after pass 3 (writes stats)
+// The step's histograms are first summed over the world into shared memory
+// (world == 1: a copy), then walked there.
 template <int STEP>
 __global__ void __launch_bounds__(256)
-rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, double* __restrict__ stats) {
+rowstats_resolve_kernel(const __grid_constant__ PeerSet P, int64_t n_total, int64_t top, double* __restrict__ stats) {
+  extern __shared__ long long hs[];   // STEP 0: hist1, STEP 1: hist2[NT], STEP 2: hist3[NT]
   __shared__ long long scratch[256];
   __shared__ double red_d[32];
   __shared__ long long red_i[32];
   __shared__ int bin_s;
   __shared__ long long rem_s;
-  RowWS* w = ws + blockIdx.x;
+  const int64_t row = blockIdx.x;
+  RowWS* w = P.ws[P.rank] + row;
   const long long n = n_total, K = top;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+  if (P.world > 1 && !wait_peers(P, STEP)) {
+    if (STEP == 3 && threadIdx.x < 12) stats[row * 12 + threadIdx.x] = qnan;
+    return;
+  }
 
   if (STEP == 0) {
+    gather_i64(P, row, OFF_H1, L1_BINS, hs);
+    __syncthreads();
     const long long ranks[NT] = {(n - 1) / 2, n - K, n - K + (K - 1) / 2, (n - K - 1) / 2};
     for (int j = 0; j < NT; ++j) {
-      find_bin(w->hist1, L1_BINS, ranks[j], &bin_s, &rem_s, scratch);
+      find_bin(hs, L1_BINS, ranks[j], &bin_s, &rem_s, scratch);
       if (threadIdx.x == 0) {
         w->prefix[j] = (unsigned long long)((uint32_t)bin_s << (32 - L1_BITS));
         w->rank[j] = rem_s;
@@ -364,13 +461,13 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
     }
     // anything with the sign bit set (level-1 bins 0..1023)?  4 bins per thread
     int neg = 0;
-    for (int i = 0; i < 4; ++i) neg |= w->hist1[threadIdx.x * 4 + i] != 0;
+    for (int i = 0; i < 4; ++i) neg |= hs[threadIdx.x * 4 + i] != 0;
     neg = __syncthreads_or(neg);
     if (threadIdx.x == 0) {
-      w->key_mode = w->hist1[2047] > 0 ? KEY_FULL : neg ? KEY_NO_NAN : KEY_POSITIVE;
-      w->mean_all = w->sum_all / (double)n;
+      w->key_mode = hs[2047] > 0 ? KEY_FULL : neg ? KEY_NO_NAN : KEY_POSITIVE;
+      w->mean_all = gather_f64(P, row, 0) / (double)n;
       // key bins that can only hold non-finite values: 3 = -inf, 2044 = +inf, 2047 = NaN
-      const long long ninf = w->hist1[3], pinf = w->hist1[2044], nan = w->hist1[2047];
+      const long long ninf = hs[3], pinf = hs[2044], nan = hs[2047];
       const long long hi = pinf + nan;  // sort to the top
       w->nonfinite[0] = (hi + ninf) > 0;
       w->nonfinite[1] = hi > 0 || ninf > n - K;
@@ -380,8 +477,10 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
       w->has_nan[2] = nan > K;
     }
   } else if (STEP == 1) {
+    gather_i64(P, row, OFF_H2, NT * L2_BINS, hs);
+    __syncthreads();
     for (int j = 0; j < NT; ++j) {
-      find_bin(w->hist2[j], L2_BINS, w->rank[j], &bin_s, &rem_s, scratch);
+      find_bin(hs + j * L2_BINS, L2_BINS, w->rank[j], &bin_s, &rem_s, scratch);
       if (threadIdx.x == 0) {
         w->prefix[j] |= (unsigned long long)((uint32_t)bin_s << L3_BITS);
         w->rank[j] = rem_s;
@@ -389,8 +488,10 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
       __syncthreads();
     }
   } else if (STEP == 2) {
+    gather_i64(P, row, OFF_H3, NT * L3_BINS, hs);
+    __syncthreads();
     for (int j = 0; j < NT; ++j) {
-      find_bin(w->hist3[j], L3_BINS, w->rank[j], &bin_s, &rem_s, scratch);
+      find_bin(hs + j * L3_BINS, L3_BINS, w->rank[j], &bin_s, &rem_s, scratch);
       if (threadIdx.x == 0) {
         w->prefix[j] |= (unsigned long long)(uint32_t)bin_s;
         w->rank[j] = rem_s;
@@ -405,7 +506,7 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
     double s_gt = 0, s_lt = 0;
     long long c_gt = 0, c_lt = 0, c_all = 0;
     for (uint32_t lo = threadIdx.x; lo < (uint32_t)L3_BINS; lo += blockDim.x) {
-      const long long c = w->hist3[1][lo];
+      const long long c = hs[L3_BINS + lo];
       c_all += c;
       if (c == 0 || lo == thr_lo) continue;   // an empty bin must not contribute 0 * inf
       const double v = (double)c * (double)key_float(base | lo);
@@ -415,9 +516,11 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
     c_gt = block_sum(c_gt, red_i); c_lt = block_sum(c_lt, red_i); c_all = block_sum(c_all, red_i);
     if (threadIdx.x == 0) {
       const double thr = w->value[1];
+      const long long cnt_gt = gather_i64_word(P, row, OFF_CNT);
+      const double coarse_gt = gather_f64(P, row, 3), coarse_lt = gather_f64(P, row, 4);
       // below thr's prefix = everything that is neither above it nor inside it
-      const long long n_gt = w->cnt_gt + c_gt, n_lt = (n - w->cnt_gt - c_all) + c_lt;
-      const double sum_gt = c_gt ? w->sum_gt + s_gt : w->sum_gt, sum_lt = c_lt ? w->sum_lt + s_lt : w->sum_lt;
+      const long long n_gt = cnt_gt + c_gt, n_lt = (n - cnt_gt - c_all) + c_lt;
+      const double sum_gt = c_gt ? coarse_gt + s_gt : coarse_gt, sum_lt = c_lt ? coarse_lt + s_lt : coarse_lt;
       const long long n_eq = n - n_gt - n_lt;
       const long long tt = K - n_gt;  // ties that belong to the top group
       w->ties_top = tt;
@@ -428,23 +531,25 @@ rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, do
     }
   } else {
     if (threadIdx.x == 0) {
+      const double absdev_all = gather_f64(P, row, 1), sqdev_all = gather_f64(P, row, 2);
+      const double absdev_gt = gather_f64(P, row, 5), sqdev_gt = gather_f64(P, row, 6);
+      const double absdev_lt = gather_f64(P, row, 7), sqdev_lt = gather_f64(P, row, 8);
       const double thr = w->value[1];
       const double dt = thr - w->mean_top, da = thr - w->mean_adj;
       const double tt = (double)w->ties_top, ta = (double)w->ties_adj;
       // a tie share of zero must not contribute inf*0
-      const double abs_top = w->absdev_gt + (tt > 0 ? tt * fabs(dt) : 0.0);
-      const double sq_top = w->sqdev_gt + (tt > 0 ? tt * dt * dt : 0.0);
-      const double abs_adj = w->absdev_lt + (ta > 0 ? ta * fabs(da) : 0.0);
-      const double sq_adj = w->sqdev_lt + (ta > 0 ? ta * da * da : 0.0);
-      double* s = stats + (int64_t)blockIdx.x * 12;
+      const double abs_top = absdev_gt + (tt > 0 ? tt * fabs(dt) : 0.0);
+      const double sq_top = sqdev_gt + (tt > 0 ? tt * dt * dt : 0.0);
+      const double abs_adj = absdev_lt + (ta > 0 ? ta * fabs(da) : 0.0);
+      const double sq_adj = sqdev_lt + (ta > 0 ? ta * da * da : 0.0);
+      double* s = stats + row * 12;
       s[0] = w->mean_all; s[1] = w->mean_top; s[2] = w->mean_adj;
-      s[3] = w->absdev_all / (double)n; s[4] = abs_top / (double)K; s[5] = abs_adj / (double)(n - K);
-      s[6] = sqrt(w->sqdev_all / (double)n); s[7] = sqrt(sq_top / (double)K);
+      s[3] = absdev_all / (double)n; s[4] = abs_top / (double)K; s[5] = abs_adj / (double)(n - K);
+      s[6] = sqrt(sqdev_all / (double)n); s[7] = sqrt(sq_top / (double)K);
       s[8] = sqrt(sq_adj / (double)(n - K));
       s[9] = w->value[0]; s[10] = w->value[2]; s[11] = w->value[3];
       // torch semantics: Welford's std_mean turns any non-finite member into
       // nan mean/std (hence nan MAD); median propagates NaN
-      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
       // ... except that a ONE-element group's mean is the element itself (Welford's
       // first update is exact: mean = +-inf, then std = MAD = nan)
       const long long size[3] = {n, K, n - K};
@@ -480,15 +585,31 @@ static int launch_pass(int pass, const float* values, int64_t rows, int64_t n, i
   return check_cuda(cudaGetLastError(), "rowstats pass launch");
 }
 
-static int launch_resolve(int step, int64_t rows, int64_t n_total, int64_t top, RowWS* ws, double* stats,
+static int launch_resolve(int step, int64_t rows, int64_t n_total, int64_t top, const PeerSet& P, double* stats,
                           cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {   // step 1 sums four 2048-bin histograms of 8-byte counts: 64 KB
+    B200_CUDA(cudaFuncSetAttribute(rowstats_resolve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   NT * L2_BINS * 8));
+    attr_set[dev] = true;
+  }
   switch (step) {
-    case 0: rowstats_resolve_kernel<0><<<(unsigned)rows, 256, 0, st>>>(ws, n_total, top, stats); break;
-    case 1: rowstats_resolve_kernel<1><<<(unsigned)rows, 256, 0, st>>>(ws, n_total, top, stats); break;
-    case 2: rowstats_resolve_kernel<2><<<(unsigned)rows, 256, 0, st>>>(ws, n_total, top, stats); break;
-    case 3: rowstats_resolve_kernel<3><<<(unsigned)rows, 256, 0, st>>>(ws, n_total, top, stats); break;
+    case 0: rowstats_resolve_kernel<0><<<(unsigned)rows, 256, L1_BINS * 8, st>>>(P, n_total, top, stats); break;
+    case 1: rowstats_resolve_kernel<1><<<(unsigned)rows, 256, NT * L2_BINS * 8, st>>>(P, n_total, top, stats); break;
+    case 2: rowstats_resolve_kernel<2><<<(unsigned)rows, 256, NT * L3_BINS * 8, st>>>(P, n_total, top, stats); break;
+    case 3: rowstats_resolve_kernel<3><<<(unsigned)rows, 256, 0, st>>>(P, n_total, top, stats); break;
   }
   return check_cuda(cudaGetLastError(), "rowstats resolve launch");
+}
+
+static PeerSet single_rank(RowWS* ws) {
+  PeerSet P;
+  memset(&P, 0, sizeof(P));
+  P.ws[0] = ws;
+  P.world = 1;
+  return P;
 }
 
 }  // namespace b200
@@ -529,7 +650,7 @@ extern "C" int b200_rowstats(const float* values, int64_t rows, int64_t n, int64
     if (p == 0) {
       B200_CUDA(cudaMemsetAsync(ws, 0, (size_t)rows * sizeof(RowWS), st));
     } else {
-      rc = launch_resolve(p - 1, rows, n_total, top, ws, stats, st);
+      rc = launch_resolve(p - 1, rows, n_total, top, single_rank(ws), stats, st);
       if (rc) return rc;
     }
     if (p <= 3) {
@@ -553,5 +674,43 @@ extern "C" int b200_rowstats_exchange(int32_t phase, int64_t out[5]) {
     default: break;
   }
   out[0] = io; out[1] = ic; out[2] = d_o; out[3] = dc; out[4] = ROW_WORDS;
+  return 0;
+}
+
+// The whole statistic block over investor shards of `world` GPUs of one node, the
+// cross-GPU sums taken by the resolve kernels out of the peers' workspaces.
+extern "C" int b200_rowstats_p2p(const float* values, int64_t rows, int64_t n, int64_t ld, int64_t n_total, int64_t top,
+                                 const b200_peer_set* peers, double* stats, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_REQUIRE(peers != nullptr, "rowstats_p2p: peers is NULL");
+  B200_REQUIRE(peers->world >= 1 && peers->world <= B200_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+               "rowstats_p2p: need 1 <= world <= %d and 0 <= rank < world", B200_MAX_PEERS);
+  B200_REQUIRE(rows >= 0 && n >= 0, "rowstats_p2p: negative size");
+  if (rows == 0) return 0;
+  B200_REQUIRE(rows <= 65535, "rowstats_p2p: rows > 65535 per call");
+  B200_REQUIRE(values != nullptr || n == 0, "rowstats_p2p: values is NULL");
+  B200_REQUIRE(stats != nullptr, "rowstats_p2p: stats is NULL");
+  B200_REQUIRE(n_total >= 2 && n <= n_total, "rowstats_p2p: need n_total >= 2 and n <= n_total");
+  B200_REQUIRE(top >= 1 && top < n_total, "rowstats_p2p: need 1 <= top < n_total (top=%lld)", (long long)top);
+  B200_REQUIRE(ld >= n, "rowstats_p2p: ld < n");
+  PeerSet P;
+  memset(&P, 0, sizeof(P));
+  P.world = peers->world; P.rank = peers->rank; P.epoch = peers->epoch;
+  for (int r = 0; r < peers->world; ++r) {
+    B200_REQUIRE(peers->workspace[r] != nullptr && (peers->world == 1 || peers->flags[r] != nullptr),
+                 "rowstats_p2p: workspace / flags of rank %d is NULL", r);
+    P.ws[r] = (RowWS*)peers->workspace[r];
+    P.flags[r] = peers->flags[r];
+  }
+  RowWS* ws = P.ws[P.rank];
+  B200_CUDA(cudaMemsetAsync(ws, 0, (size_t)rows * sizeof(RowWS), st));
+  for (int p = 0; p < 4; ++p) {
+    if (int rc = launch_pass(p, values, rows, n, ld, ws, st)) return rc;
+    if (P.world > 1) {
+      rowstats_signal_kernel<<<1, 32, 0, st>>>(P, p);
+      B200_CUDA(cudaGetLastError());
+    }
+    if (int rc = launch_resolve(p, rows, n_total, top, P, stats, st)) return rc;
+  }
   return 0;
 }

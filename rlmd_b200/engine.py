@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -394,14 +395,17 @@ def rowstats_workspace(rows: int, device) -> torch.Tensor:
 
 
 def rowstats(values: torch.Tensor, top: int, *, n_total: Optional[int] = None, group=None,
-             workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+             workspace: Optional[torch.Tensor] = None, exchange: Optional[str] = None) -> torch.Tensor:
     """
     The reference's 12 summary statistics for every row of `values` [rows, n]
     (fp32, CUDA, unit inner stride) -> float64 [rows, 12] (STAT_NAMES order).
 
     With `group` (a torch.distributed process group) the rows are investor
-    shards of a global vector of n_total entries: histograms and partial sums are
-    all-reduced between passes, every rank returns the global statistics.
+    shards of a global vector of n_total entries and every rank returns the global
+    statistics.  exchange = "p2p" (default; RLMD_B200_EXCHANGE overrides): the
+    resolve kernels sum the peers' partial histograms out of their memory over
+    NVLink (b200_rowstats_p2p, GPUs of one node); "nccl": one packed all-reduce per
+    pass between the kernels.
     """
     require_cuda()
     if values.dim() != 2 or values.dtype != torch.float32 or not values.is_cuda or values.stride(1) != 1:
@@ -414,11 +418,22 @@ def rowstats(values: torch.Tensor, top: int, *, n_total: Optional[int] = None, g
     if rows == 0:
         return stats
     with torch.cuda.device(dev):
-        ws = workspace if workspace is not None else rowstats_workspace(rows, dev)
         if group is None:
+            ws = workspace if workspace is not None else rowstats_workspace(rows, dev)
             check(lib.b200_rowstats(ptr(values), rows, n, ld, n_total, int(top), ptr(ws), ptr(stats), -1, stream_ptr()))
             return stats
         from . import sharding
+
+        how = exchange or os.environ.get("RLMD_B200_EXCHANGE", "p2p")
+        if how not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if how == "p2p":
+            pw = sharding.peer_workspace(rows, group, dev)
+            ps = pw.peer_set()
+            check(lib.b200_rowstats_p2p(ptr(values), rows, n, ld, n_total, int(top), C.byref(ps), ptr(stats),
+                                        stream_ptr()))
+            return stats
+        ws = workspace if workspace is not None else rowstats_workspace(rows, dev)
 
         def run_phase(phase):
             check(lib.b200_rowstats(ptr(values), rows, n, ld, n_total, int(top), ptr(ws), ptr(stats), phase,

@@ -48,6 +48,70 @@ def global_count(n_local: int, group, device) -> int:
     return int(t.item())
 
 
+class PeerWorkspace:
+    """
+    The statistics workspaces of all ranks of `group` (the GPUs of one node), each
+    mapped into every process through torch's symmetric memory (CUDA IPC over
+    NVLink), for b200_rowstats_p2p: two workspaces per rank (successive calls
+    alternate: a peer may still be summing the previous call's histograms) and one
+    flag block.  Construction and `peer_set` are collective: every rank must make
+    the same calls in the same order.
+    """
+
+    FLAG_WORDS = 64   # uint32 [8 ranks][4 phases] + error word, in 8-byte slots
+
+    def __init__(self, rows: int, group, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from ._lib import MAX_PEERS
+
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > MAX_PEERS:
+            raise ValueError(f"the peer-memory exchange spans at most {MAX_PEERS} GPUs of one node")
+        self.rows = int(rows)
+        self.row_words = int(lib.b200_rowstats_workspace_bytes(1)) // 8
+        words = 2 * self.rows * self.row_words + self.FLAG_WORDS
+        self.buf = symm.empty(words, dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)          # every rank's flags are zero before anyone signals
+        self.epoch = 0
+
+    def peer_set(self):
+        """The b200_peer_set of the next call (advances the epoch: collective)."""
+        from ._lib import PeerSet
+
+        self.epoch += 1
+        parity = self.epoch & 1
+        ps = PeerSet()
+        ps.world, ps.rank, ps.epoch = self.world, self.rank, self.epoch
+        for r in range(self.world):
+            ps.workspace[r] = self.ptrs[r] + 8 * parity * self.rows * self.row_words
+            ps.flags[r] = self.ptrs[r] + 8 * 2 * self.rows * self.row_words
+        return ps
+
+    def timed_out(self) -> bool:
+        """True when a resolve kernel gave up waiting for a peer (its statistics are NaN)."""
+        flags = self.buf[2 * self.rows * self.row_words:].view(torch.int32)
+        return bool(flags[32].item())
+
+
+_peer_cache = {}
+
+
+def peer_workspace(rows: int, group, device) -> PeerWorkspace:
+    """Cached per (group, device); grown (collectively) when a call needs more rows."""
+    key = (id(group), str(device))
+    pw = _peer_cache.get(key)
+    if pw is None or pw.rows < rows:
+        pw = PeerWorkspace(max(rows, 64), group, device)
+        _peer_cache[key] = pw
+    return pw
+
+
 def exchange_phases(run_phase: Callable[[int], None], workspace: torch.Tensor, group, what: str = "rowstats",
                     n_phases: int = N_PHASES) -> None:
     """

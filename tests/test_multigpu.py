@@ -68,8 +68,23 @@ def _worker(rank, world, port, out_dir):
         v[2, ::9] = v[2, 1]
         off, cnt = sharding.shard_range(v.shape[1], world, rank)
         local = torch.as_tensor(v[:, off:off + cnt], device="cuda")
-        st = engine.rowstats(local, 11, n_total=v.shape[1], group=dist.group.WORLD)
+        st = engine.rowstats(local, 11, n_total=v.shape[1], group=dist.group.WORLD)                 # peer memory
         np.save(os.path.join(out_dir, f"stats{rank}.npy"), st.cpu().numpy())
+        st_nccl = engine.rowstats(local, 11, n_total=v.shape[1], group=dist.group.WORLD, exchange="nccl")
+        np.save(os.path.join(out_dir, f"stats_nccl{rank}.npy"), st_nccl.cpu().numpy())
+        # back-to-back calls alternate between the two peer workspaces; rows of every key
+        # mode, a different row count, a rank with far fewer investors than the other
+        pw = sharding.peer_workspace(1, dist.group.WORLD, local.device)
+        for it in range(5):
+            rsi = np.random.RandomState(100 + it)
+            vi = np.exp(rsi.standard_normal((3 + it, 20_011)) * 2).astype(np.float32)
+            vi[0] = rsi.standard_normal(20_011).astype(np.float32)           # sign bit set
+            vi[1, 5] = np.float32(np.nan)
+            cut = 17 if it % 2 else 12_000
+            loc = torch.as_tensor(vi[:, :cut] if rank == 0 else vi[:, cut:], device="cuda")
+            sti = engine.rowstats(loc, 7, n_total=vi.shape[1], group=dist.group.WORLD)
+            np.save(os.path.join(out_dir, f"loop{it}_{rank}.npy"), sti.cpu().numpy())
+        assert not pw.timed_out()
         # (2) the dice_smart_lev shim on sharded rows of the reference's fixture
         case = golden_io.lev_case("dice_top5")
         oc = golden_io.draw_outcomes(case)
@@ -105,9 +120,24 @@ def test_two_ranks_equal_one(tmp_path):
     v[2, ::9] = v[2, 1]
     want = engine.rowstats(torch.as_tensor(v, device="cuda"), 11).cpu().numpy()
     for r in range(world):
-        got = np.load(tmp_path / f"stats{r}.npy")
-        assert np.array_equal(got[:, 9:12], want[:, 9:12])
-        np.testing.assert_allclose(got, want, rtol=1e-12)
+        for name in ("stats", "stats_nccl"):
+            got = np.load(tmp_path / f"{name}{r}.npy")
+            assert np.array_equal(got[:, 9:12], want[:, 9:12])
+            np.testing.assert_allclose(got, want, rtol=1e-12)
+    # the peer-memory exchange sums the ranks in one order everywhere: identical bits on both ranks
+    assert np.array_equal(np.load(tmp_path / "stats0.npy"), np.load(tmp_path / "stats1.npy"))
+    for it in range(5):
+        rsi = np.random.RandomState(100 + it)
+        vi = np.exp(rsi.standard_normal((3 + it, 20_011)) * 2).astype(np.float32)
+        vi[0] = rsi.standard_normal(20_011).astype(np.float32)
+        vi[1, 5] = np.float32(np.nan)
+        wi = engine.rowstats(torch.as_tensor(vi, device="cuda"), 7).cpu().numpy()
+        for r in range(world):
+            gi = np.load(tmp_path / f"loop{it}_{r}.npy")
+            assert np.array_equal(np.isnan(gi), np.isnan(wi))
+            ok = ~np.isnan(wi)
+            assert np.array_equal(gi[:, 9:12][ok[:, 9:12]], wi[:, 9:12][ok[:, 9:12]])
+            np.testing.assert_allclose(gi[ok], wi[ok], rtol=1e-12)
     case = golden_io.lev_case("dice_top5")
     gold = golden_io.load("lev_dice_top5")
     cols = gold["cols"]
