@@ -289,31 +289,35 @@ def run_gpu(args):
                                packed=packed)
     row_bytes = (h + 3) // 4 if packed else h            # algorithmic bytes per investor row
     resident = outcomes.data if packed else outcomes
-    data_T = torch.empty((g, n), dtype=torch.float32, device=dev)
-    ws = engine.rowstats_workspace(g, dev)
+    # the public pipeline object: sweep on one stream, the statistics of the previous step beside it on another
+    # (--no-pipeline: one data_T buffer, i.e. every sweep waits for the previous step's statistics)
+    pipe = engine.FinalSweepPipeline("discrete", table, V0, top_total, device=dev, group=group, n_total=n_total,
+                                     depth=1 if args.no_pipeline else 2)
+    pipe.timing = True
     stats_holder = {}
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [None] * args.steps
 
     def step(i=None):
+        stats_holder["s"] = pipe.submit(outcomes)
         if i is not None:
-            ev[i][0].record()
-        engine.lev_sweep("discrete", table, V0, outcomes=outcomes, mode="log", out_data_T=data_T)
-        if i is not None:
-            ev[i][1].record()
-        stats_holder["s"] = engine.rowstats(data_T, top_total, n_total=n_total, group=group, workspace=ws)
+            ev[i] = pipe.last_sweep
 
     for _ in range(max(args.warmup, 3)):
         step()
+    pipe.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
+    cur = torch.cuda.current_stream()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(args.steps):
         step(i)
+    cur.wait_stream(pipe.sweep_stream)
+    cur.wait_stream(pipe.stats_stream)
     t_end.record()
     sampler.sample()
     torch.cuda.synchronize()
@@ -439,6 +443,9 @@ def run_gpu(args):
         "config": {
             "workload": WORKLOAD, "investors_per_gpu": n, "horizon": h, "leverages": g, "top": top_total,
             "mode": "log-domain final sweep + exact row statistics", "sharding": f"investors x{world}",
+            "pipeline": "none: each sweep waits for the previous step's statistics" if args.no_pipeline else
+                        "engine.FinalSweepPipeline: the statistics of step i run beside the sweep of step i+1 "
+                        "(two streams, two data_T buffers)",
             "statistics_exchange": {None: "none (one GPU)", "p2p": "resolve kernels sum the peers' histograms over "
                                     "NVLink peer memory", "nccl": "packed NCCL all-reduce per pass"}[exchange],
             "outcome_format": "packed 2-bit codes (2.5 GB per GPU)" if packed else "uint8 codes (10 GB per GPU)",
@@ -464,6 +471,8 @@ def main():
     ap.add_argument("--investors", type=int, default=N_INVESTORS, help="investors per GPU")
     ap.add_argument("--format", default="packed2", choices=["packed2", "u8"],
                     help="resident outcome format: 2-bit packed codes (default) or one uint8 per roll")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="run sweep and statistics of consecutive steps strictly one after the other")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -413,9 +413,10 @@ int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealt
 /* The same exchange WITHOUT a collective library, for the GPUs of one node: the
  * ranks' workspaces (and small flag blocks) live in memory every process has
  * mapped (CUDA IPC / torch symmetric memory).  A rank flags each finished pass
- * in its peers' flag blocks; the resolve kernel that follows waits for the
- * world's flags and sums the peers' partial histograms straight out of their
- * memory over NVLink (system-scope loads), every rank in the same order.
+ * in its peers' flag blocks; a gather kernel then waits for the world's flags and
+ * sums the peers' partial histograms straight out of their memory over NVLink
+ * (system-scope vector loads, every rank in the same order) into local scratch
+ * that the resolve kernel walks.
  *   workspace[r] : rank r's rowstats workspace as mapped HERE (>= workspace_bytes(rows))
  *   flags[r]     : rank r's flag block, uint32 [B200_MAX_PEERS * 4 + 1], zeroed once;
  *                  word B200_MAX_PEERS*4 of the own block is set when a peer's flag
@@ -428,6 +429,7 @@ int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealt
 typedef struct b200_peer_set {
   void* workspace[B200_MAX_PEERS];
   uint32_t* flags[B200_MAX_PEERS];
+  void* sums;   /* LOCAL scratch of workspace_bytes(rows): the cross-GPU sums of the step being resolved */
   int32_t world, rank;
   uint32_t epoch;
   uint32_t reserved;

@@ -48,6 +48,7 @@ class PeerSet(C.Structure):
     _fields_ = [
         ("workspace", C.c_void_p * MAX_PEERS),
         ("flags", C.c_void_p * MAX_PEERS),
+        ("sums", C.c_void_p),
         ("world", C.c_int32),
         ("rank", C.c_int32),
         ("epoch", C.c_uint32),

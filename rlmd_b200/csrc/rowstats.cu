@@ -64,9 +64,9 @@ struct RowWS {
   long long nonfinite[3];   // all / top / adj group holds +-inf or NaN (torch.std_mean -> nan)
   long long has_nan[3];     // all / top / adj group holds a NaN (torch.median -> nan)
   long long key_mode;       // KEY_FULL / KEY_NO_NAN / KEY_POSITIVE for passes 1..3 (from hist1)
-  long long pad_r[1];
+  long long pad_r[2];
 };
-static_assert(sizeof(RowWS) % 8 == 0, "8-byte words");
+static_assert(sizeof(RowWS) % 16 == 0, "8-byte words, rows 16-byte aligned (the peer gather loads word pairs)");
 static_assert(offsetof(RowWS, hist1) == 16 * 8 && offsetof(RowWS, cnt_gt) == (16 + L1_BINS + NT * L2_BINS) * 8 &&
                   offsetof(RowWS, hist3) == offsetof(RowWS, cnt_gt) + 64,
               "exchange offsets follow the struct");
@@ -357,26 +357,48 @@ __device__ bool wait_peers(const PeerSet& P, int phase) {
   return ok_s != 0;
 }
 
-// sum over the world of `count` integer words at `offset` (8-byte words) of row `row`
-__device__ __forceinline__ void gather_i64(const PeerSet& P, int64_t row, int64_t offset, int count, long long* dst) {
-  for (int i = threadIdx.x; i < count; i += blockDim.x) {
-    long long acc = 0;
-    for (int r = 0; r < P.world; ++r) acc += ld_sys(reinterpret_cast<const long long*>(P.ws[r] + row) + offset + i);
-    dst[i] = acc;
-  }
+// vector load of two 8-byte words, system scope
+__device__ __forceinline__ void ld_sys_v2(const long long* p, long long& a, long long& b) {
+  asm volatile("ld.relaxed.sys.global.v2.s64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
-__device__ __forceinline__ double gather_f64(const PeerSet& P, int64_t row, int64_t word) {
-  double acc = 0.0;
-  for (int r = 0; r < P.world; ++r) {
-    const double v = ld_sys(reinterpret_cast<const double*>(P.ws[r] + row) + word);
-    acc = r == 0 ? v : acc + v;
+
+// The cross-GPU sum of one step's exchange region (the words b200_rowstats_exchange
+// names), written to this rank's `gsum` workspace for the resolve kernel that
+// follows.  grid = (slices, rows), 256 threads, two words per thread: all of a
+// thread's loads - one 16-byte vector per rank - are in flight together, so a row's
+// region costs about one NVLink round trip.  Integer words are added, double
+// words are added in rank order (the same order on every rank).
+template <int STEP>
+__global__ void __launch_bounds__(256)
+rowstats_gather_kernel(const __grid_constant__ PeerSet P, RowWS* __restrict__ gsum) {
+  constexpr int64_t IOFF = STEP == 0 ? OFF_H1 : STEP == 1 ? OFF_H2 : OFF_CNT;
+  constexpr int ICNT = STEP == 0 ? L1_BINS : STEP == 1 ? NT * L2_BINS : STEP == 2 ? 8 + NT * L3_BINS : 0;
+  constexpr int DOFF = STEP == 0 ? 0 : STEP == 1 ? 1 : STEP == 2 ? 3 : 5;
+  constexpr int DCNT = STEP == 0 ? 1 : STEP == 1 ? 2 : STEP == 2 ? 2 : 4;
+  const int64_t row = blockIdx.y;
+  if (!wait_peers(P, STEP)) return;   // the error word is set: the final resolve writes NaN
+  long long* dst = reinterpret_cast<long long*>(gsum + row);
+  const int i = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (i < ICNT) {
+    long long a[B200_MAX_PEERS], b[B200_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < B200_MAX_PEERS; ++r)
+      if (r < P.world) ld_sys_v2(reinterpret_cast<const long long*>(P.ws[r] + row) + IOFF + i, a[r], b[r]);
+    long long sa = 0, sb = 0;
+#pragma unroll
+    for (int r = 0; r < B200_MAX_PEERS; ++r)
+      if (r < P.world) { sa += a[r]; sb += b[r]; }
+    dst[IOFF + i] = sa;
+    dst[IOFF + i + 1] = sb;
   }
-  return acc;
-}
-__device__ __forceinline__ long long gather_i64_word(const PeerSet& P, int64_t row, int64_t word) {
-  long long acc = 0;
-  for (int r = 0; r < P.world; ++r) acc += ld_sys(reinterpret_cast<const long long*>(P.ws[r] + row) + word);
-  return acc;
+  if (blockIdx.x == 0 && threadIdx.x < DCNT) {
+    double acc = 0.0;
+    for (int r = 0; r < P.world; ++r) {
+      const double v = ld_sys(reinterpret_cast<const double*>(P.ws[r] + row) + DOFF + threadIdx.x);
+      acc = r == 0 ? v : acc + v;
+    }
+    reinterpret_cast<double*>(dst)[DOFF + threadIdx.x] = acc;
+  }
 }
 
 // One block per row: walk a histogram to find the bin that holds `rank`.
@@ -430,25 +452,30 @@ __device__ void find_bin(const long long* __restrict__ hist, int bins, long long
 // (world == 1: a copy), then walked there.
 template <int STEP>
 __global__ void __launch_bounds__(256)
-rowstats_resolve_kernel(const __grid_constant__ PeerSet P, int64_t n_total, int64_t top, double* __restrict__ stats) {
+rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own, const uint32_t* __restrict__ error_word,
+                        int64_t n_total, int64_t top, double* __restrict__ stats) {
   extern __shared__ long long hs[];   // STEP 0: hist1, STEP 1: hist2[NT], STEP 2: hist3[NT]
   __shared__ long long scratch[256];
   __shared__ double red_d[32];
   __shared__ long long red_i[32];
   __shared__ int bin_s;
   __shared__ long long rem_s;
+  // `sums`: where the pass kernels' sums and histograms are - this rank's own
+  // workspace (one GPU, or all-reduced in place by the caller) or the cross-GPU
+  // sums of rowstats_gather_kernel; `own`: where the resolved prefixes / means go.
   const int64_t row = blockIdx.x;
-  RowWS* w = P.ws[P.rank] + row;
+  RowWS* w = own + row;
+  const long long* si = reinterpret_cast<const long long*>(sums + row);
+  const double* sd = reinterpret_cast<const double*>(sums + row);
   const long long n = n_total, K = top;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-
-  if (P.world > 1 && !wait_peers(P, STEP)) {
-    if (STEP == 3 && threadIdx.x < 12) stats[row * 12 + threadIdx.x] = qnan;
+  if (STEP == 3 && error_word != nullptr && *error_word) {   // a peer's flag never arrived
+    if (threadIdx.x < 12) stats[row * 12 + threadIdx.x] = qnan;
     return;
   }
 
   if (STEP == 0) {
-    gather_i64(P, row, OFF_H1, L1_BINS, hs);
+    for (int i = threadIdx.x; i < L1_BINS; i += blockDim.x) hs[i] = si[OFF_H1 + i];
     __syncthreads();
     const long long ranks[NT] = {(n - 1) / 2, n - K, n - K + (K - 1) / 2, (n - K - 1) / 2};
     for (int j = 0; j < NT; ++j) {
@@ -465,7 +492,7 @@ rowstats_resolve_kernel(const __grid_constant__ PeerSet P, int64_t n_total, int6
     neg = __syncthreads_or(neg);
     if (threadIdx.x == 0) {
       w->key_mode = hs[2047] > 0 ? KEY_FULL : neg ? KEY_NO_NAN : KEY_POSITIVE;
-      w->mean_all = gather_f64(P, row, 0) / (double)n;
+      w->mean_all = sd[0] / (double)n;
       // key bins that can only hold non-finite values: 3 = -inf, 2044 = +inf, 2047 = NaN
       const long long ninf = hs[3], pinf = hs[2044], nan = hs[2047];
       const long long hi = pinf + nan;  // sort to the top
@@ -477,7 +504,7 @@ rowstats_resolve_kernel(const __grid_constant__ PeerSet P, int64_t n_total, int6
       w->has_nan[2] = nan > K;
     }
   } else if (STEP == 1) {
-    gather_i64(P, row, OFF_H2, NT * L2_BINS, hs);
+    for (int i = threadIdx.x; i < NT * L2_BINS; i += blockDim.x) hs[i] = si[OFF_H2 + i];
     __syncthreads();
     for (int j = 0; j < NT; ++j) {
       find_bin(hs + j * L2_BINS, L2_BINS, w->rank[j], &bin_s, &rem_s, scratch);
@@ -488,7 +515,7 @@ rowstats_resolve_kernel(const __grid_constant__ PeerSet P, int64_t n_total, int6
       __syncthreads();
     }
   } else if (STEP == 2) {
-    gather_i64(P, row, OFF_H3, NT * L3_BINS, hs);
+    for (int i = threadIdx.x; i < NT * L3_BINS; i += blockDim.x) hs[i] = si[OFF_H3 + i];
     __syncthreads();
     for (int j = 0; j < NT; ++j) {
       find_bin(hs + j * L3_BINS, L3_BINS, w->rank[j], &bin_s, &rem_s, scratch);
@@ -516,8 +543,8 @@ rowstats_resolve_kernel(const __grid_constant__ PeerSet P, int64_t n_total, int6
     c_gt = block_sum(c_gt, red_i); c_lt = block_sum(c_lt, red_i); c_all = block_sum(c_all, red_i);
     if (threadIdx.x == 0) {
       const double thr = w->value[1];
-      const long long cnt_gt = gather_i64_word(P, row, OFF_CNT);
-      const double coarse_gt = gather_f64(P, row, 3), coarse_lt = gather_f64(P, row, 4);
+      const long long cnt_gt = si[OFF_CNT];
+      const double coarse_gt = sd[3], coarse_lt = sd[4];
       // below thr's prefix = everything that is neither above it nor inside it
       const long long n_gt = cnt_gt + c_gt, n_lt = (n - cnt_gt - c_all) + c_lt;
       const double sum_gt = c_gt ? coarse_gt + s_gt : coarse_gt, sum_lt = c_lt ? coarse_lt + s_lt : coarse_lt;
@@ -531,9 +558,8 @@ rowstats_resolve_kernel(const __grid_constant__ PeerSet P, int64_t n_total, int6
     }
   } else {
     if (threadIdx.x == 0) {
-      const double absdev_all = gather_f64(P, row, 1), sqdev_all = gather_f64(P, row, 2);
-      const double absdev_gt = gather_f64(P, row, 5), sqdev_gt = gather_f64(P, row, 6);
-      const double absdev_lt = gather_f64(P, row, 7), sqdev_lt = gather_f64(P, row, 8);
+      const double absdev_all = sd[1], sqdev_all = sd[2];
+      const double absdev_gt = sd[5], sqdev_gt = sd[6], absdev_lt = sd[7], sqdev_lt = sd[8];
       const double thr = w->value[1];
       const double dt = thr - w->mean_top, da = thr - w->mean_adj;
       const double tt = (double)w->ties_top, ta = (double)w->ties_adj;
@@ -566,8 +592,10 @@ static int launch_pass(int pass, const float* values, int64_t rows, int64_t n, i
                        cudaStream_t st) {
   if (n <= 0 || rows <= 0) return 0;
   // Several waves of blocks (the last, partly filled wave then costs little), but
-  // at least four tiles of work per block so that flushing its shared-memory
-  // histogram stays a small share of its time.
+  // at least four tiles of work per block so that zeroing and flushing its
+  // shared-memory histograms stays a small share of its time.  (Measured: a single
+  // wave of 16-tile blocks is 30 % slower on 20 rows x 1e6 and 8 % slower on
+  // 320 x 1e6 - the stream needs the many blocks to keep enough loads in flight.)
   const int sms = sm_count();
   const int64_t tile = (int64_t)RS_THREADS * RS_ITEMS;
   int64_t slices = ((int64_t)sms * 32 + rows - 1) / rows;
@@ -585,31 +613,36 @@ static int launch_pass(int pass, const float* values, int64_t rows, int64_t n, i
   return check_cuda(cudaGetLastError(), "rowstats pass launch");
 }
 
-static int launch_resolve(int step, int64_t rows, int64_t n_total, int64_t top, const PeerSet& P, double* stats,
-                          cudaStream_t st) {
+static int launch_resolve(int step, int64_t rows, int64_t n_total, int64_t top, const RowWS* sums, RowWS* own,
+                          const uint32_t* error_word, double* stats, cudaStream_t st) {
   static bool attr_set[64] = {false};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && !attr_set[dev]) {   // step 1 sums four 2048-bin histograms of 8-byte counts: 64 KB
+  if (dev < 64 && !attr_set[dev]) {   // step 1 walks four 2048-bin histograms of 8-byte counts: 64 KB
     B200_CUDA(cudaFuncSetAttribute(rowstats_resolve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    NT * L2_BINS * 8));
     attr_set[dev] = true;
   }
+  const unsigned g = (unsigned)rows;
   switch (step) {
-    case 0: rowstats_resolve_kernel<0><<<(unsigned)rows, 256, L1_BINS * 8, st>>>(P, n_total, top, stats); break;
-    case 1: rowstats_resolve_kernel<1><<<(unsigned)rows, 256, NT * L2_BINS * 8, st>>>(P, n_total, top, stats); break;
-    case 2: rowstats_resolve_kernel<2><<<(unsigned)rows, 256, NT * L3_BINS * 8, st>>>(P, n_total, top, stats); break;
-    case 3: rowstats_resolve_kernel<3><<<(unsigned)rows, 256, 0, st>>>(P, n_total, top, stats); break;
+    case 0: rowstats_resolve_kernel<0><<<g, 256, L1_BINS * 8, st>>>(sums, own, error_word, n_total, top, stats); break;
+    case 1: rowstats_resolve_kernel<1><<<g, 256, NT * L2_BINS * 8, st>>>(sums, own, error_word, n_total, top, stats); break;
+    case 2: rowstats_resolve_kernel<2><<<g, 256, NT * L3_BINS * 8, st>>>(sums, own, error_word, n_total, top, stats); break;
+    case 3: rowstats_resolve_kernel<3><<<g, 256, 0, st>>>(sums, own, error_word, n_total, top, stats); break;
   }
   return check_cuda(cudaGetLastError(), "rowstats resolve launch");
 }
 
-static PeerSet single_rank(RowWS* ws) {
-  PeerSet P;
-  memset(&P, 0, sizeof(P));
-  P.ws[0] = ws;
-  P.world = 1;
-  return P;
+static int launch_gather(int step, int64_t rows, const PeerSet& P, RowWS* gsum, cudaStream_t st) {
+  const int icnt[4] = {L1_BINS, NT * L2_BINS, 8 + NT * L3_BINS, 0};
+  dim3 grid((unsigned)std::max(1, (icnt[step] + 511) / 512), (unsigned)rows);
+  switch (step) {
+    case 0: rowstats_gather_kernel<0><<<grid, 256, 0, st>>>(P, gsum); break;
+    case 1: rowstats_gather_kernel<1><<<grid, 256, 0, st>>>(P, gsum); break;
+    case 2: rowstats_gather_kernel<2><<<grid, 256, 0, st>>>(P, gsum); break;
+    case 3: rowstats_gather_kernel<3><<<grid, 256, 0, st>>>(P, gsum); break;
+  }
+  return check_cuda(cudaGetLastError(), "rowstats gather launch");
 }
 
 }  // namespace b200
@@ -650,7 +683,7 @@ extern "C" int b200_rowstats(const float* values, int64_t rows, int64_t n, int64
     if (p == 0) {
       B200_CUDA(cudaMemsetAsync(ws, 0, (size_t)rows * sizeof(RowWS), st));
     } else {
-      rc = launch_resolve(p - 1, rows, n_total, top, single_rank(ws), stats, st);
+      rc = launch_resolve(p - 1, rows, n_total, top, ws, ws, nullptr, stats, st);
       if (rc) return rc;
     }
     if (p <= 3) {
@@ -703,14 +736,19 @@ extern "C" int b200_rowstats_p2p(const float* values, int64_t rows, int64_t n, i
     P.flags[r] = peers->flags[r];
   }
   RowWS* ws = P.ws[P.rank];
+  RowWS* gsum = (RowWS*)peers->sums;
+  B200_REQUIRE(P.world == 1 || gsum != nullptr, "rowstats_p2p: sums workspace is NULL");
   B200_CUDA(cudaMemsetAsync(ws, 0, (size_t)rows * sizeof(RowWS), st));
   for (int p = 0; p < 4; ++p) {
     if (int rc = launch_pass(p, values, rows, n, ld, ws, st)) return rc;
-    if (P.world > 1) {
-      rowstats_signal_kernel<<<1, 32, 0, st>>>(P, p);
-      B200_CUDA(cudaGetLastError());
+    if (P.world == 1) {
+      if (int rc = launch_resolve(p, rows, n_total, top, ws, ws, nullptr, stats, st)) return rc;
+      continue;
     }
-    if (int rc = launch_resolve(p, rows, n_total, top, P, stats, st)) return rc;
+    rowstats_signal_kernel<<<1, 32, 0, st>>>(P, p);
+    B200_CUDA(cudaGetLastError());
+    if (int rc = launch_gather(p, rows, P, gsum, st)) return rc;
+    if (int rc = launch_resolve(p, rows, n_total, top, gsum, ws, P.flags[P.rank] + FLAG_ERROR_WORD, stats, st)) return rc;
   }
   return 0;
 }

@@ -388,6 +388,76 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
     return (stats, data_T) if return_data_T else stats
 
 
+class FinalSweepPipeline:
+    """
+    A sequence of final-time sweeps (the *_fixed_final_lev hot path: LOG sweep ->
+    data_T [G,N] -> 12 statistics per leverage) on one GPU or one investor shard,
+    with the statistics of sweep i running beside sweep i+1: two streams, `depth`
+    data_T buffers.  The statistic passes are short kernels with dependent launches
+    (and, across GPUs, four exchange points); next to the HBM-bound sweep they fill
+    otherwise idle time.  Results are those of lev_sweep + rowstats called one after
+    the other.
+
+        pipe = FinalSweepPipeline("discrete", table, 100.0, top, device=dev)
+        stats = [pipe.submit(oc) for oc in outcome_arrays]   # float64 [G,12] each, on the device
+        pipe.synchronize()                                   # then read them
+    """
+
+    def __init__(self, kind: str, factors: np.ndarray, value_0: float, top: int, *, device="cuda", group=None,
+                 n_total: Optional[int] = None, depth: int = 2):
+        require_cuda()
+        self.kind, self.value_0, self.top = kind, float(value_0), int(top)
+        self.factors = np.ascontiguousarray(factors, dtype=np.float32)
+        self.group, self.n_total = group, n_total
+        self.dev = torch.device(device)
+        self.depth = max(1, int(depth))
+        with torch.cuda.device(self.dev):
+            # the statistics' short, dependent kernels go first whenever they are ready
+            self.sweep_stream, self.stats_stream = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+        self.data_T = [None] * self.depth
+        self.ws = [None] * self.depth
+        self.free = [None] * self.depth       # statistics that last read data_T[b]
+        self.count = 0
+        self.last_sweep = None                # (start, end) events of the last sweep, when timing is on
+        self.timing = False
+
+    def submit(self, outcomes, factors: Optional[np.ndarray] = None) -> torch.Tensor:
+        f = self.factors if factors is None else np.ascontiguousarray(factors, dtype=np.float32)
+        g = f.shape[0]
+        n = outcomes.shape[0]
+        b = self.count % self.depth
+        self.count += 1
+        with torch.cuda.device(self.dev):
+            cur = torch.cuda.current_stream()
+            self.sweep_stream.wait_stream(cur)        # the caller produced `outcomes` on its stream
+            with torch.cuda.stream(self.sweep_stream):
+                if self.free[b] is not None:
+                    self.sweep_stream.wait_event(self.free[b])
+                if self.data_T[b] is None or tuple(self.data_T[b].shape) != (g, n):
+                    self.data_T[b] = torch.empty((g, n), dtype=torch.float32, device=self.dev)
+                    self.ws[b] = rowstats_workspace(g, self.dev)
+                if self.timing:
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t0.record(self.sweep_stream)
+                lev_sweep(self.kind, f, self.value_0, outcomes=outcomes, mode="log", out_data_T=self.data_T[b])
+                swept = torch.cuda.Event(enable_timing=self.timing)
+                swept.record(self.sweep_stream)
+                if self.timing:
+                    self.last_sweep = (t0, swept)
+            with torch.cuda.stream(self.stats_stream):
+                self.stats_stream.wait_event(swept)
+                stats = rowstats(self.data_T[b], self.top, n_total=self.n_total, group=self.group,
+                                 workspace=self.ws[b])
+                done = torch.cuda.Event()
+                done.record(self.stats_stream)
+                self.free[b] = done
+        return stats
+
+    def synchronize(self) -> None:
+        self.sweep_stream.synchronize()
+        self.stats_stream.synchronize()
+
+
 # ----------------------------------------------------------------- rowstats
 def rowstats_workspace(rows: int, device) -> torch.Tensor:
     nbytes = lib.b200_rowstats_workspace_bytes(rows)

@@ -71,7 +71,7 @@ class PeerWorkspace:
             raise ValueError(f"the peer-memory exchange spans at most {MAX_PEERS} GPUs of one node")
         self.rows = int(rows)
         self.row_words = int(lib.b200_rowstats_workspace_bytes(1)) // 8
-        words = 2 * self.rows * self.row_words + self.FLAG_WORDS
+        words = 3 * self.rows * self.row_words + self.FLAG_WORDS    # two alternating workspaces, the sums, the flags
         self.buf = symm.empty(words, dtype=torch.int64, device=device)
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, group)
@@ -90,12 +90,13 @@ class PeerWorkspace:
         ps.world, ps.rank, ps.epoch = self.world, self.rank, self.epoch
         for r in range(self.world):
             ps.workspace[r] = self.ptrs[r] + 8 * parity * self.rows * self.row_words
-            ps.flags[r] = self.ptrs[r] + 8 * 2 * self.rows * self.row_words
+            ps.flags[r] = self.ptrs[r] + 8 * 3 * self.rows * self.row_words
+        ps.sums = self.ptrs[self.rank] + 8 * 2 * self.rows * self.row_words
         return ps
 
     def timed_out(self) -> bool:
         """True when a resolve kernel gave up waiting for a peer (its statistics are NaN)."""
-        flags = self.buf[2 * self.rows * self.row_words:].view(torch.int32)
+        flags = self.buf[3 * self.rows * self.row_words:].view(torch.int32)
         return bool(flags[32].item())
 
 

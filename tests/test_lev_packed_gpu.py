@@ -116,3 +116,19 @@ def test_chain_mode_refuses_packed_outcomes(eng):
         eng.lev_sweep("discrete", np.float32([[1.0, 1.1]]), 1.0, outcomes=p, mode="chain")
     with pytest.raises(ValueError):
         eng.PackedCodes(torch.zeros((4, 1), dtype=torch.uint8), 8)      # 1 byte cannot hold 8 codes
+
+
+def test_pipelined_final_sweeps_equal_the_sequential_calls(eng):
+    """FinalSweepPipeline overlaps the statistics of sweep i with sweep i+1: same numbers, any order of completion."""
+    rs = np.random.RandomState(2)
+    n, h, top = 30_000, 257, 3
+    f = np.float32([[1.25, 0.75, 1.025], [1.5, 0.5, 1.05], [1.05, 0.95, 1.005]])
+    arrays = [eng.pack_codes(eng.encode_codes(rs.randint(0, 3, size=(n, h)).astype(np.uint8))) for _ in range(5)]
+    arrays.append(eng.encode_codes(rs.randint(0, 3, size=(n, h)).astype(np.uint8)))    # uint8 codes too
+    want = [eng.rowstats(eng.lev_sweep("discrete", f, 100.0, outcomes=a, mode="log")["data_T"], top) for a in arrays]
+    pipe = eng.FinalSweepPipeline("discrete", f, 100.0, top)
+    got = [pipe.submit(a) for a in arrays]
+    pipe.synchronize()
+    for g, w in zip(got, want):
+        assert torch.equal(g[:, 9:12], w[:, 9:12])                      # order statistics: exact
+        assert torch.allclose(g, w, rtol=1e-12, atol=0)                 # fp64 sums: block order varies
