@@ -332,6 +332,14 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed, sweep_s = float(t[0]), float(t[1])
     value = n_total * h * args.steps / elapsed
+    # the count kernel alone (nothing beside it), after the timed region: beside the statistics kernels of the
+    # previous step its live launch duration above is longer than its own
+    alone_s = _event_time(torch, lambda: engine.lev_sweep("discrete", table, V0, outcomes=outcomes, mode="log",
+                                                          out_data_T=pipe.data_T[0]), 2, 20)
+    if world > 1:
+        t = torch.tensor([alone_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        alone_s = float(t[0])
     # sweep + 4 statistic passes + 4 row-resolve kernels; multi-GPU: + 4 flag kernels (peer-memory exchange,
     # the default) or + pack / unpack around each of the 4 all-reduces (RLMD_B200_EXCHANGE=nccl)
     exchange = os.environ.get("RLMD_B200_EXCHANGE", "p2p") if world > 1 else None
@@ -421,6 +429,10 @@ def run_gpu(args):
         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
         "algorithmic_bytes_per_launch": n * row_bytes, "bytes_per_investor_step": row_bytes / h,
         "avg_launch_ms": sweep_s * 1e3,
+        "alone": {"avg_launch_ms": alone_s * 1e3, "achieved": n * row_bytes / alone_s / 1e9,
+                  "frac": n * row_bytes / alone_s / 1e9 / hbm_peak,
+                  "note": "the same launch with nothing beside it (20 launches after the timed region); in the timed "
+                          "region the statistics kernels of the previous step share the GPU with it"},
     }
 
     cpu = None

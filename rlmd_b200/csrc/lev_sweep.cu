@@ -228,7 +228,7 @@ template <int K>
 __global__ void __launch_bounds__(COUNT_WARPS * 32, 4)   // 64 registers: 4 blocks per SM measured best (3: 0.86, 5: 0.83 of HBM)
 log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, int32_t H, int64_t N, int32_t G,
                            const __grid_constant__ LogFactorTable lf, double logV0, float* __restrict__ data_T,
-                           double* __restrict__ log_w, int32_t* __restrict__ counts, int64_t ldT) {
+                           double* __restrict__ log_w, int32_t* __restrict__ counts, int64_t ldT, int32_t task_rows) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * COUNT_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * COUNT_WARPS;
@@ -251,8 +251,8 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
     if (K >= 3) s2 += __popc((c >> 1) & 0x55u);
     if (K >= 4) s3 += __popc(c & (c >> 1) & 0x55u);
   };
-  for (int64_t row0 = warp_global * 32; row0 < N; row0 += nwarps * 32) {
-    const int nr = (int)min((int64_t)32, N - row0);
+  for (int64_t row0 = warp_global * task_rows; row0 < N; row0 += nwarps * task_rows) {
+    const int nr = (int)min((int64_t)task_rows, N - row0);
     uint32_t m1 = 0, m2 = 0, m3 = 0;   // sums of row (row0 + lane)
     for (int r = 0; r < nr; ++r) {
       const uint8_t* __restrict__ p = outcomes + (row0 + r) * ldb;
@@ -666,7 +666,11 @@ static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, con
   const double logV0 = log((double)d.value_0);
   const int64_t N = d.n_investors;
   // a warp per row (uint8 codes) / per 32 rows (packed)
-  const int64_t warps = d.outcome_bits == 2 ? (N + 31) / 32 : N;
+  // rows per packed task (<= 32: one lane per row in the epilogue).  Fewer rows = shorter-lived blocks
+  // (kernels on other streams get SM slots sooner) but a thinner epilogue.
+  static const int task_rows = [] { const char* e = getenv("B200_PACKED_TASK_ROWS"); int v = e ? atoi(e) : 32;
+                                    return v < 1 ? 1 : v > 32 ? 32 : v; }();
+  const int64_t warps = d.outcome_bits == 2 ? (N + task_rows - 1) / task_rows : N;
   int64_t blocks = (warps + COUNT_WARPS - 1) / COUNT_WARPS;
   // packed: one 32-row task per warp, handed out by the block scheduler (a capped
   // grid would give each warp 3.3 tasks at 1e6 rows: a fifth of the run spent in the tail)
@@ -674,13 +678,16 @@ static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, con
   if (blocks > cap) blocks = cap;
 #define B200_LOG_LAUNCH(KERNEL, ...)                                                                                     \
   KERNEL<__VA_ARGS__><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, \
-                                                                     logV0, data_T, log_w, counts, out_ld(d))
+                                                                     logV0, data_T, log_w, counts, out_ld(d) B200_EXTRA)
   if (d.outcome_bits == 2) {
+#define B200_EXTRA , task_rows
     switch (d.n_outcomes) {
       case 2: B200_LOG_LAUNCH(log_discrete_packed_kernel, 2); break;
       case 3: B200_LOG_LAUNCH(log_discrete_packed_kernel, 3); break;
       default: B200_LOG_LAUNCH(log_discrete_packed_kernel, 4); break;
     }
+#undef B200_EXTRA
+#define B200_EXTRA
   } else {
     switch (d.n_outcomes) {
       case 2: B200_LOG_LAUNCH(log_discrete_stream_kernel, 2); break;
@@ -689,6 +696,7 @@ static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, con
     }
   }
 #undef B200_LOG_LAUNCH
+#undef B200_EXTRA
   return check_cuda(cudaGetLastError(), "log_discrete_stream launch");
 }
 
