@@ -198,11 +198,10 @@ replay_store_host_kernel(const b200_replay_desc d, const __grid_constant__ HostR
 // restates it word for word.
 constexpr unsigned long long SET_EMPTY = ~0ull;
 
-__global__ void __launch_bounds__(1024)
-replay_draw_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t B, uint64_t seed, uint64_t draw_index,
-                   const int64_t* __restrict__ draw_counter, int64_t lanes, int64_t lane_len, int32_t table_size,
-                   int64_t* __restrict__ out_idx) {
-  extern __shared__ unsigned long long table[];
+__device__ __forceinline__ void draw_block(const b200_replay_desc& d, int64_t filled_arg, int32_t B, uint64_t seed,
+                                           uint64_t draw_index, const int64_t* __restrict__ draw_counter,
+                                           int64_t lanes, int64_t lane_len, int32_t table_size,
+                                           int64_t* __restrict__ out_idx, unsigned long long* table) {
   // lanes > 1 (collector): every lane holds the same number of transitions and the
   // memory is slot-major (slot = local * lanes + lane), so the filled part is the
   // prefix [0, lanes * lane_filled) and a drawn value is a slot
@@ -262,6 +261,14 @@ replay_draw_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t B, uint
     }
     if (!__syncthreads_or(pending_bits != 0)) break;
   }
+}
+
+__global__ void __launch_bounds__(1024)
+replay_draw_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t B, uint64_t seed, uint64_t draw_index,
+                   const int64_t* __restrict__ draw_counter, int64_t lanes, int64_t lane_len, int32_t table_size,
+                   int64_t* __restrict__ out_idx) {
+  extern __shared__ unsigned long long table[];
+  draw_block(d, filled_arg, B, seed, draw_index, draw_counter, lanes, lane_len, table_size, out_idx, table);
 }
 
 // ----------------------------------------------------------------- gather
@@ -343,16 +350,14 @@ replay_gather_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, 
 // flight (the lane-group kernel above keeps 4): the gather is a chain of three
 // dependent memory latencies (slot -> bookkeeping -> rows), and throughput is
 // the number of chains in flight.  Same arithmetic, term by term.
-__global__ void __launch_bounds__(256)
-replay_gather_thread_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, int64_t n_samples,
-                            int64_t filled_arg, int64_t lanes, int64_t lane_len, int32_t n_steps, int32_t additive,
-                            const __grid_constant__ GammaPow gp, float* __restrict__ out_state,
-                            float* __restrict__ out_action, float* __restrict__ out_reward,
-                            float* __restrict__ out_next_state, uint8_t* __restrict__ out_done,
-                            int64_t* __restrict__ out_eff) {
+__device__ __forceinline__ void gather_sample(const b200_replay_desc& d, const int64_t* __restrict__ idx, int64_t q,
+                                              int64_t filled_arg, int64_t lanes, int64_t lane_len, int32_t n_steps,
+                                              int32_t additive, const GammaPow& gp, float* __restrict__ out_state,
+                                              float* __restrict__ out_action, float* __restrict__ out_reward,
+                                              float* __restrict__ out_next_state, uint8_t* __restrict__ out_done,
+                                              int64_t* __restrict__ out_eff) {
   const int S = d.state_dim, A = d.action_dim;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_samples;
-       q += (int64_t)gridDim.x * blockDim.x) {
+  {
     const int64_t slot = idx[q];
     const int64_t lane_id = (slot >= 0 && lanes > 1) ? slot % lanes : 0;
     const int64_t i = (slot >= 0 && lanes > 1) ? slot / lanes : slot;
@@ -417,6 +422,38 @@ replay_gather_thread_kernel(const b200_replay_desc d, const int64_t* __restrict_
     out_done[q] = term;
     out_eff[q] = eff;
   }
+}
+
+__global__ void __launch_bounds__(256)
+replay_gather_thread_kernel(const b200_replay_desc d, const int64_t* __restrict__ idx, int64_t n_samples,
+                            int64_t filled_arg, int64_t lanes, int64_t lane_len, int32_t n_steps, int32_t additive,
+                            const __grid_constant__ GammaPow gp, float* __restrict__ out_state,
+                            float* __restrict__ out_action, float* __restrict__ out_reward,
+                            float* __restrict__ out_next_state, uint8_t* __restrict__ out_done,
+                            int64_t* __restrict__ out_eff) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_samples;
+       q += (int64_t)gridDim.x * blockDim.x)
+    gather_sample(d, idx, q, filled_arg, lanes, lane_len, n_steps, additive, gp, out_state, out_action, out_reward,
+                  out_next_state, out_done, out_eff);
+}
+
+// Narrow rows, indices drawn on the device: ONE launch per call - the block that
+// drew a mini-batch's indices gathers its samples (a 256-sample call is bound by
+// launch latency: two dependent launches cost twice as much as one).
+__global__ void __launch_bounds__(1024)
+replay_draw_gather_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t B, uint64_t seed, uint64_t draw_index,
+                          const int64_t* __restrict__ draw_counter, int64_t lanes, int64_t lane_len,
+                          int32_t table_size, int64_t* __restrict__ out_idx, int32_t n_steps, int32_t additive,
+                          const __grid_constant__ GammaPow gp, float* __restrict__ out_state,
+                          float* __restrict__ out_action, float* __restrict__ out_reward,
+                          float* __restrict__ out_next_state, uint8_t* __restrict__ out_done,
+                          int64_t* __restrict__ out_eff) {
+  extern __shared__ unsigned long long table[];
+  draw_block(d, filled_arg, B, seed, draw_index, draw_counter, lanes, lane_len, table_size, out_idx, table);
+  __syncthreads();   // the block's own writes of out_idx
+  for (int t = threadIdx.x; t < B; t += blockDim.x)
+    gather_sample(d, out_idx, (int64_t)blockIdx.x * B + t, filled_arg, lanes, lane_len, n_steps, additive, gp,
+                  out_state, out_action, out_reward, out_next_state, out_done, out_eff);
 }
 
 static int check_desc(const b200_replay_desc* d) {
@@ -521,6 +558,8 @@ int replay_sample_lanes(const b200_replay_desc* d, int64_t lanes, int64_t lane_l
   B200_REQUIRE(out_state && out_action && out_reward && out_next_state && out_done && out_eff,
                "replay_sample: an output pointer is NULL");
   cudaStream_t st = (cudaStream_t)stream;
+  GammaPow gp;
+  for (int t = 0; t < B200_REPLAY_MAX_STEPS; ++t) gp.v[t] = (multi_steps > 1 && t < multi_steps) ? gamma_pow_host[t] : 0.0f;
   if (idx == nullptr) {
     B200_REQUIRE(out_idx != nullptr, "replay_sample: out_idx is NULL while indices are drawn on the device");
     if (batch > 8192) return set_error(B200_ELIMIT, "replay_sample: on-device draw supports batch <= 8192 (got %d)", batch);
@@ -534,14 +573,24 @@ int replay_sample_lanes(const b200_replay_desc* d, int64_t lanes, int64_t lane_l
     B200_CUDA(cudaGetDevice(&dev));
     if (smem > 48 * 1024 && dev < 64 && !attr_set[dev]) {
       B200_CUDA(cudaFuncSetAttribute(replay_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      B200_CUDA(cudaFuncSetAttribute(replay_draw_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     128 * 1024));
       attr_set[dev] = true;
+    }
+    // narrow rows, a few mini-batches (the latency-bound call: a 256-sample draw + gather is two dependent
+    // launches otherwise): one launch.  Many mini-batches keep the separate gather, whose thread-per-sample
+    // grid is the faster one (5.7e9 against 4.6e9 samples/s at 1024 x 256).
+    if (d->state_dim < 32 && n_batches <= 4) {
+      replay_draw_gather_kernel<<<(unsigned)n_batches, threads, smem, st>>>(
+          *d, filled, batch, seed, draw_index, draw_counter, lanes, lane_len, table, out_idx, multi_steps, additive,
+          gp, out_state, out_action, out_reward, out_next_state, out_done, out_eff);
+      B200_CUDA(cudaGetLastError());
+      return 0;
     }
     replay_draw_kernel<<<(unsigned)n_batches, threads, smem, st>>>(*d, filled, batch, seed, draw_index, draw_counter,
                                                                     lanes, lane_len, table, out_idx);
     idx = out_idx;
   }
-  GammaPow gp;
-  for (int t = 0; t < B200_REPLAY_MAX_STEPS; ++t) gp.v[t] = (multi_steps > 1 && t < multi_steps) ? gamma_pow_host[t] : 0.0f;
   if (d->state_dim >= 32) {
     const int64_t want_blocks = (n_samples * 32 + 255) / 256;
     const int grid = (int)std::min<int64_t>(want_blocks, (int64_t)sm_count() * 8);
