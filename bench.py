@@ -12,6 +12,9 @@ pass of the `dice_fixed_final_lev` hot path over one synthetic outcome array:
 The outcome array is resident in HBM in the engine's packed format (2 bits per
 roll, `--format packed2`, the default; `--format u8` = one byte per roll): the
 sweep is bound by the one read of that array, so its size is the cost.
+Steps run strictly one after the other (sweep, then its statistics); the rate of
+the same steps through engine.FinalSweepPipeline (statistics of step i beside
+the sweep of step i+1) is reported as `pipelined` (`--pipeline` times that mode).
 With N GPUs (one process per GPU, torchrun) every rank owns its own 1e6
 investors (weak scaling); the only cross-GPU traffic is the all-reduce of the
 per-leverage partial sums and radix histograms inside the statistics.
@@ -289,10 +292,11 @@ def run_gpu(args):
                                packed=packed)
     row_bytes = (h + 3) // 4 if packed else h            # algorithmic bytes per investor row
     resident = outcomes.data if packed else outcomes
-    # the public pipeline object: sweep on one stream, the statistics of the previous step beside it on another
-    # (--no-pipeline: one data_T buffer, i.e. every sweep waits for the previous step's statistics)
+    # the public pipeline object with ONE data_T buffer: every sweep waits for the previous step's statistics,
+    # so a step is sweep -> statistics, one after the other (--pipeline: two buffers, the statistics of step i
+    # run beside the sweep of step i+1)
     pipe = engine.FinalSweepPipeline("discrete", table, V0, top_total, device=dev, group=group, n_total=n_total,
-                                     depth=1 if args.no_pipeline else 2)
+                                     depth=2 if args.pipeline else 1)
     pipe.timing = True
     stats_holder = {}
     ev = [None] * args.steps
@@ -397,6 +401,34 @@ def run_gpu(args):
                     "statistics read back to the host every step (PCIe-bound)",
         }
 
+    # ---- the same K steps through a two-buffer pipeline (statistics of step i beside the sweep of step i+1)
+    pipelined = None
+    if not args.pipeline and not args.no_secondary:
+        p2 = engine.FinalSweepPipeline("discrete", table, V0, top_total, device=dev, group=group, n_total=n_total,
+                                       depth=2)
+        for _ in range(3):
+            p2.submit(outcomes)
+        p2.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            p2.submit(outcomes)
+        cur.wait_stream(p2.sweep_stream)
+        cur.wait_stream(p2.stats_stream)
+        b.record()
+        torch.cuda.synchronize()
+        dtp = a.elapsed_time(b) * 1e-3
+        if world > 1:
+            t = torch.tensor([dtp], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtp = float(t[0])
+        pipelined = {"value": n_total * h * args.steps / dtp, "unit": UNIT, "ms_per_step": 1e3 * dtp / args.steps,
+                     "note": "engine.FinalSweepPipeline with two data_T buffers, measured after the timed region"}
+        del p2
+
     # ---- end to end: pinned host outcomes -> H2D (overlapped with the sweep) -> statistics -> host
     e2e = None
     if not args.no_e2e:
@@ -431,8 +463,8 @@ def run_gpu(args):
         "avg_launch_ms": sweep_s * 1e3,
         "alone": {"avg_launch_ms": alone_s * 1e3, "achieved": n * row_bytes / alone_s / 1e9,
                   "frac": n * row_bytes / alone_s / 1e9 / hbm_peak,
-                  "note": "the same launch with nothing beside it (20 launches after the timed region); in the timed "
-                          "region the statistics kernels of the previous step share the GPU with it"},
+                  "note": "the same launch, 20 times after the timed region (with --pipeline the statistics kernels "
+                          "of the previous step share the GPU with it inside the timed region)"},
     }
 
     cpu = None
@@ -455,9 +487,9 @@ def run_gpu(args):
         "config": {
             "workload": WORKLOAD, "investors_per_gpu": n, "horizon": h, "leverages": g, "top": top_total,
             "mode": "log-domain final sweep + exact row statistics", "sharding": f"investors x{world}",
-            "pipeline": "none: each sweep waits for the previous step's statistics" if args.no_pipeline else
-                        "engine.FinalSweepPipeline: the statistics of step i run beside the sweep of step i+1 "
-                        "(two streams, two data_T buffers)",
+            "pipeline": "engine.FinalSweepPipeline: the statistics of step i run beside the sweep of step i+1 "
+                        "(two streams, two data_T buffers)" if args.pipeline else
+                        "none: each sweep waits for the previous step's statistics",
             "statistics_exchange": {None: "none (one GPU)", "p2p": "resolve kernels sum the peers' histograms over "
                                     "NVLink peer memory", "nccl": "packed NCCL all-reduce per pass"}[exchange],
             "outcome_format": "packed 2-bit codes (2.5 GB per GPU)" if packed else "uint8 codes (10 GB per GPU)",
@@ -465,7 +497,7 @@ def run_gpu(args):
         },
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
-        "path_steps_per_s": value * g, "secondary": secondary,
+        "path_steps_per_s": value * g, "pipelined": pipelined, "secondary": secondary,
         "check": {"median_wealth_lev0": float(stats[0, 9]), "mean_wealth_lev0": float(stats[0, 0])},
     }
     print(json.dumps(line), flush=True)
@@ -483,8 +515,9 @@ def main():
     ap.add_argument("--investors", type=int, default=N_INVESTORS, help="investors per GPU")
     ap.add_argument("--format", default="packed2", choices=["packed2", "u8"],
                     help="resident outcome format: 2-bit packed codes (default) or one uint8 per roll")
-    ap.add_argument("--no-pipeline", action="store_true",
-                    help="run sweep and statistics of consecutive steps strictly one after the other")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="timed region: the statistics of step i beside the sweep of step i+1 (two streams); by default "
+                         "steps run strictly one after the other and the pipelined rate is reported as `pipelined`")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
