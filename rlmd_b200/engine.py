@@ -497,6 +497,8 @@ def rowstats(values: torch.Tensor, top: int, *, n_total: Optional[int] = None, g
         how = exchange or os.environ.get("RLMD_B200_EXCHANGE", "p2p")
         if how not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if how == "p2p" and not sharding.peer_memory_available(group, dev):
+            how = "nccl"     # no peer mapping between these GPUs: the all-reduce path (both run on the GPUs)
         if how == "p2p":
             pw = sharding.peer_workspace(rows, group, dev)
             ps = pw.peer_set()

@@ -101,6 +101,34 @@ class PeerWorkspace:
 
 
 _peer_cache = {}
+_peer_ok = {}
+
+
+def peer_memory_available(group, device) -> bool:
+    """
+    Whether the ranks of `group` can map each other's memory (torch symmetric
+    memory: the GPUs of one node with peer access).  Decided once per group by ALL
+    ranks together (a collective: a rank that cannot allocate vetoes for everyone),
+    so that every rank takes the same exchange path afterwards.
+    """
+    import sys
+
+    import torch.distributed as dist
+
+    key = (id(group), str(device))
+    if key not in _peer_ok:
+        ok = 1
+        try:
+            _peer_cache[key] = PeerWorkspace(64, group, device)
+        except Exception as exc:  # noqa: BLE001 - any failure means "use the all-reduce path"
+            ok = 0
+            print(f"rlmd_b200: peer-memory exchange unavailable ({exc}); using NCCL all-reduces", file=sys.stderr)
+        t = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        _peer_ok[key] = bool(t.item())
+        if not _peer_ok[key]:
+            _peer_cache.pop(key, None)
+    return _peer_ok[key]
 
 
 def peer_workspace(rows: int, group, device) -> PeerWorkspace:

@@ -85,6 +85,17 @@ def _worker(rank, world, port, out_dir):
             sti = engine.rowstats(loc, 7, n_total=vi.shape[1], group=dist.group.WORLD)
             np.save(os.path.join(out_dir, f"loop{it}_{rank}.npy"), sti.cpu().numpy())
         assert not pw.timed_out()
+        # the two-stream pipeline on shards: statistics (with their cross-GPU sums) beside the next sweep
+        f = np.float32([[1.25, 0.75, 1.025], [1.5, 0.5, 1.05]])
+        arrays = [engine.lev_draw("discrete", 20_000, 257, seed=50 + j, investor_offset=rank * 20_000,
+                                  probs=(1 / 6, 1 / 6, 2 / 3), packed=True) for j in range(4)]
+        seq = [engine.rowstats(engine.lev_sweep("discrete", f, 100.0, outcomes=a, mode="log")["data_T"], 4,
+                               n_total=40_000, group=dist.group.WORLD) for a in arrays]
+        pipe = engine.FinalSweepPipeline("discrete", f, 100.0, 4, group=dist.group.WORLD, n_total=40_000)
+        got = [pipe.submit(a) for a in arrays]
+        pipe.synchronize()
+        for g_, w_ in zip(got, seq):
+            assert torch.equal(g_[:, 9:12], w_[:, 9:12]) and torch.allclose(g_, w_, rtol=1e-12, atol=0)
         # (2) the dice_smart_lev shim on sharded rows of the reference's fixture
         case = golden_io.lev_case("dice_top5")
         oc = golden_io.draw_outcomes(case)
