@@ -7,8 +7,9 @@ small inputs in the other files):
   (sum = H) and follow the die's probabilities; log-wealth is the linear form
   log V0 + sum_k n_k log m_gk of those counts (recomputed in torch fp64); the exact
   fp32 chain agrees with exp(log-wealth); the three chain variants are
-  bit-identical; investor slices reproduce the full run; Philox shards are
-  invisible; the order statistics equal torch.sort's.
+  bit-identical; the 2-bit packed array gives the uint8 sweep bit for bit;
+  investor slices reproduce the full run; Philox shards are invisible; the
+  order statistics equal torch.sort's.
 * C4  GBM, one GPU's shard (1.25e7 x 1e4, on-device Philox): W(l) W(-l) = V0^2,
   growth rates follow l (mu - sigma^2/2), valid-run counts equal the finite
   positive entries.
@@ -87,6 +88,32 @@ def test_chain_variants_are_bit_identical_and_agree_with_the_log_form(c2):
     assert float((rel <= tol).double().mean()) >= 0.9999
     # the lowest leverage (10 %) never leaves the range: every path within the tolerance
     assert bool(live[0].all()) and float(((chain[0] - ref[0]).abs() / ref[0]).max()) <= tol
+
+
+def test_packed_array_gives_the_same_sweep_at_full_size(c2):
+    """
+    The bench's format: the 1e6 x 1e4 die rolls at 2 bits each (2.5 GB).  Packing the
+    uint8 draws and drawing straight into the packed layout give the same bytes, and
+    the sweep over them returns the uint8 sweep's counts, log-wealth and wealth bit for bit.
+    """
+    eng = c2["engine"]
+    packed = eng.pack_codes(c2["codes"])
+    drawn = eng.lev_draw("discrete", N, H, seed=420, probs=PROBS, packed=True)
+    assert packed.data.shape == (N, 2512) and torch.equal(packed.data, drawn.data)
+    got = eng.lev_sweep("discrete", c2["table"], V0, outcomes=packed, mode="log", want_log_w=True, want_counts=True)
+    ref = c2["log"]
+    assert torch.equal(got["counts"], ref["counts"])
+    assert torch.equal(got["log_w"].view(torch.int64), ref["log_w"].view(torch.int64))
+    assert torch.equal(got["data_T"].view(torch.int32), ref["data_T"].view(torch.int32))
+    # and the statistics of the 20-leverage script grid through the two-stream pipeline equal the direct call
+    want = eng.rowstats(ref["data_T"], TOP)
+    pipe = eng.FinalSweepPipeline("discrete", c2["table"], V0, TOP)
+    st = [pipe.submit(packed) for _ in range(3)]
+    pipe.synchronize()
+    for s_ in st:
+        assert torch.equal(s_[:, 9:12], want[:, 9:12])                  # order statistics: exact
+        # fp64 sums of 1e6 heavy-tailed terms, block order not fixed (atomics): last digits differ
+        assert torch.allclose(s_, want, rtol=1e-9, atol=0, equal_nan=True)
 
 
 def test_investor_slices_reproduce_the_full_run(c2):
