@@ -446,6 +446,23 @@ __device__ void find_bin(const long long* __restrict__ hist, int bins, long long
   __syncthreads();
 }
 
+// A step's histogram(s) from the workspace (L2) into shared memory: every thread's
+// 16-byte loads are issued before the first store (a rolled loop would pay the L2
+// latency once per iteration: 8 dependent round trips for the 64 KB of step 1).
+template <int COUNT>
+__device__ __forceinline__ void copy_hist(long long* __restrict__ dst, const long long* __restrict__ src) {
+  static_assert(COUNT % 512 == 0, "256 threads x word pairs");
+  constexpr int PER = COUNT / 512;
+  const longlong2* __restrict__ s2 = reinterpret_cast<const longlong2*>(src);
+  longlong2* __restrict__ d2 = reinterpret_cast<longlong2*>(dst);
+  longlong2 v[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) v[u] = s2[u * 256 + threadIdx.x];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) d2[u * 256 + threadIdx.x] = v[u];
+  __syncthreads();
+}
+
 // STEP 0: after pass 0   STEP 1: after pass 1   STEP 2: after pass 2 (order
 // statistics, top / adj split and means)   STEP 3: after pass 3 (writes stats)
 // The step's histograms are first summed over the world into shared memory
@@ -475,8 +492,7 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
   }
 
   if (STEP == 0) {
-    for (int i = threadIdx.x; i < L1_BINS; i += blockDim.x) hs[i] = si[OFF_H1 + i];
-    __syncthreads();
+    copy_hist<L1_BINS>(hs, si + OFF_H1);
     const long long ranks[NT] = {(n - 1) / 2, n - K, n - K + (K - 1) / 2, (n - K - 1) / 2};
     for (int j = 0; j < NT; ++j) {
       find_bin(hs, L1_BINS, ranks[j], &bin_s, &rem_s, scratch);
@@ -504,8 +520,7 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
       w->has_nan[2] = nan > K;
     }
   } else if (STEP == 1) {
-    for (int i = threadIdx.x; i < NT * L2_BINS; i += blockDim.x) hs[i] = si[OFF_H2 + i];
-    __syncthreads();
+    copy_hist<NT * L2_BINS>(hs, si + OFF_H2);
     for (int j = 0; j < NT; ++j) {
       find_bin(hs + j * L2_BINS, L2_BINS, w->rank[j], &bin_s, &rem_s, scratch);
       if (threadIdx.x == 0) {
@@ -515,8 +530,7 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
       __syncthreads();
     }
   } else if (STEP == 2) {
-    for (int i = threadIdx.x; i < NT * L3_BINS; i += blockDim.x) hs[i] = si[OFF_H3 + i];
-    __syncthreads();
+    copy_hist<NT * L3_BINS>(hs, si + OFF_H3);
     for (int j = 0; j < NT; ++j) {
       find_bin(hs + j * L3_BINS, L3_BINS, w->rank[j], &bin_s, &rem_s, scratch);
       if (threadIdx.x == 0) {

@@ -46,9 +46,11 @@ def test_struct_layout_matches_c(tmp_path):
     from rlmd_b200 import _lib
 
     structs = {"b200_lev_desc": _lib.LevDesc}
-    for extra in ("EnvDesc", "ReplayDesc"):
+    names = {"EnvDesc": "b200_env_desc", "ReplayDesc": "b200_replay_desc", "PeerSet": "b200_peer_set",
+             "MarketDesc": "b200_market_desc", "CollectDesc": "b200_collect_desc", "BigBrainDesc": "b200_bigbrain_desc"}
+    for extra, cname in names.items():
         if hasattr(_lib, extra):
-            structs[{"EnvDesc": "b200_env_desc", "ReplayDesc": "b200_replay_desc"}[extra]] = getattr(_lib, extra)
+            structs[cname] = getattr(_lib, extra)
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
