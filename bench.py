@@ -353,7 +353,9 @@ def run_gpu(args):
     def measure_e2e(as_packed):
         """Pinned host outcomes -> lev_final_host (H2D inside) -> statistics on the host, CUDA-event timed."""
         n_host = n
-        width = (h + 3) // 4 if as_packed else h
+        # packed rows keep the engine's 16-byte row padding (2512 bytes for 1e4 rolls): a chunk is then one
+        # contiguous copy and every device row starts on a 16-byte boundary
+        width = resident.shape[1] if (as_packed and packed) else (-(-((h + 3) // 4) // 16) * 16 if as_packed else h)
         while True:   # halve the e2e sample if the host refuses to pin that much
             try:
                 host = torch.empty((n_host, width), dtype=torch.uint8, pin_memory=True)

@@ -333,6 +333,18 @@ def lev_series(
     return data, data_T
 
 
+_copy_streams = {}
+
+
+def _copy_stream(dev) -> "torch.cuda.Stream":
+    """One H2D stream per device, kept: a fresh stream per call also means a fresh allocator pool per call."""
+    key = str(dev)
+    if key not in _copy_streams:
+        with torch.cuda.device(dev):
+            _copy_streams[key] = torch.cuda.Stream()
+    return _copy_streams[key]
+
+
 def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, outcomes_host, *,
                    mode: str = "log", chunk_rows: Optional[int] = None, variant: int = 0, device="cuda",
                    return_data_T: bool = False, group=None, n_total: Optional[int] = None):
@@ -342,7 +354,10 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
     in row chunks through two device staging buffers - the H2D copy of chunk i+1
     overlaps the sweep of chunk i - and the statistics come back to the host.
     `outcomes_host`: uint8 codes / fp32 returns [N,H], or PackedCodes over a host
-    tensor (a quarter of the bytes over PCIe).
+    tensor (a quarter of the bytes over PCIe).  Rows whose byte length is a multiple
+    of 16 (every PackedCodes made by pack_codes / lev_draw; H a multiple of 16 / 4
+    otherwise) travel as ONE contiguous copy per chunk; other widths make each
+    chunk a pitched copy through a device temporary, which is much slower.
     Returns float64 [G,12] numpy (and data_T on the device when asked).
     """
     require_cuda()
@@ -368,7 +383,7 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
         data_T = torch.empty((g, n), dtype=torch.float32, device=dev)
         bufs = [torch.empty((chunk_rows, ld), dtype=want, device=dev) for _ in range(2)]
         comp = torch.cuda.current_stream()
-        copy = torch.cuda.Stream()
+        copy = _copy_stream(dev)
         ready = [torch.cuda.Event() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
         copy.wait_stream(comp)
