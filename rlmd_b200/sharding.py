@@ -136,6 +136,12 @@ def peer_workspace(rows: int, group, device) -> PeerWorkspace:
     key = (id(group), str(device))
     pw = _peer_cache.get(key)
     if pw is None or pw.rows < rows:
+        if pw is not None:
+            # peers may still be reading the old workspaces: every rank finishes its work, then all let go together
+            import torch.distributed as dist
+
+            torch.cuda.synchronize(device)
+            dist.barrier(group=group)
         pw = PeerWorkspace(max(rows, 64), group, device)
         _peer_cache[key] = pw
     return pw
