@@ -235,8 +235,13 @@ def require_cuda():
 
 
 def stream_ptr():
+    """The current torch stream of the current device as a cudaStream_t (called on every launch: the raw
+    accessor skips building a torch.cuda.Stream object)."""
     import torch
 
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return C.c_void_p(raw(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
