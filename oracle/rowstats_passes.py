@@ -78,9 +78,6 @@ class RowStatsPasses:
                 hi = pinf + nan
                 self.nonfinite[r] = [(hi + ninf) > 0, hi > 0 or ninf > n - K, hi > K or ninf > 0]
                 self.has_nan[r] = [nan > 0, nan > 0, nan > K]
-                with np.errstate(invalid="ignore", over="ignore"):
-                    d = x - self.mean[r, 0]
-                    D[1], D[2] = np.abs(d).sum(), (d * d).sum()
                 top_bits = k >> np.uint64(32 - L1)
                 mid = ((k >> np.uint64(L3)) & np.uint64((1 << L2) - 1)).astype(np.int64)
                 for j in range(NT):
@@ -103,7 +100,7 @@ class RowStatsPasses:
                 thr_hi = self.prefix[r, 1] >> np.uint64(L3)
                 gt, lt = hi > thr_hi, hi < thr_hi
                 with np.errstate(invalid="ignore"):
-                    D[3], D[4] = x[gt].sum(), x[lt].sum()
+                    D[1], D[2] = x[gt].sum(), x[lt].sum()
                 I[off["cnt"]] = int(gt.sum())     # the count below follows from the total (phase 3)
             elif phase == 3:
                 for j in range(NT):
@@ -115,7 +112,7 @@ class RowStatsPasses:
                 thr = int(self.prefix[r, 1])
                 thr_lo, base = thr & ((1 << L3) - 1), thr & ~((1 << L3) - 1)
                 h3 = I[off["h3"] + (1 << L3):off["h3"] + 2 * (1 << L3)]
-                n_gt, s_gt, s_lt = int(I[off["cnt"]]), D[3], D[4]
+                n_gt, s_gt, s_lt = int(I[off["cnt"]]), D[1], D[2]
                 n_lt = n - n_gt - int(h3.sum())
                 f_gt = f_lt = 0.0
                 c_gt = c_lt = 0
@@ -141,6 +138,8 @@ class RowStatsPasses:
                     gt, lt = k > np.uint64(thr), k < np.uint64(thr)
                     dt, da = x[gt] - self.mean[r, 1], x[lt] - self.mean[r, 2]
                     D[5], D[6], D[7], D[8] = np.abs(dt).sum(), (dt * dt).sum(), np.abs(da).sum(), (da * da).sum()
+                    d = x - self.mean[r, 0]           # the all-group moments ride on this pass too
+                    D[3], D[4] = np.abs(d).sum(), (d * d).sum()
             else:
                 thr_v = self.value[r, 1]
                 dt, da = thr_v - self.mean[r, 1], thr_v - self.mean[r, 2]
@@ -151,9 +150,9 @@ class RowStatsPasses:
                 sq_adj = D[8] + (ta * da * da if ta > 0 else 0.0)
                 s = self.stats[r]
                 s[0:3] = self.mean[r]
-                s[3:6] = [D[1] / n, abs_top / K, abs_adj / (n - K)]
+                s[3:6] = [D[3] / n, abs_top / K, abs_adj / (n - K)]
                 with np.errstate(invalid="ignore"):
-                    s[6:9] = [np.sqrt(D[2] / n), np.sqrt(sq_top / K), np.sqrt(sq_adj / (n - K))]
+                    s[6:9] = [np.sqrt(D[4] / n), np.sqrt(sq_top / K), np.sqrt(sq_adj / (n - K))]
                 s[9:12] = [self.value[r, 0], self.value[r, 2], self.value[r, 3]]
                 size = (n, K, n - K)
                 single = (np.nan, self.value[r, 1], self.value[r, 3])

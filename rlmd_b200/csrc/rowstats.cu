@@ -15,12 +15,14 @@
 //
 // Four passes over the data, each an HBM stream (4 B per element per pass):
 //   pass 0: sum, level-1 histogram
-//   pass 1: |w-mean|, (w-mean)^2, level-2 histograms
+//   pass 1: level-2 histograms
 //   pass 2: level-3 histograms + sums/counts of the elements whose 22-bit prefix is
 //           above / below thr's (the elements that share thr's prefix all sit in
 //           thr's level-3 histogram, and a level-3 bin IS one fp32 value, so the
 //           resolve step finishes the top / adj split exactly from the bin counts)
-//   pass 3: deviations of top / adj about their own means
+//   pass 3: |w-mean|, (w-mean)^2 of all, and the deviations of top / adj about
+//           their own means (pass 3 has the fewest instructions per element left:
+//           the all-group moments ride there, not on the histogram passes)
 // Between passes a one-block-per-row "resolve" kernel turns histograms into
 // prefixes/ranks.  Every cross-block quantity lives in the caller's workspace as
 // 8-byte words so that a multi-GPU caller can all-reduce it between passes.
@@ -40,10 +42,10 @@ constexpr int NT = 4;  // targets
 struct RowWS {
   // ---- doubles (exchange region D) -------------------------------------
   double sum_all;      // pass 0
-  double absdev_all;   // pass 1
-  double sqdev_all;    // pass 1
   double sum_gt;       // pass 2: sum of w whose 22-bit key prefix is above thr's
   double sum_lt;       // pass 2: ... below thr's
+  double absdev_all;   // pass 3 (about mean_all)
+  double sqdev_all;    // pass 3
   double absdev_gt;    // pass 3 (about mean_top), over key > key(thr)
   double sqdev_gt;
   double absdev_lt;    // pass 3 (about mean_adj), over key < key(thr)
@@ -147,7 +149,6 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
     }
   }
   if (PASS == 1) {
-    mean_a = w->mean_all;
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -158,12 +159,13 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
   if (PASS == 2) thr_key = key_const<MODE>((uint32_t)w->prefix[1] >> L3_BITS, L3_BITS);   // thr's 22-bit prefix
   if (PASS == 3) {
     thr_key = key_const<MODE>((uint32_t)w->prefix[1], 0);
+    mean_a = w->mean_all;
     mean_t = w->mean_top;
     mean_j = w->mean_adj;
   }
   __syncthreads();
 
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
   unsigned int c0 = 0;  // per-thread count: a thread sees far fewer than 2^32 elements
 
   auto process = [&](const float x) {
@@ -172,9 +174,6 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
       a0 += (double)x;
       atomicAdd(&smem_hist[k >> (32 - L1_BITS)], 1u);
     } else if (PASS == 1) {
-      const double d = (double)x - mean_a;
-      a0 += fabs(d);
-      a1 = __fma_rn(d, d, a1);
       const int off = lut[k >> (32 - L1_BITS)];
       if (off >= 0)
         atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(smem_hist) + off +
@@ -196,8 +195,12 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
         }
       }
     } else {
-      if (k < thr_key) { const double d = (double)x - mean_j; a2 += fabs(d); a3 = __fma_rn(d, d, a3); }
-      else if (k > thr_key) { const double d = (double)x - mean_t; a0 += fabs(d); a1 = __fma_rn(d, d, a1); }
+      const double xd = (double)x;
+      const double da = xd - mean_a;
+      a4 += fabs(da);
+      a5 = __fma_rn(da, da, a5);
+      if (k < thr_key) { const double d = xd - mean_j; a2 += fabs(d); a3 = __fma_rn(d, d, a3); }
+      else if (k > thr_key) { const double d = xd - mean_t; a0 += fabs(d); a1 = __fma_rn(d, d, a1); }
     }
   };
 
@@ -213,9 +216,7 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
 #pragma unroll
       for (int u = 0; u < RS_ITEMS / 4; ++u) t[u] = __ldcs(v4 + u * RS_THREADS + threadIdx.x);
       if (PASS == 1) {
-        // eight table lookups are issued before the first (dependent) histogram
-        // branch; two independent fp64 chains per sum (a dependent DADD/DFMA per
-        // element otherwise waits out the fp64 pipe latency)
+        // eight table lookups are issued before the first (dependent) histogram branch
         const float* e = reinterpret_cast<const float*>(t);
 #pragma unroll
         for (int h = 0; h < RS_ITEMS; h += 8) {
@@ -224,9 +225,6 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
           for (int u = 0; u < 8; ++u) off[u] = lut[float_key_fast<MODE>(e[h + u]) >> (32 - L1_BITS)];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const double d = (double)e[h + u] - mean_a;
-            if (u & 1) { a2 += fabs(d); a3 = __fma_rn(d, d, a3); }
-            else { a0 += fabs(d); a1 = __fma_rn(d, d, a1); }
             if (off[u] >= 0) {
               const uint32_t k = float_key_fast<MODE>(e[h + u]);
               atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(smem_hist) + off[u] +
@@ -250,9 +248,6 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
   if (PASS == 0) {
     double s = block_sum(a0, red_d);
     if (threadIdx.x == 0) atomic_add_f64(&w->sum_all, s);
-  } else if (PASS == 1) {
-    double s0 = block_sum(a0 + a2, red_d), s1 = block_sum(a1 + a3, red_d);
-    if (threadIdx.x == 0) { atomic_add_f64(&w->absdev_all, s0); atomic_add_f64(&w->sqdev_all, s1); }
   } else if (PASS == 2) {
     double s0 = block_sum(a0, red_d), s1 = block_sum(a1, red_d);
     long long n0 = block_sum((long long)c0, red_i);
@@ -263,9 +258,11 @@ __device__ __forceinline__ void rowstats_pass_body(const float* __restrict__ v, 
   } else if (PASS == 3) {
     double s0 = block_sum(a0, red_d), s1 = block_sum(a1, red_d);
     double s2 = block_sum(a2, red_d), s3 = block_sum(a3, red_d);
+    double s4 = block_sum(a4, red_d), s5 = block_sum(a5, red_d);
     if (threadIdx.x == 0) {
       atomic_add_f64(&w->absdev_gt, s0); atomic_add_f64(&w->sqdev_gt, s1);
       atomic_add_f64(&w->absdev_lt, s2); atomic_add_f64(&w->sqdev_lt, s3);
+      atomic_add_f64(&w->absdev_all, s4); atomic_add_f64(&w->sqdev_all, s5);
     }
   }
 
@@ -373,8 +370,8 @@ __global__ void __launch_bounds__(256)
 rowstats_gather_kernel(const __grid_constant__ PeerSet P, RowWS* __restrict__ gsum) {
   constexpr int64_t IOFF = STEP == 0 ? OFF_H1 : STEP == 1 ? OFF_H2 : OFF_CNT;
   constexpr int ICNT = STEP == 0 ? L1_BINS : STEP == 1 ? NT * L2_BINS : STEP == 2 ? 8 + NT * L3_BINS : 0;
-  constexpr int DOFF = STEP == 0 ? 0 : STEP == 1 ? 1 : STEP == 2 ? 3 : 5;
-  constexpr int DCNT = STEP == 0 ? 1 : STEP == 1 ? 2 : STEP == 2 ? 2 : 4;
+  constexpr int DOFF = STEP == 0 ? 0 : STEP == 1 ? 0 : STEP == 2 ? 1 : 3;
+  constexpr int DCNT = STEP == 0 ? 1 : STEP == 1 ? 0 : STEP == 2 ? 2 : 6;
   const int64_t row = blockIdx.y;
   if (!wait_peers(P, STEP)) return;   // the error word is set: the final resolve writes NaN
   long long* dst = reinterpret_cast<long long*>(gsum + row);
@@ -558,7 +555,7 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
     if (threadIdx.x == 0) {
       const double thr = w->value[1];
       const long long cnt_gt = si[OFF_CNT];
-      const double coarse_gt = sd[3], coarse_lt = sd[4];
+      const double coarse_gt = sd[1], coarse_lt = sd[2];
       // below thr's prefix = everything that is neither above it nor inside it
       const long long n_gt = cnt_gt + c_gt, n_lt = (n - cnt_gt - c_all) + c_lt;
       const double sum_gt = c_gt ? coarse_gt + s_gt : coarse_gt, sum_lt = c_lt ? coarse_lt + s_lt : coarse_lt;
@@ -572,7 +569,7 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
     }
   } else {
     if (threadIdx.x == 0) {
-      const double absdev_all = sd[1], sqdev_all = sd[2];
+      const double absdev_all = sd[3], sqdev_all = sd[4];
       const double absdev_gt = sd[5], sqdev_gt = sd[6], absdev_lt = sd[7], sqdev_lt = sd[8];
       const double thr = w->value[1];
       const double dt = thr - w->mean_top, da = thr - w->mean_adj;
@@ -669,9 +666,9 @@ extern "C" int64_t b200_rowstats_workspace_bytes(int64_t rows) {
 
 // Phases for a multi-GPU caller:
 //   phase 0: clear + pass 0                      -> exchange D[0..1) and hist1
-//   phase 1: resolve 0 + pass 1                  -> exchange D[1..3) and hist2
-//   phase 2: resolve 1 + pass 2                  -> exchange D[3..5), cnt and hist3
-//   phase 3: resolve 2 + pass 3                  -> exchange D[5..9)
+//   phase 1: resolve 0 + pass 1                  -> exchange hist2
+//   phase 2: resolve 1 + pass 2                  -> exchange D[1..3), cnt and hist3
+//   phase 3: resolve 2 + pass 3                  -> exchange D[3..9)
 //   phase 4: resolve 3 (writes stats)
 // The workspace is laid out row-major, so an exchange region is strided by
 // ROW_WORDS; callers reduce the whole typed slab view instead (see
@@ -715,9 +712,9 @@ extern "C" int b200_rowstats_exchange(int32_t phase, int64_t out[5]) {
   int64_t io = 0, ic = 0, d_o = 0, dc = 0;
   switch (phase) {
     case 0: io = OFF_H1; ic = L1_BINS; d_o = 0; dc = 1; break;
-    case 1: io = OFF_H2; ic = (int64_t)NT * L2_BINS; d_o = 1; dc = 2; break;
-    case 2: io = OFF_CNT; ic = 8 + (int64_t)NT * L3_BINS; d_o = 3; dc = 2; break;  // cnt words, then hist3
-    case 3: d_o = 5; dc = 4; break;
+    case 1: io = OFF_H2; ic = (int64_t)NT * L2_BINS; break;
+    case 2: io = OFF_CNT; ic = 8 + (int64_t)NT * L3_BINS; d_o = 1; dc = 2; break;  // cnt words, then hist3
+    case 3: d_o = 3; dc = 6; break;
     default: break;
   }
   out[0] = io; out[1] = ic; out[2] = d_o; out[3] = dc; out[4] = ROW_WORDS;
