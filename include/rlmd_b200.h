@@ -420,7 +420,7 @@ int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealt
  *   workspace[r] : rank r's rowstats workspace as mapped HERE (>= workspace_bytes(rows))
  *   flags[r]     : rank r's flag block, uint32 [B200_MAX_PEERS * 4 + 1], zeroed once;
  *                  word B200_MAX_PEERS*4 of the own block is set when a peer's flag
- *                  did not arrive within ~10 s (the statistics are then NaN)
+ *                  did not arrive within ~60 s (the statistics are then NaN)
  *   epoch        : 1, 2, 3, ... - one more per call, the same on every rank; successive
  *                  calls must alternate between two workspaces (a peer may still be
  *                  reading the previous call's sums)

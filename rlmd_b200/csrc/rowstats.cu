@@ -326,7 +326,7 @@ __global__ void rowstats_signal_kernel(const __grid_constant__ PeerSet P, int ph
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(P.epoch) : "memory");
 }
 
-// Block-wide wait for the peers' flags of `phase`; false after ~10 s (a peer died):
+// Block-wide wait for the peers' flags of `phase`; false after ~60 s (a peer died):
 // the caller then writes NaN statistics instead of hanging the device.
 __device__ bool wait_peers(const PeerSet& P, int phase) {
   __shared__ int ok_s;
@@ -344,7 +344,7 @@ __device__ bool wait_peers(const PeerSet& P, int phase) {
         __nanosleep(200);
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 10000000000ull) { ok = 0; break; }
+        if (t1 - t0 > 60000000000ull) { ok = 0; break; }
       }
     }
     if (!ok) P.flags[P.rank][FLAG_ERROR_WORD] = 1u;

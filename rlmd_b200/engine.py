@@ -400,6 +400,10 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
             lev_sweep(kind, f, value_0, outcomes=oc, mode=mode, variant=variant, out_data_T=data_T[:, r0:r0 + rows])
             done[i & 1].record(comp)
         stats = rowstats(data_T, top, n_total=n_total, group=group).cpu().numpy() if n > 0 else np.zeros((g, 12))
+        if group is not None:
+            from . import sharding
+
+            sharding.raise_if_peers_timed_out(group, dev)
     return (stats, data_T) if return_data_T else stats
 
 
@@ -471,6 +475,10 @@ class FinalSweepPipeline:
     def synchronize(self) -> None:
         self.sweep_stream.synchronize()
         self.stats_stream.synchronize()
+        if self.group is not None:
+            from . import sharding
+
+            sharding.raise_if_peers_timed_out(self.group, self.dev)
 
 
 # ----------------------------------------------------------------- rowstats

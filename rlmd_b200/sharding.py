@@ -104,6 +104,18 @@ _peer_cache = {}
 _peer_ok = {}
 
 
+def raise_if_peers_timed_out(group, device) -> None:
+    """
+    After a synchronisation point: raises when a resolve step of the peer-memory exchange gave up
+    waiting for a peer's flag (~60 s; the statistics of that call are NaN).  Costs one 4-byte
+    device-to-host read; a no-op when the group does not use the peer-memory exchange.
+    """
+    pw = _peer_cache.get((id(group), str(device)))
+    if pw is not None and pw.timed_out():
+        raise RuntimeError("rlmd_b200: a rank did not reach the statistics exchange within 60 s "
+                           "(peer-memory flags); the statistics of that call are NaN")
+
+
 def peer_memory_available(group, device) -> bool:
     """
     Whether the ranks of `group` can map each other's memory (torch symmetric
