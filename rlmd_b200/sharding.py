@@ -104,13 +104,19 @@ _peer_cache = {}
 _peer_ok = {}
 
 
+def _key(group, device):
+    d = torch.device(device)
+    index = d.index if d.index is not None else torch.cuda.current_device()
+    return (id(group), index)
+
+
 def raise_if_peers_timed_out(group, device) -> None:
     """
     After a synchronisation point: raises when a resolve step of the peer-memory exchange gave up
     waiting for a peer's flag (~60 s; the statistics of that call are NaN).  Costs one 4-byte
     device-to-host read; a no-op when the group does not use the peer-memory exchange.
     """
-    pw = _peer_cache.get((id(group), str(device)))
+    pw = _peer_cache.get(_key(group, device))
     if pw is not None and pw.timed_out():
         raise RuntimeError("rlmd_b200: a rank did not reach the statistics exchange within 60 s "
                            "(peer-memory flags); the statistics of that call are NaN")
@@ -127,7 +133,7 @@ def peer_memory_available(group, device) -> bool:
 
     import torch.distributed as dist
 
-    key = (id(group), str(device))
+    key = _key(group, device)
     if key not in _peer_ok:
         ok = 1
         try:
@@ -145,7 +151,7 @@ def peer_memory_available(group, device) -> bool:
 
 def peer_workspace(rows: int, group, device) -> PeerWorkspace:
     """Cached per (group, device); grown (collectively) when a call needs more rows."""
-    key = (id(group), str(device))
+    key = _key(group, device)
     pw = _peer_cache.get(key)
     if pw is None or pw.rows < rows:
         if pw is not None:
