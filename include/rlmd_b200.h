@@ -139,6 +139,18 @@ int b200_lev_chunk(const b200_lev_desc* desc, const void* outcomes,
  * and the CPU oracle see the identical pre-drawn array. */
 int b200_lev_draw(const b200_lev_desc* desc, void* out, void* stream);
 
+/* Wealth of a discrete sweep from the outcome COUNTS of a previous LOG sweep
+ * (counts int32 [N,K], b200_lev_sweep's `counts` output): the leverage grid enters
+ * the wealth only through log m[g][k], so a grid of any size - the 2-D leverage x
+ * insurance-fraction grid of lev/dice_roll_sh.py's factor `1 + l r_k + (1-l) sh_k`
+ * (lev/lev_exp.py:1160-1166) with both coefficients free - costs ONE pass over the
+ * outcome array plus one call of this per tile of <= B200_MAX_GRID grid points.
+ * desc: n_investors, n_grid, n_outcomes, value_0, ld_out as for b200_lev_sweep;
+ * outputs bit-identical to the LOG sweep's. */
+int b200_lev_from_counts(const b200_lev_desc* desc, const int32_t* counts,
+                         const float* factors_host, float* data_T, double* log_w,
+                         void* stream);
+
 /* uint8 codes [N, ld_codes] -> packed 2-bit codes [N, ld_packed bytes]
  * (ld_packed >= ceil(H/4); codes are taken modulo 4, pad bits are written 0). */
 int b200_lev_pack(const uint8_t* codes, int64_t n_investors, int32_t horizon,

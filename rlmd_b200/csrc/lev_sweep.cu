@@ -650,9 +650,33 @@ static int run_chain_discrete(const b200_lev_desc& d, const uint8_t* outcomes, c
   return 0;
 }
 
-static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, const float* factors_host,
-                            float* data_T, double* log_w, int32_t* counts, cudaStream_t st) {
-  LogFactorTable lf;
+// ------------------------------------------ LOG, discrete: wealth from counts
+// Wealth depends on the outcomes only through their counts: a grid of ANY size is
+// ONE pass over the outcome array (counts) plus, per tile of 64 grid points, this
+// kernel - one thread per investor, the epilogue of the count kernels on its own
+// (same expressions in the same order: bit-identical log-wealth and wealth).
+template <int K>
+__global__ void __launch_bounds__(256)
+log_from_counts_kernel(const int32_t* __restrict__ counts, int64_t N, int32_t G,
+                       const __grid_constant__ LogFactorTable lf, double logV0, float* __restrict__ data_T,
+                       double* __restrict__ log_w, int64_t ldT) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  int n[K];
+  double nd[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { n[k] = counts[row * K + k]; nd[k] = (double)n[k]; }
+  for (int g = 0; g < G; ++g) {
+    double lw = logV0;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (n[k] > 0) lw += nd[k] * lf.lm[k][g];
+    if (log_w != nullptr) log_w[(int64_t)g * ldT + row] = lw;
+    if (data_T != nullptr) data_T[(int64_t)g * ldT + row] = (float)exp(lw);
+  }
+}
+
+static int make_log_table(const b200_lev_desc& d, const float* factors_host, LogFactorTable& lf) {
   for (int k = 0; k < B200_MAX_OUTCOMES; ++k)
     for (int g = 0; g < B200_MAX_GRID; ++g) {
       double v = 0.0;
@@ -663,6 +687,13 @@ static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, con
       }
       lf.lm[k][g] = v;
     }
+  return 0;
+}
+
+static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, const float* factors_host,
+                            float* data_T, double* log_w, int32_t* counts, cudaStream_t st) {
+  LogFactorTable lf;
+  if (int rc = make_log_table(d, factors_host, lf)) return rc;
   const double logV0 = log((double)d.value_0);
   const int64_t N = d.n_investors;
   // a warp per row (uint8 codes) / per 32 rows (packed)
@@ -843,6 +874,32 @@ extern "C" int b200_lev_draw(const b200_lev_desc* desc, void* out, void* stream)
     }
   }
   return check_cuda(cudaGetLastError(), "lev_draw launch");
+}
+
+extern "C" int b200_lev_from_counts(const b200_lev_desc* desc, const int32_t* counts, const float* factors,
+                                    float* data_T, double* log_w, void* stream) {
+  int rc = validate(desc);
+  if (rc) return rc;
+  const b200_lev_desc& d = *desc;
+  B200_REQUIRE(d.kind == B200_LEV_DISCRETE, "lev_from_counts: discrete sweeps only");
+  B200_REQUIRE(factors != nullptr, "lev_from_counts: factors is NULL");
+  B200_REQUIRE(data_T || log_w, "lev_from_counts: needs at least one output");
+  if (d.n_investors == 0) return 0;
+  B200_REQUIRE(counts != nullptr, "lev_from_counts: counts is NULL");
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  LogFactorTable lf;
+  if ((rc = make_log_table(d, factors, lf))) return rc;
+  const double logV0 = log((double)d.value_0);
+  const int64_t N = d.n_investors;
+  const unsigned blocks = (unsigned)((N + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d.n_outcomes) {
+    case 2: log_from_counts_kernel<2><<<blocks, 256, 0, st>>>(counts, N, d.n_grid, lf, logV0, data_T, log_w, out_ld(d)); break;
+    case 3: log_from_counts_kernel<3><<<blocks, 256, 0, st>>>(counts, N, d.n_grid, lf, logV0, data_T, log_w, out_ld(d)); break;
+    default: log_from_counts_kernel<4><<<blocks, 256, 0, st>>>(counts, N, d.n_grid, lf, logV0, data_T, log_w, out_ld(d)); break;
+  }
+  return check_cuda(cudaGetLastError(), "lev_from_counts launch");
 }
 
 extern "C" int b200_lev_pack(const uint8_t* codes, int64_t n_investors, int32_t horizon, int64_t ld_codes,

@@ -173,6 +173,47 @@ def lev_sweep(
     return res
 
 
+def lev_grid_sweep(factors: np.ndarray, value_0: float, outcomes, *, want_log_w: bool = False,
+                   counts: Optional[torch.Tensor] = None) -> dict:
+    """
+    Final-time LOG sweep of a discrete gamble over a grid of ANY size (factors
+    [G,K] fp32, G unbounded): the wealth depends on the outcomes only through
+    their counts, so the outcome array (uint8 codes or PackedCodes) is read ONCE
+    (b200_lev_sweep -> counts [N,K]) and every tile of 64 grid points is then one
+    b200_lev_from_counts launch over the counts.  This is the engine's route to
+    BASELINE's 2-D grid of lev/dice_roll_sh.py (leverage x insurance fraction,
+    lev_exp.grid2d_factor_table: G = La * Lb).  Pass `counts` to reuse a previous
+    call's counts (another grid over the same outcomes: no pass over the outcomes).
+    Returns {"data_T": [G,N] f32, "log_w": [G,N] f64 or None, "counts": [N,K] i32};
+    bit-identical to lev_sweep(mode="log") tile by tile.
+    """
+    require_cuda()
+    f = np.ascontiguousarray(factors, dtype=np.float32)
+    if f.ndim != 2:
+        raise ValueError("factors must be [G,K]")
+    g, k = f.shape
+    n, h = outcomes.shape
+    dev = outcomes.data.device if isinstance(outcomes, PackedCodes) else outcomes.device
+    with torch.cuda.device(dev):
+        if counts is None:
+            counts = lev_sweep("discrete", f[:1], value_0, outcomes=outcomes, mode="log", want_data_T=False,
+                               want_counts=True)["counts"]
+        elif tuple(counts.shape) != (n, k) or counts.dtype != torch.int32 or not counts.is_contiguous():
+            raise ValueError("counts must be a contiguous int32 [N,K] tensor")
+        data_T = torch.empty((g, n), dtype=torch.float32, device=dev)
+        log_w = torch.empty((g, n), dtype=torch.float64, device=dev) if want_log_w else None
+        d = LevDesc()
+        d.kind, d.mode, d.source = _lib.LEV_DISCRETE, _lib.MODE_LOG, _lib.SRC_STREAM
+        d.n_investors, d.horizon, d.ld_outcomes, d.n_outcomes = n, max(h, 1), max(h, 1), k
+        d.value_0 = float(value_0)
+        for g0 in range(0, g, _lib.MAX_GRID):
+            tile = np.ascontiguousarray(f[g0:g0 + _lib.MAX_GRID])
+            d.n_grid = tile.shape[0]
+            check(lib.b200_lev_from_counts(C.byref(d), ptr(counts), tile.ctypes.data_as(C.POINTER(C.c_float)),
+                                           ptr(data_T[g0:]), ptr(log_w[g0:]) if want_log_w else None, stream_ptr()))
+    return {"data_T": data_T, "log_w": log_w, "counts": counts}
+
+
 def lev_draw(kind: str, n_investors: int, horizon: int, *, seed: int = 0, investor_offset: int = 0,
              probs=None, log_mean: float = 0.0, sigma: float = 0.0, device="cuda", packed: bool = False):
     """The outcome array a Philox sweep with the same arguments consumes (packed=True: PackedCodes)."""

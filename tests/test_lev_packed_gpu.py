@@ -132,3 +132,47 @@ def test_pipelined_final_sweeps_equal_the_sequential_calls(eng):
     for g, w in zip(got, want):
         assert torch.equal(g[:, 9:12], w[:, 9:12])                      # order statistics: exact
         assert torch.allclose(g, w, rtol=1e-12, atol=0)                 # fp64 sums: block order varies
+
+
+def test_grid_of_any_size_from_one_pass_over_the_outcomes(eng):
+    """
+    BASELINE's 2-D grid of lev/dice_roll_sh.py (leverage x insurance fraction): 9 x 8 = 72 grid points
+    (> one 64-point tile) from ONE count pass + b200_lev_from_counts per tile, against the oracle's chain
+    and log-wealth for the same factor table, on uint8 and on packed outcomes; the first 64 points are
+    bit-identical to the LOG sweep itself; the line b = 1 - a is the reference's dice_sh factor.
+    """
+    from rlmd_b200 import lev_exp
+
+    rs = np.random.RandomState(12)
+    n, h, top = 3001, 301, 2
+    c = rs.choice(3, size=(n, h), p=[1 / 6, 1 / 6, 2 / 3]).astype(np.uint8)
+    a, b = np.linspace(0.0, 1.2, 9, dtype=np.float32), np.linspace(0.0, 0.3, 8, dtype=np.float32)
+    r, sh = (0.5, -0.5, 0.05), (-1.0, 5.0, -1.0)
+    table = lo.general_factors(np.repeat(a, 8), np.tile(b, 9), r, sh)
+    assert table.shape == (72, 3) and np.array_equal(table, lev_exp.grid2d_factor_table(np.repeat(a, 8), np.tile(b, 9), r, sh))
+    codes = eng.encode_codes(c)
+    for oc in (codes, eng.pack_codes(codes)):
+        res = eng.lev_grid_sweep(table, 100.0, oc, want_log_w=True)
+        assert np.array_equal(res["counts"].cpu().numpy(), lo.counts_discrete(c, 3))
+        want = lo.log_wealth_discrete(c, table, 100.0)
+        got = res["log_w"].cpu().numpy()
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin) and np.allclose(got[fin], want[fin], rtol=1e-13, atol=1e-11)
+        chain = lo.chain_discrete(c, table, 100.0).astype(np.float64)
+        wt = res["data_T"].cpu().numpy().astype(np.float64)
+        ok = np.isfinite(chain) & (chain > 1e-30)
+        assert (np.abs(wt[ok] - chain[ok]) / chain[ok]).max() <= 2e-5
+        direct = eng.lev_sweep("discrete", table[:64], 100.0, outcomes=oc, mode="log", want_log_w=True)
+        assert torch.equal(direct["data_T"].view(torch.int32), res["data_T"][:64].view(torch.int32))
+        assert torch.equal(direct["log_w"].view(torch.int64), res["log_w"][:64].view(torch.int64))
+        again = eng.lev_grid_sweep(table[5:70], 100.0, oc, counts=res["counts"])      # reuse the counts
+        assert torch.equal(again["data_T"].view(torch.int32), res["data_T"][5:70].view(torch.int32))
+    stats, data_T = lev_exp.dice_sh_grid2d("cuda", torch.as_tensor(c.astype(np.int64)), top, 100.0, *r, *sh, a, b)
+    assert tuple(stats.shape) == (9, 8, 12) and tuple(data_T.shape) == (9, 8, n)
+    want_stats = np.stack([lo.summary_stats(res["data_T"][g].cpu().numpy(), top) for g in range(72)]).reshape(9, 8, 12)
+    assert np.array_equal(stats.cpu().numpy()[..., 9:12], want_stats[..., 9:12])
+    assert np.allclose(stats.cpu().numpy()[..., :9], want_stats[..., :9], rtol=1e-10)
+    # the reference's own 1-D dice_sh grid is the line b = 1 - a of this family
+    lev = np.float32([0.73, 0.85, 1.0])
+    line = lev_exp.grid2d_factor_table(lev, (np.float32(1) - lev).astype(np.float32), r, sh)
+    assert np.array_equal(line, lev_exp.dice_sh_factor_table(lev, *r, *sh))

@@ -75,6 +75,20 @@ def main():
         f = lev_exp.dice_factor_table(lev10, 0.5, -0.5, 0.05)
         b, m = timeit(lambda: engine.lev_sweep("discrete", f, 100.0, outcomes=dice, mode="log", out_data_T=out10))
         emit("log_dice_G10", b, m, steps, 1, G=10)
+    if a.only in ("", "grid2d"):
+        # C3: die roll with safe-haven insurance, 2-D grid 32 x 32 (leverage x insurance fraction), packed outcomes:
+        # one count pass + 16 wealth-from-counts launches, then the 12 statistics of the 1024 rows
+        aa, bb = np.linspace(0.0, 1.2, 32, dtype=np.float32), np.linspace(0.0, 0.3, 32, dtype=np.float32)
+        table = lev_exp.grid2d_factor_table(np.repeat(aa, 32), np.tile(bb, 32), (0.5, -0.5, 0.05), (-1.0, 5.0, -1.0))
+        pk = engine.pack_codes(dice)
+        b, m = timeit(lambda: engine.lev_grid_sweep(table, 100.0, pk), warm=1, reps=3)
+        res = engine.lev_grid_sweep(table, 100.0, pk)
+        b2, m2 = timeit(lambda: engine.rowstats(res["data_T"], max(1, n // 10000)), warm=1, reps=3)
+        print(json.dumps(dict(kernel="grid2d_dice_sh_32x32_packed", n=n, h=h, grid_points=1024, sweep_s=b, stats_s=b2,
+                              investor_steps_per_s=steps / (b + b2), path_steps_per_s=1024 * steps / (b + b2),
+                              note="sweep = 1 count pass over 2.5 GB + 16 wealth-from-counts launches (4 GB of data_T); "
+                                   "stats = 4 passes over the 1024 x 1e6 wealth rows")), flush=True)
+        del pk, res
     if a.only in ("", "stats"):
         b, m = timeit(lambda: engine.rowstats(out10, max(1, n // 10000)))
         print(json.dumps(dict(kernel="rowstats_10rows", n=n, best_s=b, median_s=m,
