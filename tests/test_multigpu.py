@@ -109,6 +109,15 @@ def _worker(rank, world, port, out_dir):
         lev_exp.set_process_group(None)
         np.save(os.path.join(out_dir, f"data{rank}.npy"), data.cpu().numpy())
         np.save(os.path.join(out_dir, f"dataT{rank}.npy"), data_T.cpu().numpy())
+        # (2b) C4's shape: a GBM sweep on investor shards (on-device Philox, global investor ids) and the
+        #      growth-rate summaries of the WHOLE population from the shards
+        levg = np.asarray(lev_exp.param_range(-1.0, 1.0, 0.2), dtype=np.float32)
+        off, cnt = sharding.shard_range(60_000, world, rank)
+        gb = engine.lev_sweep("gbm", levg, 100.0, n_investors=cnt, horizon=500, seed=7, investor_offset=off,
+                              log_mean=0.05 - 0.1, sigma=0.2 ** 0.5, mode="log", want_log_w=True)
+        gs = engine.growth_summary(gb["log_w"], 500, 100.0, data_T=gb["data_T"], quantiles=(0.05, 0.5),
+                                   n_total=60_000, group=dist.group.WORLD)
+        np.save(os.path.join(out_dir, f"growth{rank}.npy"), gs.cpu().numpy())
         # (3) Philox sweeps are independent of the sharding
         lev = np.asarray(lev_exp.param_range(0.1, 1.0, 0.1), dtype=np.float32)
         off, cnt = sharding.shard_range(50_000, world, rank)
@@ -149,6 +158,15 @@ def test_two_ranks_equal_one(tmp_path):
             ok = ~np.isnan(wi)
             assert np.array_equal(gi[:, 9:12][ok[:, 9:12]], wi[:, 9:12][ok[:, 9:12]])
             np.testing.assert_allclose(gi[ok], wi[ok], rtol=1e-12)
+    levg = np.asarray(lev_exp.param_range(-1.0, 1.0, 0.2), dtype=np.float32)
+    full = engine.lev_sweep("gbm", levg, 100.0, n_investors=60_000, horizon=500, seed=7, log_mean=0.05 - 0.1,
+                            sigma=0.2 ** 0.5, mode="log", want_log_w=True)
+    want_g = engine.growth_summary(full["log_w"], 500, 100.0, data_T=full["data_T"], quantiles=(0.05, 0.5)).cpu().numpy()
+    for r in range(world):
+        got_g = np.load(tmp_path / f"growth{r}.npy")
+        assert np.array_equal(got_g[:, 0], want_g[:, 0])                   # valid-run counts
+        assert np.array_equal(got_g[:, 4:6], want_g[:, 4:6])               # min / max: exact
+        np.testing.assert_allclose(got_g, want_g, rtol=1e-11)
     case = golden_io.lev_case("dice_top5")
     gold = golden_io.load("lev_dice_top5")
     cols = gold["cols"]
