@@ -33,6 +33,8 @@ extern "C" {
 #define B200_ECUDA (-2)   /* CUDA runtime / driver error */
 #define B200_ELIMIT (-3)  /* size outside what the kernels support */
 
+#define B200_MAX_PEERS 8   /* GPUs of one node that exchange over peer-mapped memory */
+
 const char* b200_last_error(void);
 int b200_version(void);
 /* sm_count / cc_major / cc_minor of the current device */
@@ -155,6 +157,95 @@ int b200_lev_from_counts(const b200_lev_desc* desc, const int32_t* counts,
  * (ld_packed >= ceil(H/4); codes are taken modulo 4, pad bits are written 0). */
 int b200_lev_pack(const uint8_t* codes, int64_t n_investors, int32_t horizon,
                   int64_t ld_codes, uint8_t* packed, int64_t ld_packed, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * Final-time statistics from outcome-count tuples ("tally")
+ *
+ * Sits behind {coin,dice,dice_sh}_fixed_final_lev (lev/lev_exp.py:56-125,
+ * :508-583, :1121-1206): `value_T = value_0 * gambles.prod(dim=1)` followed by
+ * the summary-statistic block (:89-104).  The product depends on an investor's
+ * outcomes only through the counts (n_0 .. n_{K-1}), so investors with equal
+ * count tuples have equal wealth at EVERY leverage: the count kernel ends with
+ * one hash-table insertion per investor (no data_T), and the 12 statistics of
+ * every leverage are exact weighted order statistics / fp64 moments over the
+ * distinct tuples (a few 1e4 for iid rolls) - bit-identical medians and wealth
+ * values to b200_lev_sweep(LOG) + b200_rowstats, which stay as the general path
+ * (and the checker).  Across GPUs ONE exchange per sweep: the ranks' bin lists.
+ *
+ * Call sequence (all asynchronous on `stream`):
+ *   b200_tally_reset                    once (and after an overflow)
+ *   b200_lev_tally / b200_lev_ingest    one or more row blocks (chunks of a host array)
+ *   b200_tally_finalize                 table -> distinct tuples (merged over ranks)
+ *   b200_tally_stats                    any number of grids of <= grid_cap points
+ * ------------------------------------------------------------------ */
+typedef struct b200_tally_plan {
+  int64_t rows_cap;   /* most investor rows tallied on THIS rank between two finalizes  */
+  int64_t bins_cap;   /* most distinct count tuples after the merge (global); more
+                         raises the overflow word instead of wrong statistics           */
+  int32_t grid_cap;   /* most grid points per b200_tally_stats call, <= B200_MAX_GRID    */
+  int32_t world;      /* ranks whose tallies are merged at finalize (1: this GPU only)   */
+} b200_tally_plan;
+
+/* bytes of device workspace / of the peer-mapped exchange buffer (0 when world == 1) */
+int64_t b200_tally_workspace_bytes(const b200_tally_plan* plan);
+int64_t b200_tally_exchange_bytes(const b200_tally_plan* plan);
+
+/* Info words, int64 [B200_TALLY_INFO_WORDS] at the head of the workspace (device):
+ *   0 distinct tuples of the last finalize      1 overflow (!= 0: statistics invalid)
+ *   2 outcomes outside {0..K-1} met by b200_lev_ingest (dice: the reference would
+ *     use such a value as the factor itself, lev/lev_exp.py:541; not supported)
+ *   3 peer time-out (a rank's bins never arrived: statistics are NaN)
+ *   4 sum of the bin counts seen by the last b200_tally_stats != n_total */
+#define B200_TALLY_INFO_WORDS 8
+int b200_tally_reset(const b200_tally_plan* plan, void* workspace, void* stream);
+
+/* The discrete LOG count kernel of b200_lev_sweep with the tally as its sink:
+ * desc / outcomes as for b200_lev_sweep (STREAM source: uint8 codes or packed
+ * 2-bit codes; horizon < 2^21); counts int32 [N,K] or NULL. */
+int b200_lev_tally(const b200_lev_desc* desc, const void* outcomes,
+                   const b200_tally_plan* plan, void* workspace, int32_t* counts,
+                   void* stream);
+
+/* Reference-format outcomes -> engine format, counted on the way.
+ * src: [N, ld_src] of `src_type` exactly as the reference scripts hold them -
+ * coin: fp32 {0,1} (Bernoulli.sample, lev/coin_flip.py:160; code = (x == 1),
+ * lev/lev_exp.py:85), dice: int64 {0,1,2} (Categorical.sample,
+ * lev/dice_roll.py:147; cast to fp32 at lev/lev_exp.py:537) - or any of the
+ * other types below.  Any combination of sinks (NULL = not wanted):
+ *   codes   uint8 [N, ld_codes]   the CHAIN kernels' format (b200_lev_chunk)
+ *   counts  int32 [N, K]
+ *   tally   plan + workspace      the statistics' input (b200_tally_finalize)
+ * One pass over src (8 B per outcome for int64: HBM-bound). */
+enum { B200_DT_U8 = 0, B200_DT_I32 = 1, B200_DT_I64 = 2, B200_DT_F32 = 3, B200_DT_F64 = 4 };
+int b200_lev_ingest(const void* src, int32_t src_type, int64_t n_investors, int32_t horizon,
+                    int64_t ld_src, int32_t n_outcomes, uint8_t* codes, int64_t ld_codes,
+                    int32_t* counts, const b200_tally_plan* plan, void* workspace,
+                    void* stream);
+
+/* Multi-GPU: rank r publishes its bins in exchange[r] (peer-mapped memory of
+ * b200_tally_exchange_bytes, zeroed once) and every rank merges all of them in
+ * rank order, keeping each tuple at its first occurrence - every rank ends with
+ * the identical bin list, hence bit-identical statistics.  epoch = 1, 2, 3, ...:
+ * one more per finalize, the same on every rank. */
+typedef struct b200_tally_peers {
+  void* exchange[B200_MAX_PEERS];
+  int32_t world, rank;
+  uint32_t epoch;
+  uint32_t reserved;
+} b200_tally_peers;
+
+/* table -> distinct tuples (clears the table for the next sweep); peers NULL
+ * when plan->world == 1. */
+int b200_tally_finalize(const b200_tally_plan* plan, void* workspace,
+                        const b200_tally_peers* peers, void* stream);
+
+/* The reference's 12 statistics (b200_rowstats order) of every grid point from the
+ * finalized bins: desc supplies n_grid (<= grid_cap), n_outcomes, horizon, value_0;
+ * factors_host float [G,K] as for b200_lev_sweep; n_total / top as for
+ * b200_rowstats (2 <= n_total < 2^32).  stats double [G,12]. */
+int b200_tally_stats(const b200_tally_plan* plan, void* workspace, const b200_lev_desc* desc,
+                     const float* factors_host, int64_t n_total, int64_t top, double* stats,
+                     void* stream);
 
 /* ------------------------------------------------------------------ *
  * Row statistics (the reference's summary-statistic block)
@@ -437,7 +528,6 @@ int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealt
  *                  calls must alternate between two workspaces (a peer may still be
  *                  reading the previous call's sums)
  * Runs the whole statistic block (all passes) on `stream`. */
-#define B200_MAX_PEERS 8
 typedef struct b200_peer_set {
   void* workspace[B200_MAX_PEERS];
   uint32_t* flags[B200_MAX_PEERS];

@@ -56,6 +56,29 @@ class PeerSet(C.Structure):
     ]
 
 
+class TallyPlan(C.Structure):
+    _fields_ = [
+        ("rows_cap", C.c_int64),
+        ("bins_cap", C.c_int64),
+        ("grid_cap", C.c_int32),
+        ("world", C.c_int32),
+    ]
+
+
+class TallyPeers(C.Structure):
+    _fields_ = [
+        ("exchange", C.c_void_p * MAX_PEERS),
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("epoch", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+DT_U8, DT_I32, DT_I64, DT_F32, DT_F64 = 0, 1, 2, 3, 4
+TALLY_INFO_WORDS = 8
+TALLY_MAX_HORIZON = (1 << 21) - 1
+
 ENV_COIN, ENV_DICE, ENV_GBM, ENV_DICE_SH = 0, 1, 2, 3
 INV_A, INV_B, INV_C, INV_INSURED = 0, 1, 2, 3
 ENV_MAX_GAMBLES = 8
@@ -203,6 +226,14 @@ _SIGNATURES = {
     "b200_growth_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),
     "b200_growth_summary": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, C.c_double, _i32, C.POINTER(C.c_double),
                                       _i32, _vp, _vp, _i32, _vp]),
+    "b200_tally_workspace_bytes": (_i64, [C.POINTER(TallyPlan)]),
+    "b200_tally_exchange_bytes": (_i64, [C.POINTER(TallyPlan)]),
+    "b200_tally_reset": (C.c_int, [C.POINTER(TallyPlan), _vp, _vp]),
+    "b200_lev_tally": (C.c_int, [C.POINTER(LevDesc), _vp, C.POINTER(TallyPlan), _vp, _vp, _vp]),
+    "b200_lev_ingest": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _i32, _vp, _i64, _vp, C.POINTER(TallyPlan), _vp, _vp]),
+    "b200_tally_finalize": (C.c_int, [C.POINTER(TallyPlan), _vp, C.POINTER(TallyPeers), _vp]),
+    "b200_tally_stats": (C.c_int, [C.POINTER(TallyPlan), _vp, C.POINTER(LevDesc), C.POINTER(C.c_float), _i64, _i64,
+                                   _vp, _vp]),
     "b200_rowstats_workspace_bytes": (_i64, [_i64]),
     "b200_rowstats": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "b200_rowstats_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),

@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "lev_kernels.cuh"
+#include "tally.cuh"
 
 namespace b200 {
 
@@ -129,7 +130,7 @@ template <int K>
 __global__ void __launch_bounds__(COUNT_WARPS * 32)
 log_discrete_stream_kernel(const uint8_t* __restrict__ outcomes, int64_t ld, int32_t H, int64_t N, int32_t G,
                            const __grid_constant__ LogFactorTable lf, double logV0, float* __restrict__ data_T,
-                           double* __restrict__ log_w, int32_t* __restrict__ counts, int64_t ldT) {
+                           double* __restrict__ log_w, int32_t* __restrict__ counts, int64_t ldT, const TallyDev tally) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * COUNT_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * COUNT_WARPS;
@@ -179,6 +180,8 @@ log_discrete_stream_kernel(const uint8_t* __restrict__ outcomes, int64_t ld, int
     else if (K == 3) { n[1] = (int)s1; n[2] = (int)s2; n[0] = H - n[1] - n[2]; n[3] = 0; }
     else { n[3] = (int)s3; n[1] = (int)(s1 - s3); n[2] = (int)(s2 - s3); n[0] = H - n[1] - n[2] - n[3]; }
     if (counts != nullptr && lane < K) counts[row * K + lane] = n[lane];
+    if (tally.keys != nullptr && lane == 0) tally_insert(tally, tally_key(n[1], n[2], n[3]), 1u);
+    if (data_T == nullptr && log_w == nullptr) continue;
     for (int g = lane; g < G; g += 32) {
       double lw = logV0;
 #pragma unroll
@@ -224,11 +227,14 @@ __device__ __forceinline__ uint4 last_vector_mask(int valid) {
 // log-wealth / exp epilogue then runs once for the 32 rows with one row per lane
 // - 1/32 of the epilogue instructions per row, uniform (constant-bank) table
 // reads and 128-byte coalesced stores of data_T / log_w.
-template <int K>
+// TALLY: the row's count tuple goes to the tally (tally.cuh) and nothing else is written
+// but `counts` - the instantiation the final-time statistics run on.
+template <int K, bool TALLY>
 __global__ void __launch_bounds__(COUNT_WARPS * 32, 4)   // 64 registers: 4 blocks per SM measured best (3: 0.86, 5: 0.83 of HBM)
 log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, int32_t H, int64_t N, int32_t G,
                            const __grid_constant__ LogFactorTable lf, double logV0, float* __restrict__ data_T,
-                           double* __restrict__ log_w, int32_t* __restrict__ counts, int64_t ldT, int32_t task_rows) {
+                           double* __restrict__ log_w, int32_t* __restrict__ counts, int64_t ldT, const TallyDev tally,
+                           int32_t task_rows) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * COUNT_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * COUNT_WARPS;
@@ -326,6 +332,10 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
       if (counts != nullptr) {
 #pragma unroll
         for (int k = 0; k < K; ++k) counts[row * K + k] = n[k];
+      }
+      if (TALLY) {
+        tally_insert(tally, tally_key(n[1], n[2], n[3]), 1u);
+        continue;
       }
       double nd[K];
 #pragma unroll
@@ -691,9 +701,13 @@ static int make_log_table(const b200_lev_desc& d, const float* factors_host, Log
 }
 
 static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, const float* factors_host,
-                            float* data_T, double* log_w, int32_t* counts, cudaStream_t st) {
+                            float* data_T, double* log_w, int32_t* counts, const TallyDev& tally, cudaStream_t st) {
   LogFactorTable lf;
-  if (int rc = make_log_table(d, factors_host, lf)) return rc;
+  if (factors_host != nullptr) {
+    if (int rc = make_log_table(d, factors_host, lf)) return rc;
+  } else {
+    memset(&lf, 0, sizeof(lf));   // counts / tally only
+  }
   const double logV0 = log((double)d.value_0);
   const int64_t N = d.n_investors;
   // a warp per row (uint8 codes) / per 32 rows (packed)
@@ -709,13 +723,21 @@ static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, con
   if (blocks > cap) blocks = cap;
 #define B200_LOG_LAUNCH(KERNEL, ...)                                                                                     \
   KERNEL<__VA_ARGS__><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, \
-                                                                     logV0, data_T, log_w, counts, out_ld(d) B200_EXTRA)
+                                                                     logV0, data_T, log_w, counts, out_ld(d), tally B200_EXTRA)
   if (d.outcome_bits == 2) {
 #define B200_EXTRA , task_rows
-    switch (d.n_outcomes) {
-      case 2: B200_LOG_LAUNCH(log_discrete_packed_kernel, 2); break;
-      case 3: B200_LOG_LAUNCH(log_discrete_packed_kernel, 3); break;
-      default: B200_LOG_LAUNCH(log_discrete_packed_kernel, 4); break;
+    if (tally.keys != nullptr) {
+      switch (d.n_outcomes) {
+        case 2: B200_LOG_LAUNCH(log_discrete_packed_kernel, 2, true); break;
+        case 3: B200_LOG_LAUNCH(log_discrete_packed_kernel, 3, true); break;
+        default: B200_LOG_LAUNCH(log_discrete_packed_kernel, 4, true); break;
+      }
+    } else {
+      switch (d.n_outcomes) {
+        case 2: B200_LOG_LAUNCH(log_discrete_packed_kernel, 2, false); break;
+        case 3: B200_LOG_LAUNCH(log_discrete_packed_kernel, 3, false); break;
+        default: B200_LOG_LAUNCH(log_discrete_packed_kernel, 4, false); break;
+      }
     }
 #undef B200_EXTRA
 #define B200_EXTRA
@@ -824,13 +846,28 @@ extern "C" int b200_lev_sweep(const b200_lev_desc* desc, const void* outcomes, c
     if (d.mode == B200_MODE_LOG) {
       B200_REQUIRE(d.source == B200_SRC_STREAM, "lev_sweep: discrete LOG mode takes streamed outcomes");
       B200_REQUIRE(data_T || log_w || counts, "lev_sweep: LOG mode needs at least one output");
-      return run_log_discrete(d, (const uint8_t*)outcomes, host_f, data_T, log_w, counts, st);
+      return run_log_discrete(d, (const uint8_t*)outcomes, host_f, data_T, log_w, counts, TallyDev{nullptr, nullptr, nullptr, 0}, st);
     }
     return set_error(B200_EINVAL, "lev_sweep: unknown mode %d", d.mode);
   }
   B200_REQUIRE(d.mode == B200_MODE_LOG, "lev_sweep: GBM runs in LOG mode only (expf chains are not reproducible)");
   B200_REQUIRE(data_T || log_w, "lev_sweep: LOG mode needs at least one output");
   return run_log_gbm(d, (const float*)outcomes, host_f, data_T, log_w, st);
+}
+
+extern "C" int b200_lev_tally(const b200_lev_desc* desc, const void* outcomes, const b200_tally_plan* plan,
+                              void* workspace, int32_t* counts, void* stream) {
+  int rc = validate(desc);
+  if (rc) return rc;
+  const b200_lev_desc& d = *desc;
+  B200_REQUIRE(d.kind == B200_LEV_DISCRETE && d.source == B200_SRC_STREAM,
+               "lev_tally: discrete sweeps over streamed outcomes only");
+  B200_REQUIRE(plan != nullptr && d.n_investors <= plan->rows_cap, "lev_tally: more rows than the plan's rows_cap");
+  TallyDev t;
+  if ((rc = tally_device_view(plan, workspace, d.horizon, &t))) return rc;
+  if (d.n_investors == 0) return 0;
+  B200_REQUIRE(outcomes != nullptr, "lev_tally: outcomes is NULL");
+  return run_log_discrete(d, (const uint8_t*)outcomes, nullptr, nullptr, nullptr, counts, t, (cudaStream_t)stream);
 }
 
 extern "C" int b200_lev_draw(const b200_lev_desc* desc, void* out, void* stream) {

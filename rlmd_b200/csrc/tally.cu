@@ -1,0 +1,747 @@
+// Final-time statistics of the discrete sweeps from a tally of outcome-count
+// tuples (include/rlmd_b200.h "tally"; reference: the statistic block of
+// {coin,dice,dice_sh}_fixed_final_lev, lev/lev_exp.py:87-104, :545-562, :1168-1185).
+//
+//   count kernel epilogue  -> hash table (tally.cuh), one insertion per investor
+//   finalize               -> the distinct tuples as a dense list (compaction);
+//                             across GPUs: every rank publishes its list in
+//                             peer-mapped memory, raises a flag, and merges ALL
+//                             lists in rank order keeping each tuple at its first
+//                             occurrence - the one exchange of a sweep, and every
+//                             rank ends with the identical list
+//   statistics             -> wealth of every (grid point, tuple) with the count
+//                             kernels' own expressions (bit-identical data_T
+//                             values), then one block per grid point: weighted
+//                             3-level radix select (11+11+10 bits of the fp32 key)
+//                             for the four target ranks, exact top / rest split with
+//                             tie apportioning, two-pass fp64 moments.  The block
+//                             owns its row: no atomics on fp64, so the result does
+//                             not depend on scheduling, only on the list order.
+//
+// Semantics follow rowstats.cu (torch.sort / std_mean / median conventions):
+// the tests run both on the same sweeps and compare.
+#include <algorithm>
+#include <cstring>
+
+#include "tally.cuh"
+
+namespace b200 {
+
+struct BinEntry {
+  unsigned long long key, count;
+};
+static_assert(sizeof(BinEntry) == 16, "one 16-byte vector per bin");
+
+constexpr int MERGE_CHUNK = 2048;     // concat positions per block of the mark / unique kernels
+constexpr int EX_FLAG_BYTES = 128;    // uint32 [B200_MAX_PEERS] arrival epochs (+ spare)
+
+struct LogTable {
+  double lm[B200_MAX_OUTCOMES][B200_MAX_GRID];
+};
+
+// ------------------------------------------------------------- layout
+struct TallyLayout {
+  long long* header;
+  unsigned long long* keysA; uint32_t* countsA; uint64_t capA;
+  unsigned long long* ukeys; uint32_t* ucnt;
+  float* wbuf; int64_t ldw;
+  int64_t list_cap;
+  // world > 1
+  BinEntry* concat; uint32_t* slot_of;
+  unsigned long long* keysB; unsigned long long* countsB; uint32_t* posB; uint64_t capB;
+  int32_t* blockcnt; int64_t nblk;
+  int64_t bytes;
+};
+
+static uint64_t pow2_at_least(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static int plan_ok(const b200_tally_plan* p) {
+  B200_REQUIRE(p != nullptr, "tally: plan is NULL");
+  B200_REQUIRE(p->rows_cap >= 1 && p->rows_cap < ((int64_t)1 << 32), "tally: rows_cap must be in 1..2^32-1");
+  B200_REQUIRE(p->bins_cap >= 1 && p->bins_cap < ((int64_t)1 << 31), "tally: bins_cap must be in 1..2^31-1");
+  B200_REQUIRE(p->grid_cap >= 1 && p->grid_cap <= B200_MAX_GRID, "tally: grid_cap must be in 1..%d", B200_MAX_GRID);
+  B200_REQUIRE(p->world >= 1 && p->world <= B200_MAX_PEERS, "tally: world must be in 1..%d", B200_MAX_PEERS);
+  return 0;
+}
+
+static TallyLayout layout(const b200_tally_plan& p, void* base) {
+  TallyLayout L;
+  memset(&L, 0, sizeof(L));
+  char* b = (char*)base;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { char* r = b ? b + off : nullptr; off += (bytes + 255) & ~(int64_t)255; return r; };
+  L.header = (long long*)take(TH_WORDS * 8);
+  L.capA = pow2_at_least((uint64_t)std::max<int64_t>(1024, 2 * std::min(p.rows_cap, p.bins_cap)));
+  L.list_cap = (int64_t)(L.capA / 2);
+  L.keysA = (unsigned long long*)take((int64_t)L.capA * 8);
+  L.countsA = (uint32_t*)take((int64_t)L.capA * 4);
+  L.ukeys = (unsigned long long*)take(p.bins_cap * 8);
+  L.ucnt = (uint32_t*)take(p.bins_cap * 4);
+  L.ldw = (p.bins_cap + 3) & ~(int64_t)3;
+  L.wbuf = (float*)take((int64_t)p.grid_cap * L.ldw * 4);
+  if (p.world > 1) {
+    const int64_t cat = (int64_t)p.world * L.list_cap;
+    L.concat = (BinEntry*)take(cat * 16);
+    L.slot_of = (uint32_t*)take(cat * 4);
+    L.capB = pow2_at_least((uint64_t)std::max<int64_t>(1024, 2 * std::min(cat, p.bins_cap)));
+    L.keysB = (unsigned long long*)take((int64_t)L.capB * 8);
+    L.countsB = (unsigned long long*)take((int64_t)L.capB * 8);
+    L.posB = (uint32_t*)take((int64_t)L.capB * 4);
+    L.nblk = (cat + MERGE_CHUNK - 1) / MERGE_CHUNK;
+    L.blockcnt = (int32_t*)take(L.nblk * 4);
+  }
+  L.bytes = off;
+  return L;
+}
+
+// exchange buffer of one rank: [flags 128 B][list 0][list 1], a list = 16-byte head (count) + list_cap entries
+static int64_t exchange_list_bytes(int64_t list_cap) { return 16 + list_cap * 16; }
+
+int tally_device_view(const b200_tally_plan* plan, void* workspace, int32_t horizon, TallyDev* out) {
+  if (int rc = plan_ok(plan)) return rc;
+  B200_REQUIRE(workspace != nullptr, "tally: workspace is NULL");
+  B200_REQUIRE(horizon <= TALLY_MAX_HORIZON, "tally: horizon must be < 2^%d (use b200_lev_sweep + b200_rowstats)",
+               TALLY_COUNT_BITS);
+  const TallyLayout L = layout(*plan, workspace);
+  out->keys = L.keysA;
+  out->counts = L.countsA;
+  out->header = L.header;
+  out->mask = L.capA - 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------- reset
+__global__ void __launch_bounds__(256)
+tally_clear_kernel(unsigned long long* keys, uint32_t* counts32, unsigned long long* counts64, uint32_t* pos,
+                   uint64_t cap) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    keys[i] = TALLY_EMPTY;
+    if (counts32) counts32[i] = 0;
+    if (counts64) counts64[i] = 0;
+    if (pos) pos[i] = 0xffffffffu;
+  }
+}
+
+// ------------------------------------------------------------ compaction
+// Table -> dense list, and the table is left empty for the next sweep.  The append
+// order is whatever the scheduler makes it (one atomic per warp); the statistics
+// of ONE GPU therefore agree run to run up to the rounding of fp64 sums taken in
+// a different order, exactly like b200_rowstats.  The last block to finish
+// publishes the count (and, across GPUs, raises this rank's flag at every peer).
+struct PeerView {
+  BinEntry* list[B200_MAX_PEERS];           // the published list of rank r for this epoch, as mapped here
+  long long* list_count[B200_MAX_PEERS];
+  uint32_t* flags[B200_MAX_PEERS];
+  int32_t world, rank;
+  uint32_t epoch;
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(256)
+tally_compact_kernel(TallyDev t, unsigned long long* __restrict__ ukeys, uint32_t* __restrict__ ucnt,
+                     int64_t out_cap, const __grid_constant__ PeerView P) {
+  const uint64_t cap = t.mask + 1;
+  const int lane = threadIdx.x & 31;
+  BinEntry* list = MULTI ? P.list[P.rank] : nullptr;
+  for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); base < cap;
+       base += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = base + lane;
+    unsigned long long key = TALLY_EMPTY;
+    uint32_t c = 0;
+    if (i < cap) {
+      key = __ldcg(t.keys + i);
+      if (key != TALLY_EMPTY) {
+        c = __ldcg(t.counts + i);
+        t.keys[i] = TALLY_EMPTY;
+        t.counts[i] = 0;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, key != TALLY_EMPTY);
+    if (m == 0) continue;
+    long long pos0 = 0;
+    if (lane == 0) pos0 = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(t.header + TH_LISTPOS),
+                                                (unsigned long long)__popc(m));
+    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+    if (key != TALLY_EMPTY) {
+      const long long p = pos0 + __popc(m & ((1u << lane) - 1u));
+      if (p < out_cap) {
+        if (MULTI) { list[p].key = key; list[p].count = c; }
+        else { ukeys[p] = key; ucnt[p] = c; }
+      } else {
+        t.header[TH_OVERFLOW] = 1;
+      }
+    }
+  }
+  // last block done?
+  __shared__ int last_s;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long tk = atomicAdd(reinterpret_cast<unsigned long long*>(t.header + TH_TICKET), 1ull);
+    last_s = tk == (unsigned long long)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    const long long total = *reinterpret_cast<volatile long long*>(t.header + TH_LISTPOS);
+    const long long n = total < out_cap ? total : out_cap;
+    t.header[TH_LISTPOS] = 0;
+    t.header[TH_TICKET] = 0;
+    t.header[TH_USED] = 0;
+    if (MULTI) *P.list_count[P.rank] = n;
+    else t.header[TH_NBINS] = n;
+  }
+  if (MULTI) {
+    __syncthreads();
+    if (threadIdx.x < P.world && threadIdx.x != P.rank) {
+      __threadfence_system();
+      uint32_t* f = P.flags[threadIdx.x] + P.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(P.epoch) : "memory");
+    }
+  }
+}
+
+// ------------------------------------------------------------------ merge
+__device__ __forceinline__ void ld_sys_entry(const BinEntry* p, unsigned long long& k, unsigned long long& c) {
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(k), "=l"(c) : "l"(p));
+}
+
+// Every block waits for the world's flags (one lane per peer), then the grid walks
+// the concatenation of the ranks' lists: entry p is copied to local memory and
+// added to table B, which also keeps the smallest p of every tuple.
+__global__ void __launch_bounds__(256)
+tally_merge_kernel(const __grid_constant__ PeerView P, long long* __restrict__ header, BinEntry* __restrict__ concat,
+                   uint32_t* __restrict__ slot_of, unsigned long long* __restrict__ keysB,
+                   unsigned long long* __restrict__ countsB, uint32_t* __restrict__ posB, uint64_t capB,
+                   int64_t concat_cap) {
+  __shared__ long long off_s[B200_MAX_PEERS + 1];
+  __shared__ int ok_s;
+  if (threadIdx.x == 0) ok_s = 1;
+  __syncthreads();
+  if (threadIdx.x < P.world && threadIdx.x != P.rank) {
+    const uint32_t* f = P.flags[P.rank] + threadIdx.x;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int32_t)(v - P.epoch) >= 0) break;
+      __nanosleep(100);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 30000000000ull) { ok_s = 0; break; }
+    }
+  }
+  __syncthreads();
+  if (!ok_s) {
+    if (threadIdx.x == 0) { header[TH_TIMEOUT] = 1; header[TH_CONCAT] = 0; }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    long long acc = 0;
+    for (int r = 0; r < P.world; ++r) {
+      off_s[r] = acc;
+      long long c;
+      asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(c) : "l"(P.list_count[r]));
+      acc += c;
+    }
+    off_s[P.world] = acc;
+  }
+  __syncthreads();
+  long long total = off_s[P.world];
+  if (total > concat_cap) total = concat_cap;   // cannot happen: every list is <= list_cap
+  if (blockIdx.x == 0 && threadIdx.x == 0) header[TH_CONCAT] = total;
+  const uint64_t mask = capB - 1;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    int r = 0;
+    while (r + 1 < P.world && p >= off_s[r + 1]) ++r;
+    unsigned long long key, cnt;
+    ld_sys_entry(P.list[r] + (p - off_s[r]), key, cnt);
+    concat[p].key = key;
+    concat[p].count = cnt;
+    // insert into B
+    uint32_t found = 0xffffffffu;
+    if (*reinterpret_cast<volatile long long*>(header + TH_OVERFLOW) == 0) {
+      uint64_t slot = tally_mix(key) & mask;
+      for (uint64_t probe = 0; probe <= mask; ++probe) {
+        unsigned long long cur = __ldcg(keysB + slot);
+        if (cur == TALLY_EMPTY) {
+          cur = atomicCAS(keysB + slot, TALLY_EMPTY, key);
+          if (cur == TALLY_EMPTY) {
+            const unsigned long long used = atomicAdd(reinterpret_cast<unsigned long long*>(header + TH_USEDB), 1ull) + 1;
+            if (used > capB / 2) { header[TH_OVERFLOW] = 1; break; }
+            cur = key;
+          }
+        }
+        if (cur == key) {
+          atomicAdd(countsB + slot, cnt);
+          atomicMin(posB + slot, (uint32_t)p);
+          found = (uint32_t)slot;
+          break;
+        }
+        slot = (slot + 1) & mask;
+      }
+    }
+    slot_of[p] = found;
+  }
+}
+
+// first occurrences per block of MERGE_CHUNK positions
+__global__ void __launch_bounds__(256)
+tally_mark_kernel(const long long* __restrict__ header, const uint32_t* __restrict__ slot_of,
+                  const uint32_t* __restrict__ posB, int32_t* __restrict__ blockcnt) {
+  __shared__ long long red[32];
+  const long long total = header[TH_CONCAT];
+  const long long base = (long long)blockIdx.x * MERGE_CHUNK;
+  if (base >= total) return;
+  long long c = 0;
+  for (int u = 0; u < MERGE_CHUNK / 256; ++u) {
+    const long long p = base + (long long)threadIdx.x * (MERGE_CHUNK / 256) + u;
+    if (p < total) {
+      const uint32_t s = slot_of[p];
+      c += (s != 0xffffffffu && __ldcg(posB + s) == (uint32_t)p);
+    }
+  }
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) blockcnt[blockIdx.x] = (int32_t)c;
+}
+
+// Stable compaction of the first occurrences: the merged list in concatenation order
+// (identical on every rank); table B is emptied on the way.
+__global__ void __launch_bounds__(256)
+tally_unique_kernel(long long* __restrict__ header, const BinEntry* __restrict__ concat,
+                    const uint32_t* __restrict__ slot_of, unsigned long long* __restrict__ keysB,
+                    unsigned long long* __restrict__ countsB, uint32_t* __restrict__ posB,
+                    const int32_t* __restrict__ blockcnt, unsigned long long* __restrict__ ukeys,
+                    uint32_t* __restrict__ ucnt, int64_t bins_cap) {
+  __shared__ long long red[32];
+  __shared__ long long warp_tot[8];
+  __shared__ long long base_s;
+  const long long total = header[TH_CONCAT];
+  const long long base = (long long)blockIdx.x * MERGE_CHUNK;
+  if (base >= total) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { header[TH_NBINS] = 0; header[TH_USEDB] = 0; }
+    return;
+  }
+  long long before = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += 256) before += blockcnt[i];
+  before = block_sum(before, red);
+  if (threadIdx.x == 0) base_s = before;
+  constexpr int PER = MERGE_CHUNK / 256;
+  bool rep[PER];
+  uint32_t slot[PER];
+  int mine = 0;
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const long long p = base + (long long)threadIdx.x * PER + u;
+    rep[u] = false;
+    slot[u] = 0xffffffffu;
+    if (p < total) {
+      slot[u] = slot_of[p];
+      rep[u] = slot[u] != 0xffffffffu && __ldcg(posB + slot[u]) == (uint32_t)p;
+    }
+    mine += rep[u];
+  }
+  // exclusive scan of `mine` over the block
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  long long pre = 0, blocktotal = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < wid) pre += warp_tot[w];
+    blocktotal += warp_tot[w];
+  }
+  long long outp = base_s + pre + incl - mine;
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    if (!rep[u]) continue;
+    const long long p = base + (long long)threadIdx.x * PER + u;
+    if (outp < bins_cap) {
+      ukeys[outp] = concat[p].key;
+      ucnt[outp] = (uint32_t)__ldcg(countsB + slot[u]);
+    } else {
+      header[TH_OVERFLOW] = 1;
+    }
+    keysB[slot[u]] = TALLY_EMPTY;
+    countsB[slot[u]] = 0;
+    posB[slot[u]] = 0xffffffffu;
+    ++outp;
+  }
+  if (base + MERGE_CHUNK >= total && threadIdx.x == 0) {
+    const long long n = base_s + blocktotal;
+    header[TH_NBINS] = n < bins_cap ? n : bins_cap;
+    header[TH_USEDB] = 0;
+  }
+}
+
+// ----------------------------------------------------------------- wealth
+// data_T of every (grid point, tuple): the epilogue of the LOG count kernels
+// (lev_sweep.cu), expression for expression - so a bin's wealth is bit-identical to
+// the data_T entry of every investor in it.
+template <int K>
+__global__ void __launch_bounds__(256)
+tally_wealth_kernel(const long long* __restrict__ header, const unsigned long long* __restrict__ ukeys, int32_t H,
+                    int32_t G, const __grid_constant__ LogTable lf, double logV0, float* __restrict__ wbuf,
+                    int64_t ldw) {
+  const long long B = header[TH_NBINS];
+  const long long total = B * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i / B);
+    const long long b = i - (long long)g * B;
+    int n1, n2, n3;
+    tally_unkey(__ldg(ukeys + b), n1, n2, n3);
+    int n[4];
+    n[1] = n1; n[2] = K >= 3 ? n2 : 0; n[3] = K >= 4 ? n3 : 0;
+    n[0] = H - n[1] - n[2] - n[3];
+    double lw = logV0;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (n[k] > 0) lw += (double)n[k] * lf.lm[k][g];
+    wbuf[(int64_t)g * ldw + b] = (float)exp(lw);
+  }
+}
+
+// ----------------------------------------------------------------- select
+constexpr int SEL_THREADS = 1024;
+constexpr int SL1 = 2048, SL2 = 2048, SL3 = 1024;   // bins per level (11 + 11 + 10 key bits)
+
+// In-place inclusive scans: group `grp` (256 threads) scans histogram `grp` of
+// `bins` counters (bins % 256 == 0); groups >= n_hist idle.  Two barriers.
+__device__ __forceinline__ void scan_hists(uint32_t* hist, int bins, int n_hist, uint32_t* warp_tot /*[32]*/) {
+  const int grp = threadIdx.x >> 8, t = threadIdx.x & 255;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int per = bins >> 8;
+  uint32_t* h = hist + grp * bins + t * per;
+  uint32_t local = 0;
+  if (grp < n_hist)
+    for (int i = 0; i < per; ++i) local += h[i];
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  uint32_t pre = 0;
+  for (int w = grp * 8; w < wid; ++w) pre += warp_tot[w];
+  uint32_t run = pre + incl - local;
+  if (grp < n_hist)
+    for (int i = 0; i < per; ++i) { run += h[i]; h[i] = run; }
+  __syncthreads();
+}
+
+// smallest bin whose inclusive prefix exceeds `rank`; rem = rank inside that bin
+__device__ __forceinline__ void find_rank(const uint32_t* pre, int bins, long long rank, int& bin, long long& rem) {
+  int lo = 0, hi = bins - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)pre[mid] > rank) hi = mid; else lo = mid + 1;
+  }
+  bin = lo;
+  rem = rank - (lo > 0 ? (long long)pre[lo - 1] : 0);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+tally_select_kernel(long long* __restrict__ header, const uint32_t* __restrict__ ucnt, const float* __restrict__ wbuf,
+                    int64_t ldw, int64_t n_total, int64_t top, double* __restrict__ stats) {
+  __shared__ uint32_t hist[4 * SL2];       // level 1: [0, 2048); level 2: 4 x 2048; level 3: 4 x 1024
+  __shared__ uint32_t warp_tot[32];
+  __shared__ double red_d[32];
+  __shared__ long long red_i[32];
+  __shared__ int bin_s[4];
+  __shared__ long long rem_s[4];
+  __shared__ double sh_d[8];
+  __shared__ long long sh_i[8];
+
+  const int g = blockIdx.x;
+  const long long B = header[TH_NBINS];
+  const float* __restrict__ w = wbuf + (int64_t)g * ldw;
+  const long long n = n_total, K = top;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  double* s = stats + (int64_t)g * 12;
+  if (header[TH_TIMEOUT] != 0 || header[TH_OVERFLOW] != 0) {
+    if (threadIdx.x < 12) s[threadIdx.x] = qnan;
+    return;
+  }
+  const int tid = threadIdx.x;
+
+  // ---- pass 0: sum, count, level-1 histogram
+  for (int i = tid; i < SL1; i += SEL_THREADS) hist[i] = 0;
+  __syncthreads();
+  double a0 = 0;
+  long long c0 = 0;
+  for (long long b = tid; b < B; b += SEL_THREADS) {
+    const float x = w[b];
+    const uint32_t c = ucnt[b];
+    a0 += (double)c * (double)x;
+    c0 += c;
+    atomicAdd(&hist[float_key(x) >> 21], c);
+  }
+  const double sum_all = block_sum(a0, red_d);
+  const long long cnt_all = block_sum(c0, red_i);
+  __syncthreads();
+  if (tid == 0) {
+    if (cnt_all != n) header[TH_MISMATCH] = 1;
+    // key bins that can only hold non-finite values: 3 = -inf, 2044 = +inf, 2047 = NaN
+    const long long ninf = hist[3], pinf = hist[2044], nan = hist[2047];
+    const long long hi = pinf + nan;
+    sh_i[0] = (hi + ninf) > 0; sh_i[1] = hi > 0 || ninf > n - K; sh_i[2] = hi > K || ninf > 0;   // nonfinite all/top/adj
+    sh_i[3] = nan > 0; sh_i[4] = nan > 0; sh_i[5] = nan > K;                                       // has_nan
+    sh_d[0] = sum_all / (double)n;   // mean_all
+  }
+  scan_hists(hist, SL1, 1, warp_tot);
+  const long long ranks[4] = {(n - 1) / 2, n - K, n - K + (K - 1) / 2, (n - K - 1) / 2};
+  if (tid < 4) find_rank(hist, SL1, ranks[tid], bin_s[tid], rem_s[tid]);
+  __syncthreads();
+  uint32_t pre[4];
+  long long rk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { pre[j] = (uint32_t)bin_s[j]; rk[j] = rem_s[j]; }
+  __syncthreads();
+
+  // ---- pass 1: level-2 histograms of the elements in the targets' level-1 bins
+  for (int i = tid; i < 4 * SL2; i += SEL_THREADS) hist[i] = 0;
+  __syncthreads();
+  for (long long b = tid; b < B; b += SEL_THREADS) {
+    const uint32_t k = float_key(w[b]);
+    const uint32_t b1 = k >> 21;
+    if ((b1 == pre[0]) | (b1 == pre[1]) | (b1 == pre[2]) | (b1 == pre[3])) {
+      const uint32_t c = ucnt[b];
+      const uint32_t b2 = (k >> 10) & (SL2 - 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (b1 == pre[j]) atomicAdd(&hist[j * SL2 + b2], c);
+    }
+  }
+  __syncthreads();
+  scan_hists(hist, SL2, 4, warp_tot);
+  if (tid < 4) find_rank(hist + tid * SL2, SL2, rk[tid], bin_s[tid], rem_s[tid]);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { pre[j] = (pre[j] << 11) | (uint32_t)bin_s[j]; rk[j] = rem_s[j]; }   // 22-bit prefixes
+  __syncthreads();
+
+  // ---- pass 2: level-3 histograms + the sums on either side of thr's 22-bit prefix
+  for (int i = tid; i < 4 * SL3; i += SEL_THREADS) hist[i] = 0;
+  __syncthreads();
+  const uint32_t thr22 = pre[1];
+  double s_gt = 0, s_lt = 0;
+  long long c_gt = 0;
+  for (long long b = tid; b < B; b += SEL_THREADS) {
+    const float x = w[b];
+    const uint32_t c = ucnt[b];
+    const uint32_t k = float_key(x);
+    const uint32_t hi = k >> 10;
+    if (hi > thr22) { s_gt += (double)c * (double)x; c_gt += c; }
+    else if (hi < thr22) s_lt += (double)c * (double)x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (hi == pre[j]) atomicAdd(&hist[j * SL3 + (k & (SL3 - 1))], c);
+  }
+  const double coarse_gt = block_sum(s_gt, red_d);
+  const double coarse_lt = block_sum(s_lt, red_d);
+  const long long cnt_gt = block_sum(c_gt, red_i);
+  __syncthreads();   // histograms complete
+  // the elements that share thr's 22-bit prefix: bin `lo` of thr's level-3 histogram
+  // holds the copies of the ONE fp32 value with key (prefix22 << 10 | lo) - needed
+  // before the scan overwrites the counts; thr's own bin is not known yet, so the
+  // per-bin products are re-walked after the scan through prefix differences.
+  scan_hists(hist, SL3, 4, warp_tot);
+  if (tid < 4) find_rank(hist + tid * SL3, SL3, rk[tid], bin_s[tid], rem_s[tid]);
+  __syncthreads();
+  uint32_t key_j[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) key_j[j] = (pre[j] << 10) | (uint32_t)bin_s[j];
+  const uint32_t thr_key = key_j[1];
+  const uint32_t thr_lo = thr_key & (SL3 - 1), base = thr_key & ~(uint32_t)(SL3 - 1);
+  double f_gt = 0, f_lt = 0;
+  long long fc_gt = 0, fc_lt = 0, fc_all = 0;
+  {
+    const uint32_t* h3 = hist + 1 * SL3;
+    for (uint32_t lo = tid; lo < (uint32_t)SL3; lo += SEL_THREADS) {
+      const long long c = (long long)h3[lo] - (lo > 0 ? (long long)h3[lo - 1] : 0);
+      fc_all += c;
+      if (c == 0 || lo == thr_lo) continue;   // an empty bin must not contribute 0 * inf
+      const double v = (double)c * (double)key_float(base | lo);
+      if (lo > thr_lo) { f_gt += v; fc_gt += c; } else { f_lt += v; fc_lt += c; }
+    }
+  }
+  f_gt = block_sum(f_gt, red_d); f_lt = block_sum(f_lt, red_d);
+  fc_gt = block_sum(fc_gt, red_i); fc_lt = block_sum(fc_lt, red_i); fc_all = block_sum(fc_all, red_i);
+  __syncthreads();
+  if (tid == 0) {
+    const double thr = (double)key_float(thr_key);
+    const long long n_gt = cnt_gt + fc_gt, n_lt = (n - cnt_gt - fc_all) + fc_lt;
+    const double sum_gt = fc_gt ? coarse_gt + f_gt : coarse_gt, sum_lt = fc_lt ? coarse_lt + f_lt : coarse_lt;
+    const long long n_eq = n - n_gt - n_lt;
+    const long long tt = K - n_gt;   // ties that belong to the top group
+    sh_i[6] = tt;
+    sh_i[7] = n_eq - tt;
+    sh_d[1] = (sum_gt + (tt > 0 ? (double)tt * thr : 0.0)) / (double)K;                   // mean_top
+    sh_d[2] = (sum_lt + (n_eq - tt > 0 ? (double)(n_eq - tt) * thr : 0.0)) / (double)(n - K);   // mean_adj
+  }
+  __syncthreads();
+  const double mean_a = sh_d[0], mean_t = sh_d[1], mean_j = sh_d[2];
+
+  // ---- pass 3: deviations
+  double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0;
+  for (long long b = tid; b < B; b += SEL_THREADS) {
+    const float x = w[b];
+    const double c = (double)ucnt[b];
+    const uint32_t k = float_key(x);
+    const double xd = (double)x;
+    const double da = xd - mean_a;
+    d4 += c * fabs(da);
+    d5 += c * (da * da);
+    if (k < thr_key) { const double d = xd - mean_j; d2 += c * fabs(d); d3 += c * (d * d); }
+    else if (k > thr_key) { const double d = xd - mean_t; d0 += c * fabs(d); d1 += c * (d * d); }
+  }
+  d0 = block_sum(d0, red_d); d1 = block_sum(d1, red_d); d2 = block_sum(d2, red_d);
+  d3 = block_sum(d3, red_d); d4 = block_sum(d4, red_d); d5 = block_sum(d5, red_d);
+  if (tid == 0) {
+    const double thr = (double)key_float(thr_key);
+    const double dt = thr - mean_t, da = thr - mean_j;
+    const double tt = (double)sh_i[6], ta = (double)sh_i[7];
+    // a tie share of zero must not contribute inf * 0
+    const double abs_top = d0 + (tt > 0 ? tt * fabs(dt) : 0.0);
+    const double sq_top = d1 + (tt > 0 ? tt * dt * dt : 0.0);
+    const double abs_adj = d2 + (ta > 0 ? ta * fabs(da) : 0.0);
+    const double sq_adj = d3 + (ta > 0 ? ta * da * da : 0.0);
+    s[0] = mean_a; s[1] = mean_t; s[2] = mean_j;
+    s[3] = d4 / (double)n; s[4] = abs_top / (double)K; s[5] = abs_adj / (double)(n - K);
+    s[6] = sqrt(d5 / (double)n); s[7] = sqrt(sq_top / (double)K); s[8] = sqrt(sq_adj / (double)(n - K));
+    s[9] = (double)key_float(key_j[0]); s[10] = (double)key_float(key_j[2]); s[11] = (double)key_float(key_j[3]);
+    // torch semantics (see rowstats_resolve_kernel<3>): a non-finite member makes mean / std / MAD
+    // nan, except that a one-element group's mean is the element itself; median propagates NaN
+    const long long size[3] = {n, K, n - K};
+    const double single[3] = {qnan, thr, (double)key_float(key_j[3])};
+    for (int j = 0; j < 3; ++j) {
+      if (sh_i[j]) { s[0 + j] = size[j] == 1 ? single[j] : qnan; s[3 + j] = qnan; s[6 + j] = qnan; }
+      if (sh_i[3 + j]) s[9 + j] = qnan;
+    }
+  }
+}
+
+static int grid_for(int64_t work, int threads, int per_sm) {
+  const int64_t want = (work + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int64_t b200_tally_workspace_bytes(const b200_tally_plan* plan) {
+  if (plan_ok(plan)) return -1;
+  return layout(*plan, nullptr).bytes;
+}
+
+extern "C" int64_t b200_tally_exchange_bytes(const b200_tally_plan* plan) {
+  if (plan_ok(plan)) return -1;
+  if (plan->world == 1) return 0;
+  const TallyLayout L = layout(*plan, nullptr);
+  return EX_FLAG_BYTES + 2 * ((exchange_list_bytes(L.list_cap) + 255) & ~(int64_t)255);
+}
+
+extern "C" int b200_tally_reset(const b200_tally_plan* plan, void* workspace, void* stream) {
+  if (int rc = plan_ok(plan)) return rc;
+  B200_REQUIRE(workspace != nullptr, "tally_reset: workspace is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const TallyLayout L = layout(*plan, workspace);
+  B200_CUDA(cudaMemsetAsync(L.header, 0, TH_WORDS * 8, st));
+  tally_clear_kernel<<<grid_for((int64_t)L.capA, 256, 8), 256, 0, st>>>(L.keysA, L.countsA, nullptr, nullptr, L.capA);
+  if (plan->world > 1)
+    tally_clear_kernel<<<grid_for((int64_t)L.capB, 256, 8), 256, 0, st>>>(L.keysB, nullptr, L.countsB, L.posB, L.capB);
+  return check_cuda(cudaGetLastError(), "tally_reset launch");
+}
+
+extern "C" int b200_tally_finalize(const b200_tally_plan* plan, void* workspace, const b200_tally_peers* peers,
+                                   void* stream) {
+  if (int rc = plan_ok(plan)) return rc;
+  B200_REQUIRE(workspace != nullptr, "tally_finalize: workspace is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const TallyLayout L = layout(*plan, workspace);
+  TallyDev t{L.keysA, L.countsA, L.header, L.capA - 1};
+  PeerView P;
+  memset(&P, 0, sizeof(P));
+  const int cgrid = grid_for((int64_t)L.capA, 256, 8);
+  if (plan->world == 1) {
+    tally_compact_kernel<false><<<cgrid, 256, 0, st>>>(t, L.ukeys, L.ucnt, std::min(plan->bins_cap, L.list_cap), P);
+    return check_cuda(cudaGetLastError(), "tally_compact launch");
+  }
+  B200_REQUIRE(peers != nullptr, "tally_finalize: peers is NULL with world > 1");
+  B200_REQUIRE(peers->world == plan->world && peers->rank >= 0 && peers->rank < peers->world,
+               "tally_finalize: peers->world / rank do not fit the plan");
+  B200_REQUIRE(peers->epoch >= 1, "tally_finalize: epoch starts at 1");
+  const int64_t lbytes = (exchange_list_bytes(L.list_cap) + 255) & ~(int64_t)255;
+  P.world = peers->world; P.rank = peers->rank; P.epoch = peers->epoch;
+  for (int r = 0; r < peers->world; ++r) {
+    B200_REQUIRE(peers->exchange[r] != nullptr, "tally_finalize: exchange buffer of rank %d is NULL", r);
+    char* ex = (char*)peers->exchange[r];
+    char* lst = ex + EX_FLAG_BYTES + (peers->epoch & 1) * lbytes;
+    P.flags[r] = (uint32_t*)ex;
+    P.list_count[r] = (long long*)lst;
+    P.list[r] = (BinEntry*)(lst + 16);
+  }
+  tally_compact_kernel<true><<<cgrid, 256, 0, st>>>(t, nullptr, nullptr, L.list_cap, P);
+  B200_CUDA(cudaGetLastError());
+  const int64_t cat = (int64_t)plan->world * L.list_cap;
+  tally_merge_kernel<<<sm_count() * 2, 256, 0, st>>>(P, L.header, L.concat, L.slot_of, L.keysB, L.countsB, L.posB,
+                                                     L.capB, cat);
+  B200_CUDA(cudaGetLastError());
+  tally_mark_kernel<<<(unsigned)L.nblk, 256, 0, st>>>(L.header, L.slot_of, L.posB, L.blockcnt);
+  B200_CUDA(cudaGetLastError());
+  tally_unique_kernel<<<(unsigned)L.nblk, 256, 0, st>>>(L.header, L.concat, L.slot_of, L.keysB, L.countsB, L.posB,
+                                                        L.blockcnt, L.ukeys, L.ucnt, plan->bins_cap);
+  return check_cuda(cudaGetLastError(), "tally_unique launch");
+}
+
+extern "C" int b200_tally_stats(const b200_tally_plan* plan, void* workspace, const b200_lev_desc* desc,
+                                const float* factors_host, int64_t n_total, int64_t top, double* stats, void* stream) {
+  if (int rc = plan_ok(plan)) return rc;
+  B200_REQUIRE(workspace != nullptr && desc != nullptr && factors_host != nullptr && stats != nullptr,
+               "tally_stats: NULL argument");
+  B200_REQUIRE(desc->n_grid >= 1 && desc->n_grid <= plan->grid_cap, "tally_stats: n_grid must be in 1..grid_cap");
+  B200_REQUIRE(desc->n_outcomes >= 2 && desc->n_outcomes <= B200_MAX_OUTCOMES, "tally_stats: n_outcomes out of range");
+  B200_REQUIRE(desc->horizon >= 1 && desc->horizon <= TALLY_MAX_HORIZON, "tally_stats: horizon out of range");
+  B200_REQUIRE(n_total >= 2 && n_total < ((int64_t)1 << 32), "tally_stats: need 2 <= n_total < 2^32");
+  B200_REQUIRE(top >= 1 && top < n_total, "tally_stats: need 1 <= top < n_total (top=%lld)", (long long)top);
+  cudaStream_t st = (cudaStream_t)stream;
+  const TallyLayout L = layout(*plan, workspace);
+  LogTable lf;
+  for (int k = 0; k < B200_MAX_OUTCOMES; ++k)
+    for (int g = 0; g < B200_MAX_GRID; ++g) {
+      double v = 0.0;
+      if (g < desc->n_grid && k < desc->n_outcomes) {
+        const float m = factors_host[(int64_t)g * desc->n_outcomes + k];
+        if (m < 0.0f) return set_error(B200_EINVAL, "tally_stats: factors must be >= 0 (m[%d][%d] = %g)", g, k, (double)m);
+        v = log((double)m);
+      }
+      lf.lm[k][g] = v;
+    }
+  const double logV0 = log((double)desc->value_0);
+  const int wgrid = sm_count() * 8;
+  switch (desc->n_outcomes) {
+    case 2: tally_wealth_kernel<2><<<wgrid, 256, 0, st>>>(L.header, L.ukeys, desc->horizon, desc->n_grid, lf, logV0, L.wbuf, L.ldw); break;
+    case 3: tally_wealth_kernel<3><<<wgrid, 256, 0, st>>>(L.header, L.ukeys, desc->horizon, desc->n_grid, lf, logV0, L.wbuf, L.ldw); break;
+    default: tally_wealth_kernel<4><<<wgrid, 256, 0, st>>>(L.header, L.ukeys, desc->horizon, desc->n_grid, lf, logV0, L.wbuf, L.ldw); break;
+  }
+  B200_CUDA(cudaGetLastError());
+  tally_select_kernel<<<desc->n_grid, SEL_THREADS, 0, st>>>(L.header, L.ucnt, L.wbuf, L.ldw, n_total, top, stats);
+  return check_cuda(cudaGetLastError(), "tally_select launch");
+}

@@ -35,19 +35,72 @@ def device_info() -> dict:
 
 
 # ----------------------------------------------------------------- outcomes
-def encode_codes(outcomes, device="cuda") -> torch.Tensor:
+def _cuda_device(device=None) -> torch.device:
+    """The CUDA device a call runs on: `device` when it names one, else the current one
+    (the reference scripts pass T.device("cpu") with VRAM = False, lev/coin_flip.py:67,137)."""
+    if device is not None:
+        d = torch.device(device)
+        if d.type == "cuda":
+            return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def encode_codes(outcomes, device=None, n_outcomes: int = 4, chunk_bytes: int = 256 << 20) -> torch.Tensor:
     """
     Reference-format outcomes ([N,H] fp32 {0,1} for the coin, int64 {0,1,2} for
-    the dice; lev/coin_flip.py:160-161, lev/dice_roll.py:147-148) -> the engine
-    format: uint8 codes [N, ld] on the GPU with ld = H rounded up to 16 so that
-    the TMA path applies.  Returns a view [N,H] of the padded buffer.
+    the dice; lev/coin_flip.py:160-161, lev/dice_roll.py:147-148; host or device,
+    also int32 / fp64 / uint8 / bool / NumPy) -> the engine format: uint8 codes
+    [N, ld] on the GPU with ld = H rounded up to 16 so that the TMA path applies.
+    Returns a view [N,H] of the padded buffer.  The conversion is b200_lev_ingest;
+    a host array is walked in row chunks through two staging buffers (the device
+    never holds more than two chunks of the wide source format).
+    n_outcomes = 2: code = (x == 1), the coin's rule (lev/lev_exp.py:85).
     """
     require_cuda()
+    from . import tally as _tally
+
     t = torch.as_tensor(outcomes)
+    if t.dtype == torch.bool:
+        t = t.view(torch.uint8)
+    if t.dtype not in _tally._SRC_TYPES:
+        raise TypeError(f"outcomes of dtype {t.dtype} are not an accepted format")
     n, h = t.shape
+    dev = t.device if t.is_cuda else _cuda_device(device)
     ld = _round_up(h, 16)
-    buf = torch.zeros((n, ld), dtype=torch.uint8, device=device)
-    buf[:, :h].copy_(t.to(device=device, non_blocking=True))
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    with torch.cuda.device(dev):
+        buf = torch.zeros((n, ld), dtype=torch.uint8, device=dev)
+        if n == 0:
+            return buf[:, :h]
+
+        def ingest(src, dst):
+            m = src.shape[0]
+            lds = src.stride(0) if m > 1 else max(src.stride(0), h)
+            check(lib.b200_lev_ingest(ptr(src), _tally._SRC_TYPES[src.dtype], m, h, lds, int(n_outcomes), ptr(dst), ld,
+                                      None, None, None, stream_ptr()))
+
+        if t.is_cuda:
+            ingest(t, buf)
+            return buf[:, :h]
+        rows = int(max(1, min(n, chunk_bytes // max(h * t.element_size(), 1))))
+        stage = [torch.empty((rows, h), dtype=t.dtype, device=dev) for _ in range(2)]
+        comp, copy = torch.cuda.current_stream(), _copy_stream(dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        copy.wait_stream(comp)
+        for i, r0 in enumerate(range(0, n, rows)):
+            m = min(rows, n - r0)
+            if i >= 2:
+                copy.wait_event(done[i & 1])
+            with torch.cuda.stream(copy):
+                stage[i & 1][:m].copy_(t[r0:r0 + m], non_blocking=True)
+                ready[i & 1].record(copy)
+            comp.wait_event(ready[i & 1])
+            ingest(stage[i & 1][:m], buf[r0:r0 + m])
+            done[i & 1].record(comp)
+        for b in stage:
+            b.record_stream(copy)
     return buf[:, :h]
 
 
@@ -94,14 +147,22 @@ def pack_codes(codes: torch.Tensor) -> PackedCodes:
     return PackedCodes(out, h)
 
 
-def encode_returns(x, device="cuda") -> torch.Tensor:
-    """GBM log-returns -> fp32 [N, ld] on the GPU, ld a multiple of 4 (16 bytes)."""
+def encode_returns(x, device=None, chunk_bytes: int = 256 << 20) -> torch.Tensor:
+    """GBM log-returns (host or device, fp32 or fp64) -> fp32 [N, ld] on the GPU, ld a multiple of 4 (16 bytes).
+    A host array travels in row chunks (never a second whole copy of it on the device)."""
     require_cuda()
     t = torch.as_tensor(x)
     n, h = t.shape
+    dev = t.device if t.is_cuda else _cuda_device(device)
     ld = _round_up(h, 4)
-    buf = torch.zeros((n, ld), dtype=torch.float32, device=device)
-    buf[:, :h].copy_(t.to(device=device, non_blocking=True))
+    with torch.cuda.device(dev):
+        buf = torch.zeros((n, ld), dtype=torch.float32, device=dev)
+        if t.is_cuda:
+            buf[:, :h].copy_(t)
+        else:
+            rows = int(max(1, min(max(n, 1), chunk_bytes // max(h * t.element_size(), 1))))
+            for r0 in range(0, n, rows):
+                buf[r0:r0 + rows, :h].copy_(t[r0:r0 + rows], non_blocking=True)
     return buf[:, :h]
 
 
@@ -448,35 +509,130 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
     return (stats, data_T) if return_data_T else stats
 
 
+_tally_cache = {}
+
+
+def final_tally(rows: int, device, group=None):
+    """
+    The cached tally.FinalTally of (device, group) with room for `rows` investor rows
+    (grown when a call needs more).  With `group` this is COLLECTIVE the first time
+    and whenever it grows: every rank must call it with its own row count in the same
+    order (the capacity is the largest row count of the group).
+    """
+    from . import tally as _tally
+
+    dev = _cuda_device(device)
+    key = (dev.index, id(group))
+    t = _tally_cache.get(key)
+    need = max(int(rows), 1)
+    if group is not None:
+        import torch.distributed as dist
+
+        grow = torch.tensor([need if (t is None or t.plan.rows_cap < need) else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(grow, op=dist.ReduceOp.MAX, group=group)
+        need = int(grow.item())
+        if need == 0:
+            return t
+    elif t is not None and t.plan.rows_cap >= need:
+        return t
+    if t is not None:
+        torch.cuda.synchronize(dev)          # peers may still read the old exchange buffer
+        if group is not None:
+            import torch.distributed as dist
+
+            dist.barrier(group=group)
+    t = _tally.FinalTally(need, device=dev, group=group)
+    _tally_cache[key] = t
+    return t
+
+
+def lev_final_stats(factors: np.ndarray, value_0: float, top: int, outcomes, *, device=None, group=None,
+                    n_total: Optional[int] = None, check: bool = True, tally=None, info: Optional[dict] = None):
+    """
+    The *_fixed_final_lev hot path of the DISCRETE gambles (lev/lev_exp.py:56-125,
+    :508-583, :1121-1206) for outcomes in ANY accepted format, on the GPU or in host
+    memory: one read of the outcomes by a count / ingest kernel whose sink is the
+    tally of count tuples, then the reference's 12 statistics of every leverage from
+    the distinct tuples (tally.py; no data_T, no [G,N] pass).  factors [G,K] fp32.
+
+    Returns float64 [G,12] on the GPU (engine.STAT_NAMES order).  With check=True the
+    call ends with one small device-to-host read and raises ValueError (outcomes
+    outside 0..K-1), tally.TallyOverflow (more distinct tuples than the plan holds:
+    use lev_sweep + rowstats), or RuntimeError (a peer timed out).  `info`, when a
+    dict, receives {"h2d_bytes": ...} and the tally's info words.
+    With `group` the rows are this rank's investor shard; statistics are global.
+    """
+    require_cuda()
+    f = np.ascontiguousarray(factors, dtype=np.float32)
+    if f.ndim != 2:
+        raise ValueError("factors must be [G,K]")
+    k = f.shape[1]
+    packed = isinstance(outcomes, PackedCodes)
+    if not packed:
+        outcomes = torch.as_tensor(outcomes)
+    data = outcomes.data if packed else outcomes
+    n, h = outcomes.shape
+    dev = data.device if data.is_cuda else _cuda_device(device)
+    if n_total is None:
+        n_total = n
+        if group is not None:
+            from . import sharding
+
+            n_total = sharding.global_count(n, group, dev)
+    with torch.cuda.device(dev):
+        t = tally if tally is not None else final_tally(n, dev, group)
+        moved = 0
+        if data.is_cuda:
+            t.add(outcomes, k)
+        else:
+            moved = t.add_host(outcomes, k)
+        t.finalize()
+        stats = t.stats(f, float(value_0), h, n_total=int(n_total), top=int(top))
+        if info is not None:
+            info["h2d_bytes"] = moved
+        if check:
+            i = t.check()
+            if info is not None:
+                info.update(i)
+    return stats
+
+
 class FinalSweepPipeline:
     """
-    A sequence of final-time sweeps (the *_fixed_final_lev hot path: LOG sweep ->
-    data_T [G,N] -> 12 statistics per leverage) on one GPU or one investor shard,
-    with the statistics of sweep i running beside sweep i+1: two streams, `depth`
-    data_T buffers.  The statistic passes are short kernels with dependent launches
-    (and, across GPUs, four exchange points); next to the HBM-bound sweep they fill
-    otherwise idle time.  Results are those of lev_sweep + rowstats called one after
-    the other.
+    A sequence of final-time sweeps (the *_fixed_final_lev hot path) on one GPU or
+    one investor shard: float64 [G,12] statistics per submitted outcome array.
+
+    statistics = "tally" (discrete gambles; the default for them): the count kernel's
+    sink is the tally of count tuples and the statistics come from the distinct
+    tuples (tally.py) - no data_T; across GPUs one exchange per sweep.
+    statistics = "rows": LOG sweep -> data_T [G,N] -> b200_rowstats (GBM, and the
+    checker of the tally path).
+    depth = 2 runs the statistics of sweep i beside sweep i+1 (two streams, two
+    tallies / data_T buffers); depth = 1 strictly one after the other.
 
         pipe = FinalSweepPipeline("discrete", table, 100.0, top, device=dev)
-        stats = [pipe.submit(oc) for oc in outcome_arrays]   # float64 [G,12] each, on the device
-        pipe.synchronize()                                   # then read them
+        stats = [pipe.submit(oc) for oc in outcome_arrays]   # on the device
+        pipe.synchronize()                                   # then read them (raises on overflow / time-out)
     """
 
     def __init__(self, kind: str, factors: np.ndarray, value_0: float, top: int, *, device="cuda", group=None,
-                 n_total: Optional[int] = None, depth: int = 2):
+                 n_total: Optional[int] = None, depth: int = 2, statistics: Optional[str] = None):
         require_cuda()
         self.kind, self.value_0, self.top = kind, float(value_0), int(top)
         self.factors = np.ascontiguousarray(factors, dtype=np.float32)
         self.group, self.n_total = group, n_total
-        self.dev = torch.device(device)
+        self.dev = _cuda_device(device)
         self.depth = max(1, int(depth))
+        self.statistics = statistics or ("tally" if kind == "discrete" else "rows")
+        if self.statistics not in ("tally", "rows") or (self.statistics == "tally" and kind != "discrete"):
+            raise ValueError("statistics must be 'tally' (discrete gambles) or 'rows'")
         with torch.cuda.device(self.dev):
             # the statistics' short, dependent kernels go first whenever they are ready
             self.sweep_stream, self.stats_stream = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
         self.data_T = [None] * self.depth
         self.ws = [None] * self.depth
-        self.free = [None] * self.depth       # statistics that last read data_T[b]
+        self.tallies = [None] * self.depth
+        self.free = [None] * self.depth       # statistics that last read data_T[b] / tally[b]
         self.count = 0
         self.last_sweep = None                # (start, end) events of the last sweep, when timing is on
         self.timing = False
@@ -484,39 +640,58 @@ class FinalSweepPipeline:
     def submit(self, outcomes, factors: Optional[np.ndarray] = None) -> torch.Tensor:
         f = self.factors if factors is None else np.ascontiguousarray(factors, dtype=np.float32)
         g = f.shape[0]
-        n = outcomes.shape[0]
+        n, h = outcomes.shape
         b = self.count % self.depth
         self.count += 1
+        tally = self.statistics == "tally"
         with torch.cuda.device(self.dev):
             cur = torch.cuda.current_stream()
             self.sweep_stream.wait_stream(cur)        # the caller produced `outcomes` on its stream
+            data = outcomes.data if isinstance(outcomes, PackedCodes) else outcomes
+            data.record_stream(self.sweep_stream)
+            if tally and (self.tallies[b] is None or self.tallies[b].plan.rows_cap < n):
+                from . import tally as _tally
+
+                self.tallies[b] = _tally.FinalTally(n, device=self.dev, group=self.group)   # collective with a group
             with torch.cuda.stream(self.sweep_stream):
                 if self.free[b] is not None:
                     self.sweep_stream.wait_event(self.free[b])
-                if self.data_T[b] is None or tuple(self.data_T[b].shape) != (g, n):
+                if not tally and (self.data_T[b] is None or tuple(self.data_T[b].shape) != (g, n)):
                     self.data_T[b] = torch.empty((g, n), dtype=torch.float32, device=self.dev)
                     self.ws[b] = rowstats_workspace(g, self.dev)
                 if self.timing:
                     t0 = torch.cuda.Event(enable_timing=True)
                     t0.record(self.sweep_stream)
-                lev_sweep(self.kind, f, self.value_0, outcomes=outcomes, mode="log", out_data_T=self.data_T[b])
+                if tally:
+                    self.tallies[b].add(outcomes, f.shape[1])
+                else:
+                    lev_sweep(self.kind, f, self.value_0, outcomes=outcomes, mode="log", out_data_T=self.data_T[b])
                 swept = torch.cuda.Event(enable_timing=self.timing)
                 swept.record(self.sweep_stream)
                 if self.timing:
                     self.last_sweep = (t0, swept)
+            n_total = self.n_total if self.n_total is not None else n
             with torch.cuda.stream(self.stats_stream):
                 self.stats_stream.wait_event(swept)
-                stats = rowstats(self.data_T[b], self.top, n_total=self.n_total, group=self.group,
-                                 workspace=self.ws[b])
+                if tally:
+                    self.tallies[b].finalize()
+                    stats = self.tallies[b].stats(f, self.value_0, h, n_total=n_total, top=self.top)
+                else:
+                    stats = rowstats(self.data_T[b], self.top, n_total=self.n_total, group=self.group,
+                                     workspace=self.ws[b])
                 done = torch.cuda.Event()
                 done.record(self.stats_stream)
                 self.free[b] = done
+                stats.record_stream(cur)
         return stats
 
     def synchronize(self) -> None:
         self.sweep_stream.synchronize()
         self.stats_stream.synchronize()
-        if self.group is not None:
+        for t in self.tallies:
+            if t is not None:
+                t.check()
+        if self.group is not None and self.statistics == "rows":
             from . import sharding
 
             sharding.raise_if_peers_timed_out(self.group, self.dev)

@@ -12,8 +12,16 @@ Reference behaviour kept on the host, verbatim in meaning:
     (:80-81 and siblings; never for GBM :961,1042);
   * factors are evaluated left to right in fp32 on 0-dim operands
     (`1 + lev * up_r`, `1 + lev * r + (1 - lev) * sh`; :85, :541-543, :1160-1166).
-The sweeps run in CHAIN mode (exact fp32 sequential product), so `data_T` of
-the coin / dice / dice_sh functions is bit-identical to the reference's.
+The `*_smart_lev` / `*_big_brain_lev` sweeps run in CHAIN mode (exact fp32
+sequential product), so their `data_T` and medians are bit-identical to the
+reference's.  The `*_fixed_final_lev` functions reduce with `torch.prod` in the
+reference (order unspecified) and only print three significant digits: the
+discrete ones run the log-domain count sweep whose sink is the tally of count
+tuples (engine.lev_final_stats: one read of the outcomes in whatever format the
+caller holds them, then weighted exact statistics of the distinct tuples), the
+GBM one the log-domain sum.  `outcomes` may live on the GPU or in host memory,
+in the reference's dtypes (fp32 {0,1}, int64 {0,1,2}, fp32 x) or the engine's
+(uint8 codes, engine.PackedCodes); host arrays are streamed in row chunks.
 """
 from __future__ import annotations
 
@@ -100,7 +108,7 @@ def dice_sh_grid2d(device, outcomes, top, value_0, up_r, down_r, mid_r, sh_up_r,
     # point (i, j) = (a_i, b_j), row-major
     table = grid2d_factor_table(np.repeat(a, len(b)), np.tile(b, len(a)), (up_r, down_r, mid_r),
                                 (sh_up_r, sh_down_r, sh_mid_r))
-    codes = outcomes if isinstance(outcomes, engine.PackedCodes) else _codes(outcomes)
+    codes = outcomes if isinstance(outcomes, engine.PackedCodes) else _codes(outcomes, 3, device)
     res = engine.lev_grid_sweep(table, _as_float(value_0), codes)
     data_T = res["data_T"]
     n = data_T.shape[1]
@@ -116,17 +124,34 @@ def _as_float(x) -> float:
     return float(x.item()) if isinstance(x, T.Tensor) else float(x)
 
 
-def _codes(outcomes) -> T.Tensor:
+_codes_cache = {"key": None, "codes": None}
+
+
+def _codes(outcomes, n_outcomes: int, device=None) -> T.Tensor:
+    """uint8 codes [N,H] on the GPU for the CHAIN kernels.  The scripts hand the SAME outcome tensor to
+    several sweeps in a row (lev/coin_flip.py:163-227): the last conversion is kept (keyed on the source's
+    storage, shape, dtype and in-place version counter)."""
     if isinstance(outcomes, T.Tensor) and outcomes.is_cuda and outcomes.dtype == T.uint8:
         return outcomes  # already in the engine format
-    return engine.encode_codes(outcomes)
+    t = T.as_tensor(outcomes)
+    key = (t.data_ptr(), tuple(t.shape), t.dtype, t._version, str(t.device), int(n_outcomes))
+    if _codes_cache["key"] == key:
+        return _codes_cache["codes"]
+    codes = engine.encode_codes(t, device=device, n_outcomes=n_outcomes)
+    _codes_cache["key"], _codes_cache["codes"] = key, codes
+    return codes
 
 
-def _returns(outcomes) -> T.Tensor:
+def drop_codes_cache() -> None:
+    """Frees the kept conversion (10 GB for 1e6 x 1e4 outcomes)."""
+    _codes_cache["key"] = _codes_cache["codes"] = None
+
+
+def _returns(outcomes, device=None) -> T.Tensor:
     if isinstance(outcomes, T.Tensor) and outcomes.is_cuda and outcomes.dtype == T.float32 \
             and outcomes.stride(1) == 1 and outcomes.stride(0) % 4 == 0:
         return outcomes
-    return engine.encode_returns(outcomes)
+    return engine.encode_returns(outcomes, device=device)
 
 
 _FINAL_FMT = """       lev {:1.0f}%:
@@ -165,26 +190,37 @@ def _n_total(n_local: int, device) -> int:
     return n_local if _GROUP is None else sharding.global_count(n_local, _GROUP, device)
 
 
-def _final(kind, outcomes, table, lev, top, value_0, mode="chain"):
-    res = engine.lev_sweep(kind, table, _as_float(value_0), outcomes=outcomes, mode=mode)
-    n_total = _n_total(outcomes.shape[0], outcomes.device)
-    stats = engine.rowstats(res["data_T"], int(top), n_total=n_total, group=_GROUP)
-    return res["data_T"], stats.cpu().numpy()
+def _final_discrete(device, outcomes, table, top, value_0) -> np.ndarray:
+    """Statistics [G,12] of a discrete final-time sweep: the tally path; inputs it cannot hold (more
+    distinct count tuples than its plan, horizon >= 2^21) take the general path (LOG sweep -> data_T
+    -> row statistics)."""
+    from . import tally as _tally
+
+    k = table.shape[1]
+    h = outcomes.shape[1]
+    if h <= _tally._lib.TALLY_MAX_HORIZON:
+        try:
+            return engine.lev_final_stats(table, _as_float(value_0), _as_int(top), outcomes, device=device,
+                                          group=_GROUP).cpu().numpy()
+        except _tally.TallyOverflow:
+            pass
+    codes = outcomes if isinstance(outcomes, engine.PackedCodes) else _codes(outcomes, k, device)
+    res = engine.lev_sweep("discrete", table, _as_float(value_0), outcomes=codes, mode="log")
+    n_total = _n_total(codes.shape[0], res["data_T"].device)
+    return engine.rowstats(res["data_T"], _as_int(top), n_total=n_total, group=_GROUP).cpu().numpy()
 
 
 # ----------------------------------------------------- fixed final leverage
 def coin_fixed_final_lev(device, outcomes, top, value_0, up_r, down_r, lev_low, lev_high, lev_incr):
     """lev/lev_exp.py:56-125 - prints the final-time statistics per leverage."""
     lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
-    _, stats = _final("discrete", _codes(outcomes), coin_factor_table(lev, up_r, down_r), lev, top, value_0)
-    _print_final(lev, stats)
+    _print_final(lev, _final_discrete(device, outcomes, coin_factor_table(lev, up_r, down_r), top, value_0))
 
 
 def dice_fixed_final_lev(device, outcomes, top, value_0, up_r, down_r, mid_r, lev_low, lev_high, lev_incr):
     """lev/lev_exp.py:508-583."""
     lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
-    _, stats = _final("discrete", _codes(outcomes), dice_factor_table(lev, up_r, down_r, mid_r), lev, top, value_0)
-    _print_final(lev, stats)
+    _print_final(lev, _final_discrete(device, outcomes, dice_factor_table(lev, up_r, down_r, mid_r), top, value_0))
 
 
 def dice_sh_fixed_final_lev(device, outcomes, top, value_0, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r,
@@ -192,14 +228,24 @@ def dice_sh_fixed_final_lev(device, outcomes, top, value_0, up_r, down_r, mid_r,
     """lev/lev_exp.py:1121-1206."""
     lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
     table = dice_sh_factor_table(lev, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r)
-    _, stats = _final("discrete", _codes(outcomes), table, lev, top, value_0)
-    _print_final(lev, stats)
+    _print_final(lev, _final_discrete(device, outcomes, table, top, value_0))
 
 
 def gbm_fixed_final_lev(device, outcomes, top, value_0, lev_low, lev_high, lev_incr):
-    """lev/lev_exp.py:935-1005 (no sign flip of the grid)."""
+    """lev/lev_exp.py:935-1005 (no sign flip of the grid).  Host outcomes are streamed in row chunks."""
     lev = _grid(lev_low, lev_high, lev_incr)
-    _, stats = _final("gbm", _returns(outcomes), lev, lev, top, value_0, mode="log")
+    t = T.as_tensor(outcomes)
+    if not t.is_cuda:
+        if t.dtype != T.float32:
+            t = t.to(T.float32)
+        n_total = _n_total(t.shape[0], engine._cuda_device(device))
+        stats = engine.lev_final_host("gbm", lev, _as_float(value_0), _as_int(top), t, mode="log",
+                                      device=engine._cuda_device(device), group=_GROUP, n_total=n_total)
+    else:
+        x = _returns(t, device)
+        res = engine.lev_sweep("gbm", lev, _as_float(value_0), outcomes=x, mode="log")
+        stats = engine.rowstats(res["data_T"], _as_int(top), n_total=_n_total(x.shape[0], x.device),
+                                group=_GROUP).cpu().numpy()
     _print_final(lev, stats)
 
 
@@ -215,7 +261,7 @@ def _series(kind, outcomes, table, lev, investors, horizon, top, value_0) -> Tup
 def coin_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, down_r, lev_low, lev_high, lev_incr):
     """lev/lev_exp.py:128-237 -> (data [L,13,H-1], data_T [L,N]), fp32 on the GPU."""
     lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
-    data, data_T = _series("discrete", _codes(outcomes), coin_factor_table(lev, up_r, down_r), lev, investors,
+    data, data_T = _series("discrete", _codes(outcomes, 2, device), coin_factor_table(lev, up_r, down_r), lev, investors,
                            horizon, top, value_0)
     _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
     return data, data_T
@@ -225,7 +271,7 @@ def dice_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, dow
                    lev_incr):
     """lev/lev_exp.py:586-701."""
     lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
-    data, data_T = _series("discrete", _codes(outcomes), dice_factor_table(lev, up_r, down_r, mid_r), lev, investors,
+    data, data_T = _series("discrete", _codes(outcomes, 3, device), dice_factor_table(lev, up_r, down_r, mid_r), lev, investors,
                            horizon, top, value_0)
     _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
     return data, data_T
@@ -236,7 +282,7 @@ def dice_sh_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, 
     """lev/lev_exp.py:1209-1334."""
     lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
     table = dice_sh_factor_table(lev, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r)
-    data, data_T = _series("discrete", _codes(outcomes), table, lev, investors, horizon, top, value_0)
+    data, data_T = _series("discrete", _codes(outcomes, 3, device), table, lev, investors, horizon, top, value_0)
     _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
     return data, data_T
 
@@ -244,7 +290,7 @@ def dice_sh_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, 
 def gbm_smart_lev(device, outcomes, investors, horizon, top, value_0, lev_low, lev_high, lev_incr):
     """lev/lev_exp.py:1008-1118."""
     lev = _grid(lev_low, lev_high, lev_incr)
-    data, data_T = _series("gbm", _returns(outcomes), lev, lev, investors, horizon, top, value_0)
+    data, data_T = _series("gbm", _returns(outcomes, device), lev, lev, investors, horizon, top, value_0)
     _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
     return data, data_T
 
@@ -292,8 +338,8 @@ def _lev_factor64(lev_factor) -> float:
     return float(lev_factor.item()) if isinstance(lev_factor, T.Tensor) else float(lev_factor)
 
 
-def _big_brain(kind, outcomes, investors, horizon, top, value_0, returns_by_code, lev_factor, stop, roll):
-    codes = _codes(outcomes)
+def _big_brain(device, kind, outcomes, investors, horizon, top, value_0, returns_by_code, lev_factor, stop, roll):
+    codes = _codes(outcomes, len(returns_by_code), device)
     n, h = codes.shape
     if (investors is not None and _as_int(investors) != n) or (horizon is not None and _as_int(horizon) != h):
         raise ValueError("investors/horizon do not match the shape of outcomes")
@@ -309,14 +355,14 @@ def _big_brain(kind, outcomes, investors, horizon, top, value_0, returns_by_code
 def coin_big_brain_lev(device, outcomes, investors, horizon, top, value_0, up_r, down_r, lev_factor, stop_min,
                        stop_max, stop_incr, roll_min, roll_max, roll_incr):
     """lev/lev_exp.py:270-452 -> data [R,S,26,H-1] fp32 on the GPU."""
-    return _big_brain("coin", outcomes, investors, horizon, top, value_0, (down_r, up_r), lev_factor,
+    return _big_brain(device, "coin", outcomes, investors, horizon, top, value_0, (down_r, up_r), lev_factor,
                       (stop_min, stop_max, stop_incr), (roll_min, roll_max, roll_incr))
 
 
 def dice_big_brain_lev(device, outcomes, investors, horizon, top, value_0, up_r, down_r, mid_r, lev_factor, stop_min,
                        stop_max, stop_incr, roll_min, roll_max, roll_incr):
     """lev/lev_exp.py:741-932 -> data [R,S,26,H-1] fp32 on the GPU."""
-    return _big_brain("dice", outcomes, investors, horizon, top, value_0, (up_r, down_r, mid_r), lev_factor,
+    return _big_brain(device, "dice", outcomes, investors, horizon, top, value_0, (up_r, down_r, mid_r), lev_factor,
                       (stop_min, stop_max, stop_incr), (roll_min, roll_max, roll_incr))
 
 

@@ -47,7 +47,8 @@ def test_struct_layout_matches_c(tmp_path):
 
     structs = {"b200_lev_desc": _lib.LevDesc}
     names = {"EnvDesc": "b200_env_desc", "ReplayDesc": "b200_replay_desc", "PeerSet": "b200_peer_set",
-             "MarketDesc": "b200_market_desc", "CollectDesc": "b200_collect_desc", "BigBrainDesc": "b200_bigbrain_desc"}
+             "MarketDesc": "b200_market_desc", "CollectDesc": "b200_collect_desc", "BigBrainDesc": "b200_bigbrain_desc",
+             "TallyPlan": "b200_tally_plan", "TallyPeers": "b200_tally_peers"}
     for extra, cname in names.items():
         if hasattr(_lib, extra):
             structs[cname] = getattr(_lib, extra)
@@ -116,3 +117,29 @@ def test_factor_tables_match_oracle():
     lev = lo.lev_grid(0.73, 1.0, 0.03)
     assert np.array_equal(lev_exp.dice_sh_factor_table(lev, 0.5, -0.5, 0.05, -1, 5, -1),
                           lo.dice_sh_factors(lev, 0.5, -0.5, 0.05, -1, 5, -1))
+
+
+def test_tally_plan_sizes():
+    """Workspace arithmetic of the tally path (host code only): sizes grow with the plan, the exchange
+    buffer exists only across GPUs, bad plans are refused with a message."""
+    import ctypes as C
+
+    from rlmd_b200 import _lib
+
+    def plan(rows, bins, grid=64, world=1):
+        p = _lib.TallyPlan()
+        p.rows_cap, p.bins_cap, p.grid_cap, p.world = rows, bins, grid, world
+        return p
+
+    small = _lib.lib.b200_tally_workspace_bytes(C.byref(plan(1000, 1000)))
+    big = _lib.lib.b200_tally_workspace_bytes(C.byref(plan(1_000_000, 1_000_000)))
+    multi = _lib.lib.b200_tally_workspace_bytes(C.byref(plan(1_000_000, 1_000_000, world=8)))
+    assert 0 < small < big < multi
+    # table (12 B x 2^21) + bins (12 B) + wealth buffer (64 x 4 B) per possible tuple
+    assert big >= (1 << 21) * 12 + 1_000_000 * (12 + 256)
+    assert _lib.lib.b200_tally_exchange_bytes(C.byref(plan(1000, 1000))) == 0
+    assert _lib.lib.b200_tally_exchange_bytes(C.byref(plan(1_000_000, 1_000_000, world=8))) >= 2 * 16 * (1 << 20)
+    assert _lib.lib.b200_tally_workspace_bytes(C.byref(plan(0, 10))) < 0
+    assert b"rows_cap" in _lib.lib.b200_last_error()
+    assert _lib.lib.b200_tally_workspace_bytes(C.byref(plan(10, 10, grid=65))) < 0
+    assert _lib.lib.b200_tally_workspace_bytes(C.byref(plan(10, 10, world=9))) < 0
