@@ -20,7 +20,10 @@
 //
 // Semantics follow rowstats.cu (torch.sort / std_mean / median conventions):
 // the tests run both on the same sweeps and compare.
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "tally.cuh"
@@ -75,7 +78,7 @@ static TallyLayout layout(const b200_tally_plan& p, void* base) {
   int64_t off = 0;
   auto take = [&](int64_t bytes) { char* r = b ? b + off : nullptr; off += (bytes + 255) & ~(int64_t)255; return r; };
   L.header = (long long*)take(TH_WORDS * 8);
-  L.capA = pow2_at_least((uint64_t)std::max<int64_t>(1024, 2 * std::min(p.rows_cap, p.bins_cap)));
+  L.capA = pow2_at_least((uint64_t)std::max<int64_t>(2048, 2 * std::min(p.rows_cap, p.bins_cap)));
   L.list_cap = (int64_t)(L.capA / 2);
   L.keysA = (unsigned long long*)take((int64_t)L.capA * 8);
   L.countsA = (uint32_t*)take((int64_t)L.capA * 4);
@@ -140,37 +143,52 @@ struct PeerView {
   uint32_t epoch;
 };
 
+constexpr int COMPACT_PER = 8;                    // slots per thread
+constexpr int COMPACT_CHUNK = 256 * COMPACT_PER;  // slots per block (the table holds a multiple: capacity >= 2048... see layout)
+
 template <bool MULTI>
 __global__ void __launch_bounds__(256)
 tally_compact_kernel(TallyDev t, unsigned long long* __restrict__ ukeys, uint32_t* __restrict__ ucnt,
                      int64_t out_cap, const __grid_constant__ PeerView P) {
+  __shared__ BinEntry stage[COMPACT_CHUNK];
+  __shared__ int n_s;
+  __shared__ long long base_s;
   const uint64_t cap = t.mask + 1;
-  const int lane = threadIdx.x & 31;
-  BinEntry* list = MULTI ? P.list[P.rank] : nullptr;
-  for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); base < cap;
-       base += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t i = base + lane;
-    unsigned long long key = TALLY_EMPTY;
-    uint32_t c = 0;
-    if (i < cap) {
-      key = __ldcg(t.keys + i);
-      if (key != TALLY_EMPTY) {
-        c = __ldcg(t.counts + i);
-        t.keys[i] = TALLY_EMPTY;
-        t.counts[i] = 0;
-      }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, key != TALLY_EMPTY);
-    if (m == 0) continue;
-    long long pos0 = 0;
-    if (lane == 0) pos0 = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(t.header + TH_LISTPOS),
-                                                (unsigned long long)__popc(m));
-    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-    if (key != TALLY_EMPTY) {
-      const long long p = pos0 + __popc(m & ((1u << lane) - 1u));
+  const uint64_t base = (uint64_t)blockIdx.x * COMPACT_CHUNK;
+  if (threadIdx.x == 0) n_s = 0;
+  __syncthreads();
+  // all of a thread's slots (keys and counts) are requested before the first is looked at:
+  // one round trip to memory per block, not one per occupied slot
+  unsigned long long key[COMPACT_PER];
+  uint32_t cnt[COMPACT_PER];
+#pragma unroll
+  for (int u = 0; u < COMPACT_PER; ++u) {
+    const uint64_t i = base + (uint64_t)u * 256 + threadIdx.x;
+    key[u] = i < cap ? __ldcg(t.keys + i) : TALLY_EMPTY;
+    cnt[u] = i < cap ? __ldcg(t.counts + i) : 0u;
+  }
+#pragma unroll
+  for (int u = 0; u < COMPACT_PER; ++u) {
+    if (key[u] == TALLY_EMPTY) continue;
+    const uint64_t i = base + (uint64_t)u * 256 + threadIdx.x;
+    t.keys[i] = TALLY_EMPTY;
+    t.counts[i] = 0;
+    const int p = atomicAdd(&n_s, 1);
+    stage[p].key = key[u];
+    stage[p].count = cnt[u];
+  }
+  __syncthreads();
+  const int n = n_s;
+  if (n > 0) {   // one reservation per block
+    if (threadIdx.x == 0)
+      base_s = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(t.header + TH_LISTPOS), (unsigned long long)n);
+    __syncthreads();
+    BinEntry* list = MULTI ? P.list[P.rank] : nullptr;
+    for (int j = threadIdx.x; j < n; j += 256) {
+      const long long p = base_s + j;
       if (p < out_cap) {
-        if (MULTI) { list[p].key = key; list[p].count = c; }
-        else { ukeys[p] = key; ucnt[p] = c; }
+        if (MULTI) list[p] = stage[j];
+        else { ukeys[p] = stage[j].key; ucnt[p] = (uint32_t)stage[j].count; }
       } else {
         t.header[TH_OVERFLOW] = 1;
       }
@@ -189,12 +207,11 @@ tally_compact_kernel(TallyDev t, unsigned long long* __restrict__ ukeys, uint32_
   __threadfence();
   if (threadIdx.x == 0) {
     const long long total = *reinterpret_cast<volatile long long*>(t.header + TH_LISTPOS);
-    const long long n = total < out_cap ? total : out_cap;
+    const long long m = total < out_cap ? total : out_cap;
     t.header[TH_LISTPOS] = 0;
     t.header[TH_TICKET] = 0;
-    t.header[TH_USED] = 0;
-    if (MULTI) *P.list_count[P.rank] = n;
-    else t.header[TH_NBINS] = n;
+    if (MULTI) *P.list_count[P.rank] = m;
+    else t.header[TH_NBINS] = m;
   }
   if (MULTI) {
     __syncthreads();
@@ -255,7 +272,10 @@ tally_merge_kernel(const __grid_constant__ PeerView P, long long* __restrict__ h
   long long total = off_s[P.world];
   if (total > concat_cap) total = concat_cap;   // cannot happen: every list is <= list_cap
   if (blockIdx.x == 0 && threadIdx.x == 0) header[TH_CONCAT] = total;
-  const uint64_t mask = capB - 1;
+  // the part of table B this merge uses: a power of two >= 2 * total (every slot of B is empty between merges)
+  uint64_t used = 1024;
+  while (used < 2 * (uint64_t)total && used < capB) used <<= 1;
+  const uint64_t mask = used - 1;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
        p += (long long)gridDim.x * blockDim.x) {
     int r = 0;
@@ -264,19 +284,15 @@ tally_merge_kernel(const __grid_constant__ PeerView P, long long* __restrict__ h
     ld_sys_entry(P.list[r] + (p - off_s[r]), key, cnt);
     concat[p].key = key;
     concat[p].count = cnt;
-    // insert into B
+    // insert into B (sized for a load of at most 1/2: a long walk means it is overfull)
     uint32_t found = 0xffffffffu;
-    if (*reinterpret_cast<volatile long long*>(header + TH_OVERFLOW) == 0) {
+    {
       uint64_t slot = tally_mix(key) & mask;
-      for (uint64_t probe = 0; probe <= mask; ++probe) {
+      for (int probe = 0; probe < TALLY_MAX_PROBE; ++probe) {
         unsigned long long cur = __ldcg(keysB + slot);
         if (cur == TALLY_EMPTY) {
           cur = atomicCAS(keysB + slot, TALLY_EMPTY, key);
-          if (cur == TALLY_EMPTY) {
-            const unsigned long long used = atomicAdd(reinterpret_cast<unsigned long long*>(header + TH_USEDB), 1ull) + 1;
-            if (used > capB / 2) { header[TH_OVERFLOW] = 1; break; }
-            cur = key;
-          }
+          if (cur == TALLY_EMPTY) cur = key;
         }
         if (cur == key) {
           atomicAdd(countsB + slot, cnt);
@@ -286,6 +302,7 @@ tally_merge_kernel(const __grid_constant__ PeerView P, long long* __restrict__ h
         }
         slot = (slot + 1) & mask;
       }
+      if (found == 0xffffffffu) header[TH_OVERFLOW] = 1;
     }
     slot_of[p] = found;
   }
@@ -325,7 +342,7 @@ tally_unique_kernel(long long* __restrict__ header, const BinEntry* __restrict__
   const long long total = header[TH_CONCAT];
   const long long base = (long long)blockIdx.x * MERGE_CHUNK;
   if (base >= total) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { header[TH_NBINS] = 0; header[TH_USEDB] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) header[TH_NBINS] = 0;
     return;
   }
   long long before = 0;
@@ -382,41 +399,20 @@ tally_unique_kernel(long long* __restrict__ header, const BinEntry* __restrict__
   if (base + MERGE_CHUNK >= total && threadIdx.x == 0) {
     const long long n = base_s + blocktotal;
     header[TH_NBINS] = n < bins_cap ? n : bins_cap;
-    header[TH_USEDB] = 0;
-  }
-}
-
-// ----------------------------------------------------------------- wealth
-// data_T of every (grid point, tuple): the epilogue of the LOG count kernels
-// (lev_sweep.cu), expression for expression - so a bin's wealth is bit-identical to
-// the data_T entry of every investor in it.
-template <int K>
-__global__ void __launch_bounds__(256)
-tally_wealth_kernel(const long long* __restrict__ header, const unsigned long long* __restrict__ ukeys, int32_t H,
-                    int32_t G, const __grid_constant__ LogTable lf, double logV0, float* __restrict__ wbuf,
-                    int64_t ldw) {
-  const long long B = header[TH_NBINS];
-  const long long total = B * G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i / B);
-    const long long b = i - (long long)g * B;
-    int n1, n2, n3;
-    tally_unkey(__ldg(ukeys + b), n1, n2, n3);
-    int n[4];
-    n[1] = n1; n[2] = K >= 3 ? n2 : 0; n[3] = K >= 4 ? n3 : 0;
-    n[0] = H - n[1] - n[2] - n[3];
-    double lw = logV0;
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-      if (n[k] > 0) lw += (double)n[k] * lf.lm[k][g];
-    wbuf[(int64_t)g * ldw + b] = (float)exp(lw);
   }
 }
 
 // ----------------------------------------------------------------- select
+// One thread-block CLUSTER per grid point: the bins are split over the cluster's
+// CTAs (each keeps its slice's wealth and counts in shared memory after the first
+// pass), the radix histograms live in the leader CTA's shared memory and are fed by
+// all CTAs through distributed-shared-memory atomics, the fp64 partial sums of the
+// CTAs are handed to the leader and added in rank order.  Three cluster barriers per
+// pass; no global-memory traffic after the first pass, no atomics on fp64.
 constexpr int SEL_THREADS = 1024;
 constexpr int SL1 = 2048, SL2 = 2048, SL3 = 1024;   // bins per level (11 + 11 + 10 key bits)
+constexpr int SEL_MAX_CLUSTER = 8;
+constexpr int SEL_CACHE = 16384;                    // bins per CTA kept in shared memory (128 KB)
 
 // In-place inclusive scans: group `grp` (256 threads) scans histogram `grp` of
 // `bins` counters (bins % 256 == 0); groups >= n_hist idle.  Two barriers.
@@ -455,167 +451,358 @@ __device__ __forceinline__ void find_rank(const uint32_t* pre, int bins, long lo
   rem = rank - (lo > 0 ? (long long)pre[lo - 1] : 0);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS)
-tally_select_kernel(long long* __restrict__ header, const uint32_t* __restrict__ ucnt, const float* __restrict__ wbuf,
-                    int64_t ldw, int64_t n_total, int64_t top, double* __restrict__ stats) {
-  __shared__ uint32_t hist[4 * SL2];       // level 1: [0, 2048); level 2: 4 x 2048; level 3: 4 x 1024
-  __shared__ uint32_t warp_tot[32];
-  __shared__ double red_d[32];
-  __shared__ long long red_i[32];
-  __shared__ int bin_s[4];
-  __shared__ long long rem_s[4];
-  __shared__ double sh_d[8];
-  __shared__ long long sh_i[8];
+// hist[bin] += c for the lanes with `valid`; every lane of the warp must call.
+// A wealth row spans few binades (a level-1 histogram sees most of its elements in
+// a handful of bins) and at high leverage most wealths underflow to the SAME value
+// (then every level sees one bin): 32 lanes hitting one shared-memory word would
+// serialise (measured: 50k cycles per pass).  Two rounds of "the lanes that share
+// the first pending lane's bin add up (REDUX) and issue ONE atomic" take out the
+// two most likely crowds; what is left goes as plain atomics.
+__device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t bin, uint32_t c, bool valid) {
+  constexpr unsigned FULL = 0xffffffffu;
+  unsigned rem = __ballot_sync(FULL, valid);
+  if (rem == 0u) return;
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    if (rem == 0u) return;
+    const int ld = __ffs(rem) - 1;
+    const uint32_t lb = __shfl_sync(FULL, bin, ld);
+    const bool same = valid && bin == lb;
+    const unsigned grp = __ballot_sync(FULL, same);
+    const uint32_t sum = __reduce_add_sync(FULL, same ? c : 0u);
+    if (lane == (unsigned)ld && sum != 0u) atomicAdd(hist + lb, sum);
+    rem &= ~grp;
+    valid = valid && !same;
+  }
+  if (valid && c != 0u) atomicAdd(hist + bin, c);
+}
 
-  const int g = blockIdx.x;
+// The pass's histograms were filled in every CTA's OWN shared memory; the other CTAs now
+// add their non-empty bins to the leader's copy (few remote atomics instead of one per element).
+__device__ __forceinline__ void push_hist(uint32_t* mine, uint32_t* leaders, int bins, int rank) {
+  __syncthreads();
+  if (rank != 0)
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+      const uint32_t v = mine[i];
+      if (v != 0u) atomicAdd(leaders + i, v);
+    }
+}
+
+struct SelShared {
+  uint32_t hist[4 * SL2];                 // leader: level 1 [0,2048); level 2: 4 x 2048; level 3: 4 x 1024
+  double part_d[SEL_MAX_CLUSTER][6];      // leader: the CTAs' partial sums of the running pass
+  long long part_i[SEL_MAX_CLUSTER][2];
+  double res_d[4];                        // leader: mean_all, mean_top, mean_adj
+  long long res_i[16];                    // leader: nonfinite[3], has_nan[3], ties_top, ties_adj, bins[4], rems[4]
+  uint32_t warp_tot[32];
+  double red_d[32];
+  double red_d2[32 * 6];
+  long long red_i[32];
+};
+
+// sum of N doubles over the block in one go (thread 0 holds the result): one barrier pair for all of them
+template <int N>
+__device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch /* >= 32 * N */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < N; ++q) v[q] = warp_sum(v[q]);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int q = 0; q < N; ++q) scratch[q * 32 + wid] = v[q];
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      const double x = lane < (int)(blockDim.x >> 5) ? scratch[q * 32 + lane] : 0.0;
+      v[q] = warp_sum(x);
+    }
+  }
+}
+
+template <int NK>
+__global__ void __launch_bounds__(SEL_THREADS)
+tally_select_kernel(long long* __restrict__ header, const unsigned long long* __restrict__ ukeys,
+                    const uint32_t* __restrict__ ucnt, float* __restrict__ wbuf, int64_t ldw, int32_t H,
+                    const __grid_constant__ LogTable lf, double logV0, int64_t n_total, int64_t top,
+                    double* __restrict__ stats) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+  __shared__ SelShared sh;
+  extern __shared__ __align__(16) uint8_t dyn[];
+  float* cw = reinterpret_cast<float*>(dyn);                   // [SEL_CACHE] wealth of the slice's bins beyond the registers
+  uint32_t* cc = reinterpret_cast<uint32_t*>(dyn) + SEL_CACHE; // [SEL_CACHE] their counts
+  SelShared* L = cluster.map_shared_rank(&sh, 0);              // the leader's copy
+
+  const int g = blockIdx.x / C;
   const long long B = header[TH_NBINS];
-  const float* __restrict__ w = wbuf + (int64_t)g * ldw;
   const long long n = n_total, K = top;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   double* s = stats + (int64_t)g * 12;
-  if (header[TH_TIMEOUT] != 0 || header[TH_OVERFLOW] != 0) {
-    if (threadIdx.x < 12) s[threadIdx.x] = qnan;
+  if (header[TH_TIMEOUT] != 0 || header[TH_OVERFLOW] != 0) {   // uniform over the cluster: nobody touches remote memory
+    if (r == 0 && threadIdx.x < 12) s[threadIdx.x] = qnan;
     return;
   }
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = threadIdx.x & 31;
+#ifdef B200_TALLY_DEBUG
+  int stamp_i = 0;
+#define STAMP() do { if (r == 0 && tid == 0 && (g == 0 || g == (int)(gridDim.x / C) - 1)) { header[TH_DEBUG + (g == 0 ? 0 : 24) + stamp_i++] = clock64(); } } while (0)
+#else
+#define STAMP() do {} while (0)
+#endif
+  STAMP();
+  // this CTA's slice of the bins
+  const long long per = (((B + C - 1) / C) + 3) & ~3LL;
+  const long long lo = min(B, (long long)r * per), hi = min(B, lo + per);
+  const int m = (int)(hi - lo);
+  float* __restrict__ w = wbuf + (int64_t)g * ldw + lo;      // spill space for bins beyond the shared-memory cache
+  const uint32_t* __restrict__ cnt = ucnt + lo;
+  constexpr int REGS = 0;
+  // The wealth of this grid point at every bin of the slice: the epilogue of the LOG count kernels
+  // (lev_sweep.cu) expression for expression, so a bin's wealth is bit-identical to the data_T entry of
+  // every investor in it.  It is formed once, here, and kept in shared memory for the four passes.
+  {
+    double lm[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) lm[k] = lf.lm[k][g];
+    for (int i = tid; i < m; i += SEL_THREADS) {
+      int n1, n2, n3;
+      tally_unkey(__ldg(ukeys + lo + i), n1, n2, n3);
+      int nk[4];
+      nk[1] = n1; nk[2] = NK >= 3 ? n2 : 0; nk[3] = NK >= 4 ? n3 : 0;
+      nk[0] = H - nk[1] - nk[2] - nk[3];
+      double lw = logV0;
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+        if (nk[k] > 0) lw += (double)nk[k] * lm[k];
+      const float x = (float)exp(lw);
+      if (i < SEL_CACHE) { cw[i] = x; cc[i] = __ldg(cnt + i); }
+      else w[i] = x;
+    }
+  }
+  __syncthreads();
+  auto far_w = [&](int i) { return i < REGS + SEL_CACHE ? cw[i - REGS] : w[i]; };
+  auto far_c = [&](int i) { return i < REGS + SEL_CACHE ? cc[i - REGS] : cnt[i]; };
+  // f(x, c, in): called by every lane of a warp together (`in` = this lane holds an element)
+  auto sweep = [&](auto&& f) {
+    for (int base = (tid & ~31); base < m; base += SEL_THREADS) {
+      const int i = base + lane;
+      const bool in = i < m;
+      f(in ? far_w(i) : 0.f, in ? far_c(i) : 0u, in);
+    }
+  };
 
   // ---- pass 0: sum, count, level-1 histogram
-  for (int i = tid; i < SL1; i += SEL_THREADS) hist[i] = 0;
-  __syncthreads();
-  double a0 = 0;
-  long long c0 = 0;
-  for (long long b = tid; b < B; b += SEL_THREADS) {
-    const float x = w[b];
-    const uint32_t c = ucnt[b];
-    a0 += (double)c * (double)x;
-    c0 += c;
-    atomicAdd(&hist[float_key(x) >> 21], c);
+  for (int i = tid; i < SL1; i += SEL_THREADS) sh.hist[i] = 0;
+  cluster.sync();
+  STAMP();
+  {
+    double a0 = 0;
+    long long c0 = 0;
+    sweep([&](float x, uint32_t c, bool in) {
+      a0 += (double)c * (double)x;      // c = 0 where the lane holds nothing
+      c0 += c;
+      hist_add(sh.hist, float_key(x) >> 21, c, in);
+    });
+    STAMP();
+    push_hist(sh.hist, L->hist, SL1, r);
+    a0 = block_sum(a0, sh.red_d);
+    c0 = block_sum(c0, sh.red_i);
+    if (tid == 0) { L->part_d[r][0] = a0; L->part_i[r][0] = c0; }
   }
-  const double sum_all = block_sum(a0, red_d);
-  const long long cnt_all = block_sum(c0, red_i);
-  __syncthreads();
-  if (tid == 0) {
-    if (cnt_all != n) header[TH_MISMATCH] = 1;
-    // key bins that can only hold non-finite values: 3 = -inf, 2044 = +inf, 2047 = NaN
-    const long long ninf = hist[3], pinf = hist[2044], nan = hist[2047];
-    const long long hi = pinf + nan;
-    sh_i[0] = (hi + ninf) > 0; sh_i[1] = hi > 0 || ninf > n - K; sh_i[2] = hi > K || ninf > 0;   // nonfinite all/top/adj
-    sh_i[3] = nan > 0; sh_i[4] = nan > 0; sh_i[5] = nan > K;                                       // has_nan
-    sh_d[0] = sum_all / (double)n;   // mean_all
+  cluster.sync();
+  STAMP();
+  if (r == 0) {
+    if (tid == 0) {
+      double sum_all = 0;
+      long long cnt_all = 0;
+      for (int q = 0; q < C; ++q) { sum_all += sh.part_d[q][0]; cnt_all += sh.part_i[q][0]; }
+      if (cnt_all != n) header[TH_MISMATCH] = 1;
+      // key bins that can only hold non-finite values: 3 = -inf, 2044 = +inf, 2047 = NaN
+      const long long ninf = sh.hist[3], pinf = sh.hist[2044], nan = sh.hist[2047];
+      const long long hi_ = pinf + nan;
+      sh.res_i[0] = (hi_ + ninf) > 0; sh.res_i[1] = hi_ > 0 || ninf > n - K; sh.res_i[2] = hi_ > K || ninf > 0;
+      sh.res_i[3] = nan > 0; sh.res_i[4] = nan > 0; sh.res_i[5] = nan > K;
+      sh.res_d[0] = sum_all / (double)n;
+    }
+    scan_hists(sh.hist, SL1, 1, sh.warp_tot);   // (thread 0's reads above precede the scan's first barrier)
+    if (tid < 4) {
+      const long long ranks[4] = {(n - 1) / 2, n - K, n - K + (K - 1) / 2, (n - K - 1) / 2};
+      int bin; long long rem;
+      find_rank(sh.hist, SL1, ranks[tid], bin, rem);
+      sh.res_i[8 + tid] = bin; sh.res_i[12 + tid] = rem;
+    }
   }
-  scan_hists(hist, SL1, 1, warp_tot);
-  const long long ranks[4] = {(n - 1) / 2, n - K, n - K + (K - 1) / 2, (n - K - 1) / 2};
-  if (tid < 4) find_rank(hist, SL1, ranks[tid], bin_s[tid], rem_s[tid]);
-  __syncthreads();
+  cluster.sync();
   uint32_t pre[4];
   long long rk[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { pre[j] = (uint32_t)bin_s[j]; rk[j] = rem_s[j]; }
-  __syncthreads();
+  for (int j = 0; j < 4; ++j) { pre[j] = (uint32_t)L->res_i[8 + j]; rk[j] = L->res_i[12 + j]; }
+  const double mean_a = L->res_d[0];
+  STAMP();
+  // targets that share a prefix share a histogram: only the first of them (its representative) is counted,
+  // the leader copies it for the others before it scans
+  int rep[4];
+  auto find_reps = [&]() {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      rep[j] = j;
+#pragma unroll
+      for (int q = 3; q >= 0; --q)
+        if (q < j && pre[q] == pre[j]) rep[j] = q;
+    }
+  };
+  auto copy_reps = [&](int bins) {     // leader only
+    for (int j = 1; j < 4; ++j)
+      if (rep[j] != j)
+        for (int i = tid; i < bins; i += SEL_THREADS) sh.hist[j * bins + i] = sh.hist[rep[j] * bins + i];
+    __syncthreads();
+  };
+  find_reps();
 
   // ---- pass 1: level-2 histograms of the elements in the targets' level-1 bins
-  for (int i = tid; i < 4 * SL2; i += SEL_THREADS) hist[i] = 0;
-  __syncthreads();
-  for (long long b = tid; b < B; b += SEL_THREADS) {
-    const uint32_t k = float_key(w[b]);
-    const uint32_t b1 = k >> 21;
-    if ((b1 == pre[0]) | (b1 == pre[1]) | (b1 == pre[2]) | (b1 == pre[3])) {
-      const uint32_t c = ucnt[b];
-      const uint32_t b2 = (k >> 10) & (SL2 - 1);
+  // (the leader next writes its results after the barrier that ends the pass: every read above is done by then)
+  for (int j = 0; j < 4; ++j)
+    if (rep[j] == j)
+      for (int i = tid; i < SL2; i += SEL_THREADS) sh.hist[j * SL2 + i] = 0;
+  cluster.sync();
+  {
+    sweep([&](float x, uint32_t c, bool in) {
+      const uint32_t k = float_key(x);
+      const uint32_t b1 = k >> 21, b2 = (k >> 10) & (SL2 - 1);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (b1 == pre[j]) atomicAdd(&hist[j * SL2 + b2], c);
-    }
-  }
-  __syncthreads();
-  scan_hists(hist, SL2, 4, warp_tot);
-  if (tid < 4) find_rank(hist + tid * SL2, SL2, rk[tid], bin_s[tid], rem_s[tid]);
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { pre[j] = (pre[j] << 11) | (uint32_t)bin_s[j]; rk[j] = rem_s[j]; }   // 22-bit prefixes
-  __syncthreads();
-
-  // ---- pass 2: level-3 histograms + the sums on either side of thr's 22-bit prefix
-  for (int i = tid; i < 4 * SL3; i += SEL_THREADS) hist[i] = 0;
-  __syncthreads();
-  const uint32_t thr22 = pre[1];
-  double s_gt = 0, s_lt = 0;
-  long long c_gt = 0;
-  for (long long b = tid; b < B; b += SEL_THREADS) {
-    const float x = w[b];
-    const uint32_t c = ucnt[b];
-    const uint32_t k = float_key(x);
-    const uint32_t hi = k >> 10;
-    if (hi > thr22) { s_gt += (double)c * (double)x; c_gt += c; }
-    else if (hi < thr22) s_lt += (double)c * (double)x;
+        if (rep[j] == j) hist_add(sh.hist + j * SL2, b2, c, in && b1 == pre[j]);     // (rep is warp-uniform)
+    });
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (hi == pre[j]) atomicAdd(&hist[j * SL3 + (k & (SL3 - 1))], c);
+      if (rep[j] == j) push_hist(sh.hist + j * SL2, L->hist + j * SL2, SL2, r);
   }
-  const double coarse_gt = block_sum(s_gt, red_d);
-  const double coarse_lt = block_sum(s_lt, red_d);
-  const long long cnt_gt = block_sum(c_gt, red_i);
-  __syncthreads();   // histograms complete
-  // the elements that share thr's 22-bit prefix: bin `lo` of thr's level-3 histogram
-  // holds the copies of the ONE fp32 value with key (prefix22 << 10 | lo) - needed
-  // before the scan overwrites the counts; thr's own bin is not known yet, so the
-  // per-bin products are re-walked after the scan through prefix differences.
-  scan_hists(hist, SL3, 4, warp_tot);
-  if (tid < 4) find_rank(hist + tid * SL3, SL3, rk[tid], bin_s[tid], rem_s[tid]);
-  __syncthreads();
-  uint32_t key_j[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) key_j[j] = (pre[j] << 10) | (uint32_t)bin_s[j];
-  const uint32_t thr_key = key_j[1];
-  const uint32_t thr_lo = thr_key & (SL3 - 1), base = thr_key & ~(uint32_t)(SL3 - 1);
-  double f_gt = 0, f_lt = 0;
-  long long fc_gt = 0, fc_lt = 0, fc_all = 0;
-  {
-    const uint32_t* h3 = hist + 1 * SL3;
-    for (uint32_t lo = tid; lo < (uint32_t)SL3; lo += SEL_THREADS) {
-      const long long c = (long long)h3[lo] - (lo > 0 ? (long long)h3[lo - 1] : 0);
-      fc_all += c;
-      if (c == 0 || lo == thr_lo) continue;   // an empty bin must not contribute 0 * inf
-      const double v = (double)c * (double)key_float(base | lo);
-      if (lo > thr_lo) { f_gt += v; fc_gt += c; } else { f_lt += v; fc_lt += c; }
+  STAMP();
+  cluster.sync();
+  STAMP();
+  if (r == 0) {
+    copy_reps(SL2);
+    scan_hists(sh.hist, SL2, 4, sh.warp_tot);
+    if (tid < 4) {
+      int bin; long long rem;
+      find_rank(sh.hist + tid * SL2, SL2, rk[tid], bin, rem);
+      sh.res_i[8 + tid] = bin; sh.res_i[12 + tid] = rem;
     }
   }
-  f_gt = block_sum(f_gt, red_d); f_lt = block_sum(f_lt, red_d);
-  fc_gt = block_sum(fc_gt, red_i); fc_lt = block_sum(fc_lt, red_i); fc_all = block_sum(fc_all, red_i);
-  __syncthreads();
-  if (tid == 0) {
-    const double thr = (double)key_float(thr_key);
-    const long long n_gt = cnt_gt + fc_gt, n_lt = (n - cnt_gt - fc_all) + fc_lt;
-    const double sum_gt = fc_gt ? coarse_gt + f_gt : coarse_gt, sum_lt = fc_lt ? coarse_lt + f_lt : coarse_lt;
-    const long long n_eq = n - n_gt - n_lt;
-    const long long tt = K - n_gt;   // ties that belong to the top group
-    sh_i[6] = tt;
-    sh_i[7] = n_eq - tt;
-    sh_d[1] = (sum_gt + (tt > 0 ? (double)tt * thr : 0.0)) / (double)K;                   // mean_top
-    sh_d[2] = (sum_lt + (n_eq - tt > 0 ? (double)(n_eq - tt) * thr : 0.0)) / (double)(n - K);   // mean_adj
+  cluster.sync();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { pre[j] = (pre[j] << 11) | (uint32_t)L->res_i[8 + j]; rk[j] = L->res_i[12 + j]; }   // 22 bits
+  find_reps();
+  STAMP();
+
+  // ---- pass 2: level-3 histograms + the sums on either side of thr's 22-bit prefix
+  for (int j = 0; j < 4; ++j)
+    if (rep[j] == j)
+      for (int i = tid; i < SL3; i += SEL_THREADS) sh.hist[j * SL3 + i] = 0;
+  cluster.sync();
+  const uint32_t thr22 = pre[1];
+  {
+    double v[2] = {0, 0};
+    long long c_gt = 0;
+    sweep([&](float x, uint32_t c, bool in) {
+      const uint32_t k = float_key(x);
+      const uint32_t hi22 = k >> 10;
+      const double cx = (double)c * (double)x;
+      if (in && hi22 > thr22) { v[0] += cx; c_gt += c; }
+      else if (in && hi22 < thr22) v[1] += cx;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (rep[j] == j) hist_add(sh.hist + j * SL3, k & (SL3 - 1), c, in && hi22 == pre[j]);
+    });
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (rep[j] == j) push_hist(sh.hist + j * SL3, L->hist + j * SL3, SL3, r);
+    STAMP();
+    block_sum_n<2>(v, sh.red_d2);
+    c_gt = block_sum(c_gt, sh.red_i);
+    if (tid == 0) { L->part_d[r][0] = v[0]; L->part_d[r][1] = v[1]; L->part_i[r][0] = c_gt; }
   }
-  __syncthreads();
-  const double mean_a = sh_d[0], mean_t = sh_d[1], mean_j = sh_d[2];
+  cluster.sync();
+  if (r == 0) {
+    // thr's level-3 histogram: bin `b3` holds the copies of the ONE fp32 value with key (prefix22 << 10 | b3).
+    // The scan overwrites the counts with prefixes; the per-bin counts are read back as differences.
+    copy_reps(SL3);
+    scan_hists(sh.hist, SL3, 4, sh.warp_tot);
+    if (tid < 4) {
+      int bin; long long rem;
+      find_rank(sh.hist + tid * SL3, SL3, rk[tid], bin, rem);
+      sh.res_i[8 + tid] = bin; sh.res_i[12 + tid] = rem;
+    }
+    __syncthreads();
+    const uint32_t thr_key = (pre[1] << 10) | (uint32_t)sh.res_i[8 + 1];
+    const uint32_t thr_lo = thr_key & (SL3 - 1), base = thr_key & ~(uint32_t)(SL3 - 1);
+    double f[5] = {0, 0, 0, 0, 0};      // sum > thr, sum < thr, count > thr, count < thr, count of the whole histogram
+    const uint32_t* h3 = sh.hist + 1 * SL3;
+    for (uint32_t b3 = tid; b3 < (uint32_t)SL3; b3 += SEL_THREADS) {
+      const long long c = (long long)h3[b3] - (b3 > 0 ? (long long)h3[b3 - 1] : 0);
+      f[4] += (double)c;                  // counts < 2^32: exact in fp64
+      if (c == 0 || b3 == thr_lo) continue;   // an empty bin must not contribute 0 * inf
+      const double val = (double)c * (double)key_float(base | b3);
+      if (b3 > thr_lo) { f[0] += val; f[2] += (double)c; } else { f[1] += val; f[3] += (double)c; }
+    }
+    block_sum_n<5>(f, sh.red_d2);
+    if (tid == 0) {
+      const long long fc_gt = (long long)f[2], fc_lt = (long long)f[3], fc_all = (long long)f[4];
+      double coarse_gt = 0, coarse_lt = 0;
+      long long cnt_gt = 0;
+      for (int q = 0; q < C; ++q) { coarse_gt += sh.part_d[q][0]; coarse_lt += sh.part_d[q][1]; cnt_gt += sh.part_i[q][0]; }
+      const double thr = (double)key_float(thr_key);
+      const long long n_gt = cnt_gt + fc_gt, n_lt = (n - cnt_gt - fc_all) + fc_lt;
+      const double sum_gt = fc_gt ? coarse_gt + f[0] : coarse_gt, sum_lt = fc_lt ? coarse_lt + f[1] : coarse_lt;
+      const long long n_eq = n - n_gt - n_lt;
+      const long long tt = K - n_gt;   // ties that belong to the top group
+      sh.res_i[6] = tt;
+      sh.res_i[7] = n_eq - tt;
+      sh.res_d[1] = (sum_gt + (tt > 0 ? (double)tt * thr : 0.0)) / (double)K;                       // mean_top
+      sh.res_d[2] = (sum_lt + (n_eq - tt > 0 ? (double)(n_eq - tt) * thr : 0.0)) / (double)(n - K);   // mean_adj
+    }
+  }
+  cluster.sync();
+  uint32_t key_j[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) key_j[j] = (pre[j] << 10) | (uint32_t)L->res_i[8 + j];
+  const uint32_t thr_key = key_j[1];
+  const double mean_t = L->res_d[1], mean_j = L->res_d[2];
+  STAMP();
 
   // ---- pass 3: deviations
-  double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0;
-  for (long long b = tid; b < B; b += SEL_THREADS) {
-    const float x = w[b];
-    const double c = (double)ucnt[b];
+  double d[6] = {0, 0, 0, 0, 0, 0};
+  sweep([&](float x, uint32_t ci, bool in) {
+    const double c = (double)ci;          // 0 where the lane holds nothing
     const uint32_t k = float_key(x);
     const double xd = (double)x;
     const double da = xd - mean_a;
-    d4 += c * fabs(da);
-    d5 += c * (da * da);
-    if (k < thr_key) { const double d = xd - mean_j; d2 += c * fabs(d); d3 += c * (d * d); }
-    else if (k > thr_key) { const double d = xd - mean_t; d0 += c * fabs(d); d1 += c * (d * d); }
+    d[4] += c * fabs(da);
+    d[5] += c * (da * da);
+    if (k < thr_key) { const double e = xd - mean_j; d[2] += c * fabs(e); d[3] += c * (e * e); }
+    else if (k > thr_key) { const double e = xd - mean_t; d[0] += c * fabs(e); d[1] += c * (e * e); }
+  });
+  STAMP();
+  block_sum_n<6>(d, sh.red_d2);
+  STAMP();
+  if (tid == 0) {                        // (the leader consumed pass 2's partials before the last barrier)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) L->part_d[r][q] = d[q];
   }
-  d0 = block_sum(d0, red_d); d1 = block_sum(d1, red_d); d2 = block_sum(d2, red_d);
-  d3 = block_sum(d3, red_d); d4 = block_sum(d4, red_d); d5 = block_sum(d5, red_d);
-  if (tid == 0) {
+  cluster.sync();
+  STAMP();
+  if (r == 0 && tid == 0) {
+    double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0;
+    for (int q = 0; q < C; ++q) {
+      d0 += sh.part_d[q][0]; d1 += sh.part_d[q][1]; d2 += sh.part_d[q][2];
+      d3 += sh.part_d[q][3]; d4 += sh.part_d[q][4]; d5 += sh.part_d[q][5];
+    }
     const double thr = (double)key_float(thr_key);
     const double dt = thr - mean_t, da = thr - mean_j;
-    const double tt = (double)sh_i[6], ta = (double)sh_i[7];
+    const double tt = (double)sh.res_i[6], ta = (double)sh.res_i[7];
     // a tie share of zero must not contribute inf * 0
     const double abs_top = d0 + (tt > 0 ? tt * fabs(dt) : 0.0);
     const double sq_top = d1 + (tt > 0 ? tt * dt * dt : 0.0);
@@ -630,10 +817,50 @@ tally_select_kernel(long long* __restrict__ header, const uint32_t* __restrict__
     const long long size[3] = {n, K, n - K};
     const double single[3] = {qnan, thr, (double)key_float(key_j[3])};
     for (int j = 0; j < 3; ++j) {
-      if (sh_i[j]) { s[0 + j] = size[j] == 1 ? single[j] : qnan; s[3 + j] = qnan; s[6 + j] = qnan; }
-      if (sh_i[3 + j]) s[9 + j] = qnan;
+      if (sh.res_i[j]) { s[0 + j] = size[j] == 1 ? single[j] : qnan; s[3 + j] = qnan; s[6 + j] = qnan; }
+      if (sh.res_i[3 + j]) s[9 + j] = qnan;
     }
   }
+}
+
+static int select_cluster_size() {
+  static int v = [] {
+    const char* e = getenv("B200_SELECT_CLUSTER");
+    int x = e ? atoi(e) : 6;
+    return x < 1 ? 1 : x > SEL_MAX_CLUSTER ? SEL_MAX_CLUSTER : x;
+  }();
+  return v;
+}
+
+template <int K>
+static int launch_select_k(int n_grid, long long* header, const unsigned long long* ukeys, const uint32_t* ucnt,
+                           float* wbuf, int64_t ldw, int32_t H, const LogTable& lf, double logV0, int64_t n_total,
+                           int64_t top, double* stats, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  const size_t dyn = (size_t)SEL_CACHE * 8;
+  if (dev < 64 && !attr_set[dev]) {
+    B200_CUDA(cudaFuncSetAttribute(tally_select_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set[dev] = true;
+  }
+  const int C = select_cluster_size();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(n_grid * C));
+  cfg.blockDim = dim3(SEL_THREADS);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, tally_select_kernel<K>, header, ukeys, ucnt, wbuf, ldw, H, lf, logV0,
+                                       n_total, top, stats),
+                    "tally_select launch");
 }
 
 static int grid_for(int64_t work, int threads, int per_sm) {
@@ -679,7 +906,7 @@ extern "C" int b200_tally_finalize(const b200_tally_plan* plan, void* workspace,
   TallyDev t{L.keysA, L.countsA, L.header, L.capA - 1};
   PeerView P;
   memset(&P, 0, sizeof(P));
-  const int cgrid = grid_for((int64_t)L.capA, 256, 8);
+  const int cgrid = (int)((L.capA + COMPACT_CHUNK - 1) / COMPACT_CHUNK);
   if (plan->world == 1) {
     tally_compact_kernel<false><<<cgrid, 256, 0, st>>>(t, L.ukeys, L.ucnt, std::min(plan->bins_cap, L.list_cap), P);
     return check_cuda(cudaGetLastError(), "tally_compact launch");
@@ -735,13 +962,9 @@ extern "C" int b200_tally_stats(const b200_tally_plan* plan, void* workspace, co
       lf.lm[k][g] = v;
     }
   const double logV0 = log((double)desc->value_0);
-  const int wgrid = sm_count() * 8;
   switch (desc->n_outcomes) {
-    case 2: tally_wealth_kernel<2><<<wgrid, 256, 0, st>>>(L.header, L.ukeys, desc->horizon, desc->n_grid, lf, logV0, L.wbuf, L.ldw); break;
-    case 3: tally_wealth_kernel<3><<<wgrid, 256, 0, st>>>(L.header, L.ukeys, desc->horizon, desc->n_grid, lf, logV0, L.wbuf, L.ldw); break;
-    default: tally_wealth_kernel<4><<<wgrid, 256, 0, st>>>(L.header, L.ukeys, desc->horizon, desc->n_grid, lf, logV0, L.wbuf, L.ldw); break;
+    case 2: return launch_select_k<2>(desc->n_grid, L.header, L.ukeys, L.ucnt, L.wbuf, L.ldw, desc->horizon, lf, logV0, n_total, top, stats, st);
+    case 3: return launch_select_k<3>(desc->n_grid, L.header, L.ukeys, L.ucnt, L.wbuf, L.ldw, desc->horizon, lf, logV0, n_total, top, stats, st);
+    default: return launch_select_k<4>(desc->n_grid, L.header, L.ukeys, L.ucnt, L.wbuf, L.ldw, desc->horizon, lf, logV0, n_total, top, stats, st);
   }
-  B200_CUDA(cudaGetLastError());
-  tally_select_kernel<<<desc->n_grid, SEL_THREADS, 0, st>>>(L.header, L.ucnt, L.wbuf, L.ldw, n_total, top, stats);
-  return check_cuda(cudaGetLastError(), "tally_select launch");
 }

@@ -13,10 +13,10 @@
 //
 // Table: open addressing, linear probing, 8-byte keys (~0 = empty) and 4-byte
 // counts in separate arrays; key = n_1 | n_2 << 21 | n_3 << 42 (n_0 follows from
-// the horizon; H < 2^21).  The table never holds more than capacity / 2 distinct
-// tuples: the insertion that would exceed that raises the overflow word and every
-// later insertion returns at once (the statistics of that sweep are then flagged
-// invalid - never silently wrong, never a long probe walk).
+// the horizon; H < 2^21).  The table is sized for at most capacity / 2 distinct
+// tuples; an overfull table shows as a long probe walk or as more tuples than the
+// bin list holds, and either raises the overflow word (the statistics of that sweep
+// are then flagged invalid - never silently wrong, never an unbounded walk).
 #pragma once
 #include "common.cuh"
 
@@ -33,12 +33,11 @@ enum {
   TH_BAD = 2,       // outcomes outside {0..K-1} met by an ingest kernel
   TH_TIMEOUT = 3,   // a peer's bins never arrived
   TH_MISMATCH = 4,  // sum of the bin counts != n_total at the last statistics call
-  TH_USED = 8,      // distinct tuples in the table being filled
   TH_TICKET = 9,    // last-block-done ticket of the compaction kernel
   TH_LISTPOS = 10,  // append cursor of the compaction kernel
   TH_CONCAT = 11,   // bins of all ranks before the merge removes duplicates
-  TH_USEDB = 12,    // distinct tuples in the merge table
-  TH_WORDS = 16
+  TH_DEBUG = 16,    // 48 words of per-phase clock stamps (B200_TALLY_DEBUG builds)
+  TH_WORDS = 64
 };
 
 struct TallyDev {
@@ -67,21 +66,19 @@ __host__ __device__ __forceinline__ void tally_unkey(uint64_t key, int& n1, int&
 
 // counts[slot(key)] += add.  A slot only ever goes empty -> key inside one tally,
 // so the plain (L2) read of the slot is safe: a stale "empty" just takes the CAS.
+// No global fill counter (one address hit by every new tuple serialises the kernel's
+// tail): a table kept at most half full by its sizing has clusters of a few slots,
+// so a probe walk of TALLY_MAX_PROBE slots means it is overfull - that raises the
+// overflow word (P(false alarm) ~ 0.82^256 per new tuple at load 1/2), and the
+// compaction raises it when more tuples come out than the bin list holds.
+constexpr int TALLY_MAX_PROBE = 256;
 __device__ __forceinline__ void tally_insert(const TallyDev& t, uint64_t key, uint32_t add) {
-  if (*reinterpret_cast<volatile long long*>(t.header + TH_OVERFLOW) != 0) return;
   uint64_t slot = tally_mix(key) & t.mask;
-  for (uint64_t probe = 0; probe <= t.mask; ++probe) {
+  for (int probe = 0; probe < TALLY_MAX_PROBE; ++probe) {
     unsigned long long cur = __ldcg(t.keys + slot);
     if (cur == TALLY_EMPTY) {
       cur = atomicCAS(t.keys + slot, TALLY_EMPTY, (unsigned long long)key);
-      if (cur == TALLY_EMPTY) {
-        const unsigned long long used = atomicAdd(reinterpret_cast<unsigned long long*>(t.header + TH_USED), 1ull) + 1;
-        if (used > (t.mask + 1) / 2) {   // the tuple that would overfill the table: taken back
-          t.header[TH_OVERFLOW] = 1;
-          return;
-        }
-        cur = key;
-      }
+      if (cur == TALLY_EMPTY) cur = key;
     }
     if (cur == key) { atomicAdd(t.counts + slot, add); return; }
     slot = (slot + 1) & t.mask;

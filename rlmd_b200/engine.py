@@ -628,7 +628,9 @@ class FinalSweepPipeline:
             raise ValueError("statistics must be 'tally' (discrete gambles) or 'rows'")
         with torch.cuda.device(self.dev):
             # the statistics' short, dependent kernels go first whenever they are ready
-            self.sweep_stream, self.stats_stream = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+            self.sweep_stream = torch.cuda.Stream()
+            # depth 1 is strictly sequential: one stream (a cross-stream event wait per kernel costs microseconds)
+            self.stats_stream = torch.cuda.Stream(priority=-1) if self.depth > 1 else self.sweep_stream
         self.data_T = [None] * self.depth
         self.ws = [None] * self.depth
         self.tallies = [None] * self.depth

@@ -124,27 +124,40 @@ def _as_float(x) -> float:
     return float(x.item()) if isinstance(x, T.Tensor) else float(x)
 
 
-_codes_cache = {"key": None, "codes": None}
+_codes_cache = {"on": False, "src": None, "version": None, "k": None, "codes": None}
 
 
 def _codes(outcomes, n_outcomes: int, device=None) -> T.Tensor:
-    """uint8 codes [N,H] on the GPU for the CHAIN kernels.  The scripts hand the SAME outcome tensor to
-    several sweeps in a row (lev/coin_flip.py:163-227): the last conversion is kept (keyed on the source's
-    storage, shape, dtype and in-place version counter)."""
+    """uint8 codes [N,H] on the GPU for the CHAIN kernels (engine.encode_codes: the ingest kernel; host
+    arrays travel in row chunks)."""
     if isinstance(outcomes, T.Tensor) and outcomes.is_cuda and outcomes.dtype == T.uint8:
         return outcomes  # already in the engine format
-    t = T.as_tensor(outcomes)
-    key = (t.data_ptr(), tuple(t.shape), t.dtype, t._version, str(t.device), int(n_outcomes))
-    if _codes_cache["key"] == key:
-        return _codes_cache["codes"]
-    codes = engine.encode_codes(t, device=device, n_outcomes=n_outcomes)
-    _codes_cache["key"], _codes_cache["codes"] = key, codes
+    c = _codes_cache
+    if c["on"] and isinstance(outcomes, T.Tensor) and c["src"] is outcomes and c["version"] == outcomes._version \
+            and c["k"] == int(n_outcomes):
+        return c["codes"]
+    codes = engine.encode_codes(outcomes, device=device, n_outcomes=n_outcomes)
+    if c["on"] and isinstance(outcomes, T.Tensor):
+        c["src"], c["version"], c["k"], c["codes"] = outcomes, outcomes._version, int(n_outcomes), codes
     return codes
 
 
-def drop_codes_cache() -> None:
-    """Frees the kept conversion (10 GB for 1e6 x 1e4 outcomes)."""
-    _codes_cache["key"] = _codes_cache["codes"] = None
+class reuse_codes:
+    """
+    `with lev_exp.reuse_codes():` - inside the block the conversion of an outcome tensor to the engine
+    format is kept and reused while the SAME tensor object (same in-place version) is handed to the next
+    sweep, as the scripts do (lev/coin_flip.py:163-227 passes one `outcomes` to five functions).  Off by
+    default: a caller who rewrites the tensor's memory behind torch's back (a NumPy alias) would otherwise
+    sweep stale codes.  Leaving the block frees the kept copy (10 GB for 1e6 x 1e4 outcomes).
+    """
+
+    def __enter__(self):
+        _codes_cache["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _codes_cache.update(on=False, src=None, version=None, k=None, codes=None)
+        return False
 
 
 def _returns(outcomes, device=None) -> T.Tensor:

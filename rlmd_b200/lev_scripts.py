@@ -47,6 +47,17 @@ GBM = dict(investors=1e6, horizon=5e2, value_0=1e2,
            l1_l=[-1.0, 0.2], l1_h=[1.0, 2.0], l1_i=[0.2, 0.2])
 
 
+def _reusing_codes(fn):
+    """An injected reference-format `outcomes` tensor is converted to the engine format once per script."""
+    import functools
+
+    @functools.wraps(fn)
+    def run(*a, **kw):
+        with lev_exp.reuse_codes():
+            return fn(*a, **kw)
+    return run
+
+
 def _cfg(defaults: dict, overrides: dict) -> dict:
     unknown = set(overrides) - set(defaults)
     if unknown:
@@ -80,6 +91,7 @@ def _report(t0: float) -> None:
     print("TOTAL TIME: {:1.0f}s = {:1.1f}m = {:1.2f}h".format(total, total / 60, total / 3600))
 
 
+@_reusing_codes
 def coin_flip(path_results: Optional[str] = "./results/multiverse/", *, seed: int = 420, outcomes=None,
               galaxy: bool = True, **overrides) -> Dict[str, np.ndarray]:
     """lev/coin_flip.py:154-241 -> coin_inv1_val[_T], coin_inv2_val, coin_inv3_val, coin_inv4_lev."""
@@ -106,6 +118,7 @@ def coin_flip(path_results: Optional[str] = "./results/multiverse/", *, seed: in
     return out
 
 
+@_reusing_codes
 def dice_roll(path_results: Optional[str] = "./results/multiverse/", *, seed: int = 420, outcomes=None,
               **overrides) -> Dict[str, np.ndarray]:
     """lev/dice_roll.py:143-218 -> dice_inv1_val[_T], dice_inv2_val, dice_inv3_val."""
@@ -131,6 +144,7 @@ def dice_roll(path_results: Optional[str] = "./results/multiverse/", *, seed: in
     return out
 
 
+@_reusing_codes
 def dice_roll_sh(path_results: Optional[str] = "./results/multiverse/", *, seed: int = 420, outcomes=None,
                  **overrides) -> Dict[str, np.ndarray]:
     """lev/dice_roll_sh.py:122-161 -> dice_sh_inv1_val[_T]."""
