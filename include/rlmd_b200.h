@@ -235,9 +235,13 @@ typedef struct b200_tally_peers {
 } b200_tally_peers;
 
 /* table -> distinct tuples (clears the table for the next sweep); peers NULL
- * when plan->world == 1. */
+ * when plan->world == 1.  phase = -1 runs everything; with world > 1, phase 0 =
+ * publish (compaction into this rank's exchange buffer + its flag at every peer)
+ * and phase 1 = merge (waits for the world's flags) can be issued separately - a
+ * test that plays all ranks on ONE GPU publishes every rank before any merge, so
+ * that no kernel ever waits for a kernel queued behind it. */
 int b200_tally_finalize(const b200_tally_plan* plan, void* workspace,
-                        const b200_tally_peers* peers, void* stream);
+                        const b200_tally_peers* peers, int32_t phase, void* stream);
 
 /* The reference's 12 statistics (b200_rowstats order) of every grid point from the
  * finalized bins: desc supplies n_grid (<= grid_cap), n_outcomes, horizon, value_0;

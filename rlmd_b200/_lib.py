@@ -231,7 +231,7 @@ _SIGNATURES = {
     "b200_tally_reset": (C.c_int, [C.POINTER(TallyPlan), _vp, _vp]),
     "b200_lev_tally": (C.c_int, [C.POINTER(LevDesc), _vp, C.POINTER(TallyPlan), _vp, _vp, _vp]),
     "b200_lev_ingest": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _i32, _vp, _i64, _vp, C.POINTER(TallyPlan), _vp, _vp]),
-    "b200_tally_finalize": (C.c_int, [C.POINTER(TallyPlan), _vp, C.POINTER(TallyPeers), _vp]),
+    "b200_tally_finalize": (C.c_int, [C.POINTER(TallyPlan), _vp, C.POINTER(TallyPeers), _i32, _vp]),
     "b200_tally_stats": (C.c_int, [C.POINTER(TallyPlan), _vp, C.POINTER(LevDesc), C.POINTER(C.c_float), _i64, _i64,
                                    _vp, _vp]),
     "b200_rowstats_workspace_bytes": (_i64, [_i64]),

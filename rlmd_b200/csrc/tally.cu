@@ -898,9 +898,10 @@ extern "C" int b200_tally_reset(const b200_tally_plan* plan, void* workspace, vo
 }
 
 extern "C" int b200_tally_finalize(const b200_tally_plan* plan, void* workspace, const b200_tally_peers* peers,
-                                   void* stream) {
+                                   int32_t phase, void* stream) {
   if (int rc = plan_ok(plan)) return rc;
   B200_REQUIRE(workspace != nullptr, "tally_finalize: workspace is NULL");
+  B200_REQUIRE(phase >= -1 && phase <= 1, "tally_finalize: phase must be -1, 0 or 1");
   cudaStream_t st = (cudaStream_t)stream;
   const TallyLayout L = layout(*plan, workspace);
   TallyDev t{L.keysA, L.countsA, L.header, L.capA - 1};
@@ -908,6 +909,7 @@ extern "C" int b200_tally_finalize(const b200_tally_plan* plan, void* workspace,
   memset(&P, 0, sizeof(P));
   const int cgrid = (int)((L.capA + COMPACT_CHUNK - 1) / COMPACT_CHUNK);
   if (plan->world == 1) {
+    if (phase == 1) return 0;
     tally_compact_kernel<false><<<cgrid, 256, 0, st>>>(t, L.ukeys, L.ucnt, std::min(plan->bins_cap, L.list_cap), P);
     return check_cuda(cudaGetLastError(), "tally_compact launch");
   }
@@ -925,8 +927,11 @@ extern "C" int b200_tally_finalize(const b200_tally_plan* plan, void* workspace,
     P.list_count[r] = (long long*)lst;
     P.list[r] = (BinEntry*)(lst + 16);
   }
-  tally_compact_kernel<true><<<cgrid, 256, 0, st>>>(t, nullptr, nullptr, L.list_cap, P);
-  B200_CUDA(cudaGetLastError());
+  if (phase != 1) {
+    tally_compact_kernel<true><<<cgrid, 256, 0, st>>>(t, nullptr, nullptr, L.list_cap, P);
+    B200_CUDA(cudaGetLastError());
+  }
+  if (phase == 0) return 0;
   const int64_t cat = (int64_t)plan->world * L.list_cap;
   tally_merge_kernel<<<sm_count() * 2, 256, 0, st>>>(P, L.header, L.concat, L.slot_of, L.keysB, L.countsB, L.posB,
                                                      L.capB, cat);

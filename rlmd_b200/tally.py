@@ -232,7 +232,7 @@ class FinalTally:
     def finalize(self) -> None:
         with torch.cuda.device(self.dev):
             peers = self.exchange.next_peers() if self.exchange is not None else None
-            check(lib.b200_tally_finalize(C.byref(self.plan), ptr(self.ws), C.byref(peers) if peers else None,
+            check(lib.b200_tally_finalize(C.byref(self.plan), ptr(self.ws), C.byref(peers) if peers else None, -1,
                                           stream_ptr()))
         self.rows = 0
 

@@ -96,6 +96,27 @@ def _worker(rank, world, port, out_dir):
         pipe.synchronize()
         for g_, w_ in zip(got, seq):
             assert torch.equal(g_[:, 9:12], w_[:, 9:12]) and torch.allclose(g_, w_, rtol=1e-12, atol=0)
+        # (1b) the tally path on shards: count tuples -> ONE exchange of bin lists -> statistics; device codes,
+        #      host int64 rows (the reference's dtype), an empty shard, and the drop-in function's printed text
+        case = golden_io.lev_case("dice_top5")
+        oc = golden_io.draw_outcomes(case)
+        levt = np.asarray(lev_exp.param_range(*case["grid"]), dtype=np.float32)
+        ft = lev_exp.dice_factor_table(levt, case["up_r"], case["down_r"], case["mid_r"])
+        for k, cut in enumerate((700, 0, case["n"])):
+            mine = oc[:cut] if rank == 0 else oc[cut:]
+            src = engine.encode_codes(mine) if k != 1 else torch.as_tensor(mine.astype(np.int64))
+            st = engine.lev_final_stats(ft, case["v0"], case["top"], src, device="cuda", group=dist.group.WORLD)
+            np.save(os.path.join(out_dir, f"tally{k}_{rank}.npy"), st.cpu().numpy())
+        import contextlib, io
+        lev_exp.set_process_group(dist.group.WORLD)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            off, cnt = sharding.shard_range(case["n"], world, rank)
+            lev_exp.dice_fixed_final_lev(torch.device("cuda", rank), torch.as_tensor(oc[off:off + cnt].astype(np.int64)),
+                                         case["top"], torch.tensor(case["v0"]), case["up_r"], case["down_r"],
+                                         case["mid_r"], *case["grid"])
+        lev_exp.set_process_group(None)
+        open(os.path.join(out_dir, f"text{rank}.txt"), "w").write(buf.getvalue())
         # (2) the dice_smart_lev shim on sharded rows of the reference's fixture
         case = golden_io.lev_case("dice_top5")
         oc = golden_io.draw_outcomes(case)
@@ -158,6 +179,21 @@ def test_two_ranks_equal_one(tmp_path):
             ok = ~np.isnan(wi)
             assert np.array_equal(gi[:, 9:12][ok[:, 9:12]], wi[:, 9:12][ok[:, 9:12]])
             np.testing.assert_allclose(gi[ok], wi[ok], rtol=1e-12)
+    # the tally path: both ranks bit-identical, equal to one GPU, and the printed text is the reference's
+    import json
+    case = golden_io.lev_case("dice_top5")
+    oc = golden_io.draw_outcomes(case)
+    levt = np.asarray(lev_exp.param_range(*case["grid"]), dtype=np.float32)
+    ft = lev_exp.dice_factor_table(levt, case["up_r"], case["down_r"], case["mid_r"])
+    one = engine.lev_final_stats(ft, case["v0"], case["top"], engine.encode_codes(oc)).cpu().numpy()
+    for k in range(3):
+        a, b = np.load(tmp_path / f"tally{k}_0.npy"), np.load(tmp_path / f"tally{k}_1.npy")
+        assert np.array_equal(a, b)
+        assert np.array_equal(a[:, 9:12], one[:, 9:12])
+        np.testing.assert_allclose(a, one, rtol=1e-13)
+    ref_text = json.load(open(os.path.join(golden_io.GOLDEN_DIR, "final_text.json")))["dice_top5"]
+    for r in range(world):
+        assert open(tmp_path / f"text{r}.txt").read().rstrip("\n") == ref_text
     levg = np.asarray(lev_exp.param_range(-1.0, 1.0, 0.2), dtype=np.float32)
     full = engine.lev_sweep("gbm", levg, 100.0, n_investors=60_000, horizon=500, seed=7, log_mean=0.05 - 0.1,
                             sigma=0.2 ** 0.5, mode="log", want_log_w=True)

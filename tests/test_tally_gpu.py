@@ -264,3 +264,68 @@ def test_fixed_final_prints_the_reference_text(name, where):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert a == b, (a, b)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_merge_of_rank_tallies_on_one_gpu(world):
+    """
+    The cross-GPU merge (publish -> wait -> merge in rank order, first occurrence wins) played
+    on ONE GPU: every rank has its own workspace and exchange buffer in this process, all
+    ranks publish (phase 0) before any rank merges (phase 1) - so no kernel waits for a kernel
+    queued behind it.  Every rank must end with the identical bin list (bit-identical
+    statistics) and with the statistics of the undivided population.
+    """
+    import ctypes as C
+
+    from rlmd_b200 import _lib, engine, tally
+    from rlmd_b200._lib import check, lib, ptr, stream_ptr
+
+    case = golden_io.lev_case("dice_top5")
+    oc = golden_io.draw_outcomes(case)
+    lev, f = factors_of(case)
+    n, h = oc.shape
+    codes = engine.encode_codes(oc)
+    want = engine.lev_final_stats(f, case["v0"], case["top"], codes).cpu().numpy()
+    # uneven shards, one of them empty when there are enough ranks
+    cuts = np.linspace(0, n, world + 1).astype(int)
+    cuts[1:-1] += np.arange(1, world) * 7 % 50
+    if world >= 3:
+        cuts[2] = cuts[1]
+    ranks = []
+    for r in range(world):
+        t = tally.FinalTally.__new__(tally.FinalTally)
+        t.dev, t.group, t._staging, t.rows, t.horizon = T.device("cuda", 0), None, None, 0, None
+        t.plan = _lib.TallyPlan()
+        t.plan.rows_cap, t.plan.bins_cap, t.plan.grid_cap, t.plan.world = n, n, 64, world
+        t.ws = T.empty((lib.b200_tally_workspace_bytes(C.byref(t.plan)) // 8,), dtype=T.int64, device="cuda")
+        t.exchange = None
+        t.ex_buf = T.zeros((lib.b200_tally_exchange_bytes(C.byref(t.plan)) // 8 + 1,), dtype=T.int64, device="cuda")
+        check(lib.b200_tally_reset(C.byref(t.plan), ptr(t.ws), stream_ptr()))
+        ranks.append(t)
+    for epoch in (1, 2, 3):      # successive sweeps alternate between the two published lists
+        sl = slice(None) if epoch != 2 else slice(0, h - 3)      # another horizon in between
+        ref = want if epoch != 2 else engine.lev_final_stats(f, case["v0"], case["top"],
+                                                             engine.encode_codes(oc[:, sl])).cpu().numpy()
+        hh = oc[:, sl].shape[1]
+        peers = []
+        for r, t in enumerate(ranks):
+            t.rows = 0
+            if cuts[r + 1] > cuts[r]:
+                t.add(engine.encode_codes(oc[cuts[r]:cuts[r + 1], sl]), 3)
+            p = _lib.TallyPeers()
+            p.world, p.rank, p.epoch = world, r, epoch
+            for q in range(world):
+                p.exchange[q] = ranks[q].ex_buf.data_ptr()
+            peers.append(p)
+        for r, t in enumerate(ranks):
+            check(lib.b200_tally_finalize(C.byref(t.plan), ptr(t.ws), C.byref(peers[r]), 0, stream_ptr()))
+        for r, t in enumerate(ranks):
+            check(lib.b200_tally_finalize(C.byref(t.plan), ptr(t.ws), C.byref(peers[r]), 1, stream_ptr()))
+        got = [t.stats(f, case["v0"], hh, n_total=n, top=case["top"]).cpu().numpy() for t in ranks]
+        for r, t in enumerate(ranks):
+            i = t.info()
+            assert not (i["overflow"] or i["timed_out"] or i["count_mismatch"] or i["bad_outcomes"]), (r, i)
+            assert np.array_equal(got[r], got[0]), f"rank {r} differs from rank 0"
+        assert_same_stats(got[0], ref, rtol=1e-13)
+    distinct = len({tuple(c) for c in lo.counts_discrete(oc, 3)})
+    assert ranks[0].info()["bins"] == distinct
