@@ -15,9 +15,11 @@ Restated (reference file:line):
 Parity pin: tests/golden/env_*.npz hold trajectories of the UNMODIFIED reference
 classes driven with injected random draws (tests/golden/gen_golden_more.py);
 tests/test_oracle_env.py checks this file against them to 1e-15 relative (exact
-for everything but the exp/log in the reward).  `Dice_SH_INSURED.step` cannot run
-under numpy 2.x (inhomogeneous np.array): that one class is
-"parity unpinned" - restated from :160-235 only.
+for everything but the exp/log in the reward).  `Dice_SH_INSURED.step` builds its
+`risk` vector from scalars mixed with 1-element arrays (:178-179, :228-231), which
+numpy 2.x refuses; its fixture (env_dicesh_I.npz) comes from the same unmodified class
+with the module's `np.array` reading such elements as scalars, as the reference's own
+numpy 1.22 pin does (tests/golden/gen_golden_more.py:_Numpy122) - so it is pinned too.
 
 Returns are INJECTED (`r`): the reference draws from the unseeded global
 np.random state, which is not reproduced.

@@ -34,9 +34,28 @@ class _Feeder:
         return np.array(v, dtype=np.float64)
 
 
-def gen_env():
+class _Numpy122:
+    """`np` as the reference module sees it, with numpy 1.22's reading of a ragged list handed to
+    np.array: an element that is a 1-element array counts as its scalar (numpy >= 1.24 raises
+    "inhomogeneous shape").  Generator-side only; the reference source is untouched."""
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    @staticmethod
+    def array(obj, *a, **k):
+        if isinstance(obj, list) and any(isinstance(e, np.ndarray) and e.size == 1 and e.ndim > 0 for e in obj):
+            obj = [e.reshape(()).item() if isinstance(e, np.ndarray) and e.size == 1 else e for e in obj]
+        return np.array(obj, *a, **k)
+
+
+def gen_env(only=None):
     for name, module, cls, family, investor, n_g in golden_io.ENV_CASES:
+        if only is not None and name not in only:
+            continue
         mod = ref_shim.load(module)
+        if cls == "Dice_SH_INSURED":
+            mod.np = _Numpy122()
         with ref_shim.reference_cwd():
             env = getattr(mod, cls)() if family == "dice_sh" else getattr(mod, cls)(n_g)
         a_dim = env.action_space.shape[0]
@@ -61,6 +80,8 @@ def gen_env():
                     env.reset()
         finally:
             np.random.choice, np.random.normal = old_choice, old_normal
+            if cls == "Dice_SH_INSURED":
+                mod.np = np
         out = os.path.join(HERE, f"env_{name}.npz")
         np.savez_compressed(out, actions=actions, returns=rets, state0=state0, states=np.array(states),
                             rewards=np.array(rewards), dones=np.array(dones), risks=np.array(risks),

@@ -112,6 +112,10 @@ ENV_CASES = [
     ("dicesh_A", "envs.dice_roll_sh_envs", "Dice_SH_InvA", "dice_sh", "A", 1),
     ("dicesh_B", "envs.dice_roll_sh_envs", "Dice_SH_InvB", "dice_sh", "B", 1),
     ("dicesh_C", "envs.dice_roll_sh_envs", "Dice_SH_InvC", "dice_sh", "C", 1),
+    # Dice_SH_INSURED.step builds `risk` from scalars mixed with 1-element arrays (envs/dice_roll_sh_envs.py:
+    # 178-179, 228-231): numpy 1.22 (the reference's pin) takes such elements as scalars, numpy 2 refuses.  The
+    # generator hands the reference module a numpy proxy whose `array` does what 1.22 did (gen_golden_more.py).
+    ("dicesh_I", "envs.dice_roll_sh_envs", "Dice_SH_INSURED", "dice_sh", "I", 1),
 ]
 ENV_STEPS = 600
 
