@@ -151,6 +151,10 @@ class Collector:
         """
         if batch is not None:
             batch = torch.as_tensor(batch, device=self.device).to(torch.int64).reshape(k, self.batch_size).contiguous()
+        elif self.steps * self.n_envs < self.batch_size:
+            # fewer stored transitions than a mini-batch of distinct slots: the reference's randperm()[:B] then
+            # indexes out of range (tools/replay_torch.py:383)
+            raise IndexError(f"{self.steps * self.n_envs} transitions stored, mini-batch size {self.batch_size}")
         with torch.cuda.device(self.device):
             out = self._alloc_batch(k)
         self._sample_into(out, k, batch)
@@ -164,6 +168,11 @@ class Collector:
         read in place at every replay (write the policy's output into it).  Returns
         a callable; each call replays the graph and returns the static output dict
         (keys: states, actions, rewards, next_states, dones, eff, idx).
+        NOTE: capturing performs ONE real `step(action)` + sample as its warm-up (CUDA
+        needs the kernels loaded before a capture): a transition is appended, the envs
+        advance one step and both Philox counters move on - `self.steps` counts it.
+        Until `batch_size` transitions are stored the drawn slots are -1 and the
+        sampled rows are zero with eff = 0 (check `out["idx"]`).
         """
         dev = self.device
         with torch.cuda.device(dev):

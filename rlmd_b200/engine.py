@@ -425,13 +425,18 @@ def lev_series(
             tc = t1 - t0
             dump = chunk[: g * tc * n].view(g * tc, n)
             check(lib.b200_lev_chunk(C.byref(d), ptr(outcomes), fptr, t0, t1, ptr(state), ptr(dump), stream_ptr()))
-            if n > 0:
+            if n > 0 or group is not None:      # a rank with an empty shard still takes part in the exchange
                 st = rowstats(dump, top, n_total=n_total, group=group, workspace=ws[: g * tc]).view(g, tc, 12)
                 lo = max(t0, 1)
                 if t1 > lo:
                     data[:, :12, lo - 1:t1 - 1] = st[:, lo - t0:, :].permute(0, 2, 1).to(torch.float32)
             last = dump.view(g, tc, n)[:, tc - 1, :]
         data_T = state if kind == "discrete" else last.clone()
+        if group is not None:
+            from . import sharding
+
+            torch.cuda.current_stream().synchronize()
+            sharding.raise_if_peers_timed_out(group, dev)
     return data, data_T
 
 
@@ -501,7 +506,10 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
             oc = PackedCodes(b[:rows], h) if packed else b[:rows, :h]
             lev_sweep(kind, f, value_0, outcomes=oc, mode=mode, variant=variant, out_data_T=data_T[:, r0:r0 + rows])
             done[i & 1].record(comp)
-        stats = rowstats(data_T, top, n_total=n_total, group=group).cpu().numpy() if n > 0 else np.zeros((g, 12))
+        if n > 0 or group is not None:      # a rank with an empty shard still takes part in the exchange
+            stats = rowstats(data_T, top, n_total=n_total, group=group).cpu().numpy()
+        else:
+            stats = np.zeros((g, 12))
         if group is not None:
             from . import sharding
 
@@ -741,10 +749,18 @@ def rowstats(values: torch.Tensor, top: int, *, n_total: Optional[int] = None, g
         if how == "p2p" and not sharding.peer_memory_available(group, dev):
             how = "nccl"     # no peer mapping between these GPUs: the all-reduce path (both run on the GPUs)
         if how == "p2p":
+            # ONE workspace / flag block per (group, device): its calls must run one after the other on the GPU
+            # (epochs and the alternating workspaces assume it).  Callers on different streams - two pipelines, a
+            # pipeline and a direct call - are chained here with an event: call i+1 waits for call i.
             pw = sharding.peer_workspace(rows, group, dev)
+            cur = torch.cuda.current_stream()
+            if pw.last_call is not None:
+                cur.wait_event(pw.last_call)
             ps = pw.peer_set()
             check(lib.b200_rowstats_p2p(ptr(values), rows, n, ld, n_total, int(top), C.byref(ps), ptr(stats),
                                         stream_ptr()))
+            pw.last_call = torch.cuda.Event()
+            pw.last_call.record(cur)
             return stats
         ws = workspace if workspace is not None else rowstats_workspace(rows, dev)
 
@@ -888,11 +904,16 @@ def bigbrain_series(kind: str, outcomes: torch.Tensor, top: int, value_0: float,
                 check(lib.b200_bigbrain_chunk(C.byref(d), ptr(outcomes), fptr(vm), fptr(rl),
                                               l0.ctypes.data_as(C.POINTER(C.c_double)), s, s_end, ptr(state),
                                               ptr(dump), stream_ptr()))
-                if steps > 0 and n > 0:
+                if steps > 0 and (n > 0 or group is not None):
                     st = rowstats(dump, top, n_total=n_total, group=group, workspace=ws[: pc * steps * 2])
                     st = st.view(pc, steps, 2, 12).to(torch.float32)
                     data[p0:p0 + pc, 12:24, s_lo - 1:s_end - 1] = st[:, :, 0, :].permute(0, 2, 1)
                     data[p0:p0 + pc, 0:12, s_lo - 1:s_end - 1] = st[:, :, 1, :].permute(0, 2, 1)
                 s = s_end
             wealth[p0:p0 + pc] = state[0]
+        if group is not None:
+            from . import sharding
+
+            torch.cuda.current_stream().synchronize()
+            sharding.raise_if_peers_timed_out(group, dev)
     return data.view(R, S, 26, max(h - 1, 0)), wealth.view(R, S, n)

@@ -55,7 +55,9 @@ class PeerWorkspace:
     NVLink), for b200_rowstats_p2p: two workspaces per rank (successive calls
     alternate: a peer may still be summing the previous call's histograms) and one
     flag block.  Construction and `peer_set` are collective: every rank must make
-    the same calls in the same order.
+    the same calls in the same order, and the calls of one workspace must execute
+    one after the other on the GPU - engine.rowstats chains them with an event
+    (`last_call`), whatever streams they are issued on.
     """
 
     FLAG_WORDS = 64   # uint32 [8 ranks][4 phases] + error word, in 8-byte slots
@@ -79,6 +81,7 @@ class PeerWorkspace:
         torch.cuda.synchronize(device)
         dist.barrier(group=group)          # every rank's flags are zero before anyone signals
         self.epoch = 0
+        self.last_call = None     # event after the last b200_rowstats_p2p on this workspace (engine.rowstats)
 
     def peer_set(self):
         """The b200_peer_set of the next call (advances the epoch: collective)."""
@@ -94,10 +97,13 @@ class PeerWorkspace:
         ps.sums = self.ptrs[self.rank] + 8 * 2 * self.rows * self.row_words
         return ps
 
-    def timed_out(self) -> bool:
+    def timed_out(self, clear: bool = False) -> bool:
         """True when a resolve kernel gave up waiting for a peer (its statistics are NaN)."""
         flags = self.buf[3 * self.rows * self.row_words:].view(torch.int32)
-        return bool(flags[32].item())
+        hit = bool(flags[32].item())
+        if hit and clear:
+            flags[32] = 0
+        return hit
 
 
 _peer_cache = {}
@@ -117,7 +123,7 @@ def raise_if_peers_timed_out(group, device) -> None:
     device-to-host read; a no-op when the group does not use the peer-memory exchange.
     """
     pw = _peer_cache.get(_key(group, device))
-    if pw is not None and pw.timed_out():
+    if pw is not None and pw.timed_out(clear=True):      # (the error word is cleared: later calls start clean)
         raise RuntimeError("rlmd_b200: a rank did not reach the statistics exchange within 60 s "
                            "(peer-memory flags); the statistics of that call are NaN")
 
