@@ -98,8 +98,16 @@ typedef struct b200_lev_desc {
                               fair die carries 1.25 bits per roll: the packed
                               array is a quarter of the HBM traffic of the LOG
                               sweep (the CHAIN kernels take uint8 codes)      */
-  int32_t reserved;        /* 0 */
+  int32_t flags;           /* B200_LEV_FLAG_*                                    */
 } b200_lev_desc;
+
+/* GBM, LOG mode: data_T = fl32(exp(log wealth at H)) WITHOUT the running-extremes
+ * saturation - the value `value_0 * exp(l x).prod(dim=1)` of gbm_fixed_final_lev
+ * (lev/lev_exp.py:965-967: torch.prod multiplies in blocks, so it leaves the fp32
+ * range only when the FINAL wealth does), whereas the default reproduces the
+ * time-ordered chain of gbm_smart_lev (:1048-1055: inf / 0 for good once the
+ * running wealth left the range). */
+#define B200_LEV_FLAG_FINAL_ONLY 1
 
 /*
  * outcomes : STREAM: uint8 [N,ld] (discrete, codes < K; or packed 2-bit codes,

@@ -37,10 +37,11 @@ class LevDesc(C.Structure):
         ("variant", C.c_int32),
         ("thresholds", C.c_uint32 * MAX_OUTCOMES),
         ("outcome_bits", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 
+LEV_FLAG_FINAL_ONLY = 1
 MAX_PEERS = 8
 
 

@@ -358,7 +358,8 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
 // once it fell below half the smallest denormal it is 0 for good.
 __device__ __forceinline__ void gbm_finish(double S, double Smax, double Smin, int32_t G,
                                            const LevGrid& lv, double logV0, int64_t row, int64_t ldT,
-                                           float* __restrict__ data_T, double* __restrict__ log_w) {
+                                           float* __restrict__ data_T, double* __restrict__ log_w,
+                                           bool saturate = true) {
   const double LOG_FLT_MAX = 88.72283905206835;    // ln(3.4028234664e38)
   const double LOG_FLT_ZERO = -103.97207708399179; // ln(2^-150)
   for (int g = 0; g < G; ++g) {
@@ -369,8 +370,8 @@ __device__ __forceinline__ void gbm_finish(double S, double Smax, double Smin, i
     if (log_w != nullptr) log_w[(int64_t)g * ldT + row] = lw;
     if (data_T != nullptr) {
       float v;
-      if (hi > LOG_FLT_MAX) v = __int_as_float(0x7f800000);
-      else if (lo < LOG_FLT_ZERO) v = 0.0f;
+      if (saturate && hi > LOG_FLT_MAX) v = __int_as_float(0x7f800000);
+      else if (saturate && lo < LOG_FLT_ZERO) v = 0.0f;
       else v = (float)exp(lw);
       data_T[(int64_t)g * ldT + row] = v;
     }
@@ -398,7 +399,7 @@ template <bool USE_TMA>
 __global__ void __launch_bounds__(TILE_ROWS)
 log_gbm_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ x, int64_t ld,
                       const __grid_constant__ LevGrid lv, int32_t H, int64_t N, int32_t G, double logV0,
-                      float* __restrict__ data_T, double* __restrict__ log_w, int64_t ldT) {
+                      float* __restrict__ data_T, double* __restrict__ log_w, int64_t ldT, bool saturate) {
   extern __shared__ __align__(1024) uint8_t tiles[];
   __shared__ __align__(8) uint64_t full[STAGES];
   constexpr int TILE_STEPS = TILE_BYTES / 4;  // 32 floats per row per tile
@@ -461,7 +462,7 @@ log_gbm_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     }
   }
   const int64_t row = row0 + tid;
-  if (row < N) gbm_finish(acc.S, acc.Smax, acc.Smin, G, lv, logV0, row, ldT, data_T, log_w);
+  if (row < N) gbm_finish(acc.S, acc.Smax, acc.Smin, G, lv, logV0, row, ldT, data_T, log_w, saturate);
 }
 
 // x_t = log_mean + sigma * z_t; four steps per Philox block, two Box-Muller pairs;
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(128)
 log_gbm_philox_kernel(const __grid_constant__ LevGrid lv, const __grid_constant__ PhiloxKeys K,
                       int64_t investor_offset, float log_mean,
                       float sigma, int32_t H, int64_t N, int32_t G, double logV0, float* __restrict__ data_T,
-                      double* __restrict__ log_w, int64_t ldT) {
+                      double* __restrict__ log_w, int64_t ldT, bool saturate) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= N) return;
   const uint64_t id = (uint64_t)(row + investor_offset);
@@ -518,7 +519,7 @@ log_gbm_philox_kernel(const __grid_constant__ LevGrid lv, const __grid_constant_
     for (int t = 0; t < (H & 3); ++t) acc.step(x[t]);
   }
   acc.fold();
-  gbm_finish(acc.S, acc.Smax, acc.Smin, G, lv, logV0, row, ldT, data_T, log_w);
+  gbm_finish(acc.S, acc.Smax, acc.Smin, G, lv, logV0, row, ldT, data_T, log_w, saturate);
 }
 
 __global__ void __launch_bounds__(128)
@@ -759,10 +760,11 @@ static int run_log_gbm(const b200_lev_desc& d, const float* x, const float* lev_
   for (int g = 0; g < B200_MAX_GRID; ++g) lv.lev[g] = g < d.n_grid ? lev_host[g] : 0.f;
   const double logV0 = log((double)d.value_0);
   const int64_t N = d.n_investors;
+  const bool saturate = (d.flags & B200_LEV_FLAG_FINAL_ONLY) == 0;
   if (d.source == B200_SRC_PHILOX) {
     const unsigned blocks = (unsigned)((N + 127) / 128);
     log_gbm_philox_kernel<<<blocks, 128, 0, st>>>(lv, philox_keys(d.seed), d.investor_offset, d.log_mean, d.sigma, d.horizon, N,
-                                                  d.n_grid, logV0, data_T, log_w, out_ld(d));
+                                                  d.n_grid, logV0, data_T, log_w, out_ld(d), saturate);
     return check_cuda(cudaGetLastError(), "log_gbm_philox launch");
   }
   const unsigned blocks = (unsigned)((N + TILE_ROWS - 1) / TILE_ROWS);
@@ -774,10 +776,10 @@ static int run_log_gbm(const b200_lev_desc& d, const float* x, const float* lev_
     auto kern = log_gbm_stream_kernel<true>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * TILE_SMEM));
     kern<<<blocks, TILE_ROWS, STAGES * TILE_SMEM, st>>>(map, x, d.ld_outcomes, lv, d.horizon, N, d.n_grid, logV0,
-                                                        data_T, log_w, out_ld(d));
+                                                        data_T, log_w, out_ld(d), saturate);
   } else {
     log_gbm_stream_kernel<false><<<blocks, TILE_ROWS, TILE_SMEM, st>>>(map, x, d.ld_outcomes, lv, d.horizon, N,
-                                                                       d.n_grid, logV0, data_T, log_w, out_ld(d));
+                                                                       d.n_grid, logV0, data_T, log_w, out_ld(d), saturate);
   }
   return check_cuda(cudaGetLastError(), "log_gbm_stream launch");
 }

@@ -196,6 +196,7 @@ def lev_sweep(
     variant: int = 0,
     out_data_T: Optional[torch.Tensor] = None,
     device=None,
+    final_only: bool = False,
 ) -> dict:
     """
     One launch over the whole leverage grid (b200_lev_sweep).
@@ -205,12 +206,16 @@ def lev_sweep(
               arbitrary (unit inner stride), or PackedCodes (discrete, LOG mode);
               None -> Philox draws on device
     mode      "chain" (exact fp32 product; discrete only) or "log"
+    final_only  GBM: data_T without the running-extremes saturation, i.e. what gbm_fixed_final_lev's
+              torch.prod holds (B200_LEV_FLAG_FINAL_ONLY); the default is gbm_smart_lev's chain
     returns   {"data_T": [G,N] f32, "log_w": [G,N] f64, "counts": [N,K] i32}
     """
     require_cuda()
     f = np.ascontiguousarray(factors, dtype=np.float32)
     d, g, k, n, h, dev = _fill_desc(kind, f, value_0, outcomes, n_investors, horizon, mode, seed, investor_offset,
                                     probs, log_mean, sigma, variant, device)
+    if final_only:
+        d.flags |= _lib.LEV_FLAG_FINAL_ONLY
 
     res = {}
     with torch.cuda.device(dev):
@@ -429,7 +434,7 @@ def lev_series(
                 st = rowstats(dump, top, n_total=n_total, group=group, workspace=ws[: g * tc]).view(g, tc, 12)
                 lo = max(t0, 1)
                 if t1 > lo:
-                    data[:, :12, lo - 1:t1 - 1] = st[:, lo - t0:, :].permute(0, 2, 1).to(torch.float32)
+                    data[:, :12, lo - 1:t1 - 1] = stats_to_reference_dtype(st[:, lo - t0:, :], n_total, top).permute(0, 2, 1)
             last = dump.view(g, tc, n)[:, tc - 1, :]
         data_T = state if kind == "discrete" else last.clone()
         if group is not None:
@@ -454,7 +459,7 @@ def _copy_stream(dev) -> "torch.cuda.Stream":
 
 def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, outcomes_host, *,
                    mode: str = "log", chunk_rows: Optional[int] = None, variant: int = 0, device="cuda",
-                   return_data_T: bool = False, group=None, n_total: Optional[int] = None):
+                   return_data_T: bool = False, group=None, n_total: Optional[int] = None, final_only: bool = False):
     """
     The *_fixed_final_lev hot path for outcomes that live in HOST memory
     (pinned for overlap): investor rows are independent, so the array is walked
@@ -504,7 +509,8 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
                 ready[i & 1].record(copy)
             comp.wait_event(ready[i & 1])
             oc = PackedCodes(b[:rows], h) if packed else b[:rows, :h]
-            lev_sweep(kind, f, value_0, outcomes=oc, mode=mode, variant=variant, out_data_T=data_T[:, r0:r0 + rows])
+            lev_sweep(kind, f, value_0, outcomes=oc, mode=mode, variant=variant, out_data_T=data_T[:, r0:r0 + rows],
+                      final_only=final_only)
             done[i & 1].record(comp)
         if n > 0 or group is not None:      # a rank with an empty shard still takes part in the exchange
             stats = rowstats(data_T, top, n_total=n_total, group=group).cpu().numpy()
@@ -708,6 +714,34 @@ class FinalSweepPipeline:
 
 
 # ----------------------------------------------------------------- rowstats
+_FLT_MAX = 3.4028234663852886e38
+
+
+def stats_to_reference_dtype(stats, n_total: int, top: int):
+    """
+    float64 [..., 12] statistics (torch tensor or NumPy) -> the reference's dtype, float32, with the one
+    place where its fp32 ARITHMETIC shows: `mad = T.mean(T.abs(v - mean))` (lev/lev_exp.py:99, :102, :104)
+    sums |v - mean| in fp32, so a group whose absolute deviations add up beyond FLT_MAX reports inf
+    (seen in the reference harness's GBM sweep at leverage 4) - while std_mean's Welford update and the
+    medians do not overflow.  Everything else is the plain cast.
+    """
+    sizes = (float(n_total), float(top), float(n_total - top))
+    if isinstance(stats, torch.Tensor):
+        out = stats.to(torch.float32)
+        for j, m in enumerate(sizes):
+            col = stats[..., 3 + j]
+            out[..., 3 + j] = torch.where(col * m > _FLT_MAX, torch.full_like(out[..., 3 + j], float("inf")),
+                                          out[..., 3 + j])
+        return out
+    st = np.asarray(stats, dtype=np.float64)
+    with np.errstate(over="ignore"):
+        out = st.astype(np.float32)
+    for j, m in enumerate(sizes):
+        with np.errstate(invalid="ignore", over="ignore"):
+            out[..., 3 + j] = np.where(st[..., 3 + j] * m > _FLT_MAX, np.float32(np.inf), out[..., 3 + j])
+    return out
+
+
 def rowstats_workspace(rows: int, device) -> torch.Tensor:
     nbytes = lib.b200_rowstats_workspace_bytes(rows)
     return torch.empty((rows, nbytes // 8 // max(rows, 1)), dtype=torch.int64, device=device)
@@ -906,7 +940,7 @@ def bigbrain_series(kind: str, outcomes: torch.Tensor, top: int, value_0: float,
                                               ptr(dump), stream_ptr()))
                 if steps > 0 and (n > 0 or group is not None):
                     st = rowstats(dump, top, n_total=n_total, group=group, workspace=ws[: pc * steps * 2])
-                    st = st.view(pc, steps, 2, 12).to(torch.float32)
+                    st = stats_to_reference_dtype(st, n_total, top).view(pc, steps, 2, 12)
                     data[p0:p0 + pc, 12:24, s_lo - 1:s_end - 1] = st[:, :, 0, :].permute(0, 2, 1)
                     data[p0:p0 + pc, 0:12, s_lo - 1:s_end - 1] = st[:, :, 1, :].permute(0, 2, 1)
                 s = s_end

@@ -176,9 +176,10 @@ _FINAL_FMT = """       lev {:1.0f}%:
 def _print_final(lev: np.ndarray, stats: np.ndarray, smart: bool = False) -> None:
     """The reference's per-leverage report (lev/lev_exp.py:106-125).
 
-    The *_smart_lev variants print med_top in the "adj" line (:214-233); kept.
+    coin_smart_lev - and only it - prints med_top in the "adj" line (:227,231; the
+    dice / dice_sh / gbm variants print med_adj, :691-695, :1108-1112, :1324-1328); kept (`smart`).
     """
-    for l, s in zip(lev, stats.astype(_F32)):
+    for l, s in zip(lev, stats):
         mean, mean_top, mean_adj, mad, mad_top, mad_adj, std, std_top, std_adj, med, med_top, med_adj = s
         print(_FINAL_FMT.format(float(l) * 100, mean, med, mad, std, mean_top, med_top, mad_top, std_top,
                                 mean_adj, med_top if smart else med_adj, mad_adj, std_adj))
@@ -204,23 +205,28 @@ def _n_total(n_local: int, device) -> int:
 
 
 def _final_discrete(device, outcomes, table, top, value_0) -> np.ndarray:
-    """Statistics [G,12] of a discrete final-time sweep: the tally path; inputs it cannot hold (more
-    distinct count tuples than its plan, horizon >= 2^21) take the general path (LOG sweep -> data_T
-    -> row statistics)."""
+    """Statistics [G,12] (in the reference's dtype) of a discrete final-time sweep: the tally path; inputs
+    it cannot hold (more distinct count tuples than its plan, horizon >= 2^21) take the general path (LOG
+    sweep -> data_T -> row statistics)."""
     from . import tally as _tally
 
     k = table.shape[1]
-    h = outcomes.shape[1]
+    n, h = outcomes.shape
+    data = outcomes.data if isinstance(outcomes, engine.PackedCodes) else outcomes
+    dev = data.device if isinstance(data, T.Tensor) and data.is_cuda else engine._cuda_device(device)
+    n_total = _n_total(n, dev)
+    stats = None
     if h <= _tally._lib.TALLY_MAX_HORIZON:
         try:
-            return engine.lev_final_stats(table, _as_float(value_0), _as_int(top), outcomes, device=device,
-                                          group=_GROUP).cpu().numpy()
+            stats = engine.lev_final_stats(table, _as_float(value_0), _as_int(top), outcomes, device=dev,
+                                           group=_GROUP, n_total=n_total).cpu().numpy()
         except _tally.TallyOverflow:
-            pass
-    codes = outcomes if isinstance(outcomes, engine.PackedCodes) else _codes(outcomes, k, device)
-    res = engine.lev_sweep("discrete", table, _as_float(value_0), outcomes=codes, mode="log")
-    n_total = _n_total(codes.shape[0], res["data_T"].device)
-    return engine.rowstats(res["data_T"], _as_int(top), n_total=n_total, group=_GROUP).cpu().numpy()
+            stats = None
+    if stats is None:
+        codes = outcomes if isinstance(outcomes, engine.PackedCodes) else _codes(outcomes, k, dev)
+        res = engine.lev_sweep("discrete", table, _as_float(value_0), outcomes=codes, mode="log")
+        stats = engine.rowstats(res["data_T"], _as_int(top), n_total=n_total, group=_GROUP).cpu().numpy()
+    return engine.stats_to_reference_dtype(stats, n_total, _as_int(top))
 
 
 # ----------------------------------------------------- fixed final leverage
@@ -248,18 +254,18 @@ def gbm_fixed_final_lev(device, outcomes, top, value_0, lev_low, lev_high, lev_i
     """lev/lev_exp.py:935-1005 (no sign flip of the grid).  Host outcomes are streamed in row chunks."""
     lev = _grid(lev_low, lev_high, lev_incr)
     t = T.as_tensor(outcomes)
+    dev = t.device if t.is_cuda else engine._cuda_device(device)
+    n_total = _n_total(t.shape[0], dev)
     if not t.is_cuda:
         if t.dtype != T.float32:
             t = t.to(T.float32)
-        n_total = _n_total(t.shape[0], engine._cuda_device(device))
-        stats = engine.lev_final_host("gbm", lev, _as_float(value_0), _as_int(top), t, mode="log",
-                                      device=engine._cuda_device(device), group=_GROUP, n_total=n_total)
+        stats = engine.lev_final_host("gbm", lev, _as_float(value_0), _as_int(top), t, mode="log", final_only=True,
+                                      device=dev, group=_GROUP, n_total=n_total)
     else:
         x = _returns(t, device)
-        res = engine.lev_sweep("gbm", lev, _as_float(value_0), outcomes=x, mode="log")
-        stats = engine.rowstats(res["data_T"], _as_int(top), n_total=_n_total(x.shape[0], x.device),
-                                group=_GROUP).cpu().numpy()
-    _print_final(lev, stats)
+        res = engine.lev_sweep("gbm", lev, _as_float(value_0), outcomes=x, mode="log", final_only=True)
+        stats = engine.rowstats(res["data_T"], _as_int(top), n_total=n_total, group=_GROUP).cpu().numpy()
+    _print_final(lev, engine.stats_to_reference_dtype(stats, n_total, _as_int(top)))
 
 
 # ------------------------------------------------------------ smart leverage
@@ -286,7 +292,7 @@ def dice_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, dow
     lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
     data, data_T = _series("discrete", _codes(outcomes, 3, device), dice_factor_table(lev, up_r, down_r, mid_r), lev, investors,
                            horizon, top, value_0)
-    _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
+    _print_final(lev, data[:, :12, -1].double().cpu().numpy())
     return data, data_T
 
 
@@ -296,7 +302,7 @@ def dice_sh_smart_lev(device, outcomes, investors, horizon, top, value_0, up_r, 
     lev = _grid(lev_low, lev_high, lev_incr, up_r, down_r)
     table = dice_sh_factor_table(lev, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r)
     data, data_T = _series("discrete", _codes(outcomes, 3, device), table, lev, investors, horizon, top, value_0)
-    _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
+    _print_final(lev, data[:, :12, -1].double().cpu().numpy())
     return data, data_T
 
 
@@ -304,7 +310,7 @@ def gbm_smart_lev(device, outcomes, investors, horizon, top, value_0, lev_low, l
     """lev/lev_exp.py:1008-1118."""
     lev = _grid(lev_low, lev_high, lev_incr)
     data, data_T = _series("gbm", _returns(outcomes, device), lev, lev, investors, horizon, top, value_0)
-    _print_final(lev, data[:, :12, -1].double().cpu().numpy(), smart=True)
+    _print_final(lev, data[:, :12, -1].double().cpu().numpy())
     return data, data_T
 
 
