@@ -308,24 +308,28 @@ tally_merge_kernel(const __grid_constant__ PeerView P, long long* __restrict__ h
   }
 }
 
-// first occurrences per block of MERGE_CHUNK positions
+// first occurrences per chunk of MERGE_CHUNK positions (the grid strides over the chunks: the number of
+// bins is only known on the device, and thousands of blocks that find nothing to do cost microseconds)
 __global__ void __launch_bounds__(256)
 tally_mark_kernel(const long long* __restrict__ header, const uint32_t* __restrict__ slot_of,
                   const uint32_t* __restrict__ posB, int32_t* __restrict__ blockcnt) {
   __shared__ long long red[32];
   const long long total = header[TH_CONCAT];
-  const long long base = (long long)blockIdx.x * MERGE_CHUNK;
-  if (base >= total) return;
-  long long c = 0;
-  for (int u = 0; u < MERGE_CHUNK / 256; ++u) {
-    const long long p = base + (long long)threadIdx.x * (MERGE_CHUNK / 256) + u;
-    if (p < total) {
-      const uint32_t s = slot_of[p];
-      c += (s != 0xffffffffu && __ldcg(posB + s) == (uint32_t)p);
+  const long long nchunks = (total + MERGE_CHUNK - 1) / MERGE_CHUNK;
+  for (long long j = blockIdx.x; j < nchunks; j += gridDim.x) {
+    const long long base = j * MERGE_CHUNK;
+    long long c = 0;
+    for (int u = 0; u < MERGE_CHUNK / 256; ++u) {
+      const long long p = base + (long long)threadIdx.x * (MERGE_CHUNK / 256) + u;
+      if (p < total) {
+        const uint32_t s = slot_of[p];
+        c += (s != 0xffffffffu && __ldcg(posB + s) == (uint32_t)p);
+      }
     }
+    c = block_sum(c, red);
+    if (threadIdx.x == 0) blockcnt[j] = (int32_t)c;
+    __syncthreads();
   }
-  c = block_sum(c, red);
-  if (threadIdx.x == 0) blockcnt[blockIdx.x] = (int32_t)c;
 }
 
 // Stable compaction of the first occurrences: the merged list in concatenation order
@@ -340,65 +344,66 @@ tally_unique_kernel(long long* __restrict__ header, const BinEntry* __restrict__
   __shared__ long long warp_tot[8];
   __shared__ long long base_s;
   const long long total = header[TH_CONCAT];
-  const long long base = (long long)blockIdx.x * MERGE_CHUNK;
-  if (base >= total) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) header[TH_NBINS] = 0;
-    return;
-  }
-  long long before = 0;
-  for (int i = threadIdx.x; i < (int)blockIdx.x; i += 256) before += blockcnt[i];
-  before = block_sum(before, red);
-  if (threadIdx.x == 0) base_s = before;
-  constexpr int PER = MERGE_CHUNK / 256;
-  bool rep[PER];
-  uint32_t slot[PER];
-  int mine = 0;
+  const long long nchunks = (total + MERGE_CHUNK - 1) / MERGE_CHUNK;
+  if (total == 0 && blockIdx.x == 0 && threadIdx.x == 0) header[TH_NBINS] = 0;
+  for (long long j = blockIdx.x; j < nchunks; j += gridDim.x) {
+    const long long base = j * MERGE_CHUNK;
+    long long before = 0;
+    for (long long i = threadIdx.x; i < j; i += 256) before += blockcnt[i];
+    before = block_sum(before, red);
+    if (threadIdx.x == 0) base_s = before;
+    constexpr int PER = MERGE_CHUNK / 256;
+    bool rep[PER];
+    uint32_t slot[PER];
+    int mine = 0;
 #pragma unroll
-  for (int u = 0; u < PER; ++u) {
-    const long long p = base + (long long)threadIdx.x * PER + u;
-    rep[u] = false;
-    slot[u] = 0xffffffffu;
-    if (p < total) {
-      slot[u] = slot_of[p];
-      rep[u] = slot[u] != 0xffffffffu && __ldcg(posB + slot[u]) == (uint32_t)p;
+    for (int u = 0; u < PER; ++u) {
+      const long long p = base + (long long)threadIdx.x * PER + u;
+      rep[u] = false;
+      slot[u] = 0xffffffffu;
+      if (p < total) {
+        slot[u] = slot_of[p];
+        rep[u] = slot[u] != 0xffffffffu && __ldcg(posB + slot[u]) == (uint32_t)p;
+      }
+      mine += rep[u];
     }
-    mine += rep[u];
-  }
-  // exclusive scan of `mine` over the block
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  long long incl = mine;
+    // exclusive scan of `mine` over the block
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long incl = mine;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const long long up = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += up;
-  }
-  if (lane == 31) warp_tot[wid] = incl;
-  __syncthreads();
-  long long pre = 0, blocktotal = 0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    if (w < wid) pre += warp_tot[w];
-    blocktotal += warp_tot[w];
-  }
-  long long outp = base_s + pre + incl - mine;
-#pragma unroll
-  for (int u = 0; u < PER; ++u) {
-    if (!rep[u]) continue;
-    const long long p = base + (long long)threadIdx.x * PER + u;
-    if (outp < bins_cap) {
-      ukeys[outp] = concat[p].key;
-      ucnt[outp] = (uint32_t)__ldcg(countsB + slot[u]);
-    } else {
-      header[TH_OVERFLOW] = 1;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
     }
-    keysB[slot[u]] = TALLY_EMPTY;
-    countsB[slot[u]] = 0;
-    posB[slot[u]] = 0xffffffffu;
-    ++outp;
-  }
-  if (base + MERGE_CHUNK >= total && threadIdx.x == 0) {
-    const long long n = base_s + blocktotal;
-    header[TH_NBINS] = n < bins_cap ? n : bins_cap;
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    long long pre = 0, blocktotal = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < wid) pre += warp_tot[w];
+      blocktotal += warp_tot[w];
+    }
+    long long outp = base_s + pre + incl - mine;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      if (!rep[u]) continue;
+      const long long p = base + (long long)threadIdx.x * PER + u;
+      if (outp < bins_cap) {
+        ukeys[outp] = concat[p].key;
+        ucnt[outp] = (uint32_t)__ldcg(countsB + slot[u]);
+      } else {
+        header[TH_OVERFLOW] = 1;
+      }
+      keysB[slot[u]] = TALLY_EMPTY;
+      countsB[slot[u]] = 0;
+      posB[slot[u]] = 0xffffffffu;
+      ++outp;
+    }
+    if (base + MERGE_CHUNK >= total && threadIdx.x == 0) {
+      const long long n = base_s + blocktotal;
+      header[TH_NBINS] = n < bins_cap ? n : bins_cap;
+    }
+    __syncthreads();
   }
 }
 
@@ -411,8 +416,7 @@ tally_unique_kernel(long long* __restrict__ header, const BinEntry* __restrict__
 // pass; no global-memory traffic after the first pass, no atomics on fp64.
 constexpr int SEL_THREADS = 1024;
 constexpr int SL1 = 2048, SL2 = 2048, SL3 = 1024;   // bins per level (11 + 11 + 10 key bits)
-constexpr int SEL_MAX_CLUSTER = 8;
-constexpr int SEL_CACHE = 16384;                    // bins per CTA kept in shared memory (128 KB)
+constexpr int SEL_MAX_CLUSTER = 16;                 // > 8: non-portable cluster sizes (B200 allows 16)
 
 // In-place inclusive scans: group `grp` (256 threads) scans histogram `grp` of
 // `bins` counters (bins % 256 == 0); groups >= n_hist idle.  Two barriers.
@@ -526,7 +530,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
 tally_select_kernel(long long* __restrict__ header, const unsigned long long* __restrict__ ukeys,
                     const uint32_t* __restrict__ ucnt, float* __restrict__ wbuf, int64_t ldw, int32_t H,
                     const __grid_constant__ LogTable lf, double logV0, int64_t n_total, int64_t top,
-                    double* __restrict__ stats) {
+                    double* __restrict__ stats, int32_t SEL_CACHE /* bins per CTA kept in shared memory */) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
@@ -823,13 +827,21 @@ tally_select_kernel(long long* __restrict__ header, const unsigned long long* __
   }
 }
 
-static int select_cluster_size() {
-  static int v = [] {
+// Cluster size and per-CTA shared-memory cache of the select kernel.  Defaults from measurement on
+// B200: B200_SELECT_CLUSTER / B200_SELECT_CACHE override them for experiments.
+static void select_shape(int& cluster, int& cache) {
+  static int c = [] {
     const char* e = getenv("B200_SELECT_CLUSTER");
     int x = e ? atoi(e) : 6;
     return x < 1 ? 1 : x > SEL_MAX_CLUSTER ? SEL_MAX_CLUSTER : x;
   }();
-  return v;
+  static int k = [] {
+    const char* e = getenv("B200_SELECT_CACHE");
+    int x = e ? atoi(e) : 16384;
+    return x < 0 ? 0 : x > 20480 ? 20480 : x;
+  }();
+  cluster = c;
+  cache = k;
 }
 
 template <int K>
@@ -839,12 +851,14 @@ static int launch_select_k(int n_grid, long long* header, const unsigned long lo
   static bool attr_set[64] = {false};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
-  const size_t dyn = (size_t)SEL_CACHE * 8;
+  int C = 1, cache = 0;
+  select_shape(C, cache);
+  const size_t dyn = (size_t)cache * 8;
   if (dev < 64 && !attr_set[dev]) {
     B200_CUDA(cudaFuncSetAttribute(tally_select_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    if (C > 8) B200_CUDA(cudaFuncSetAttribute(tally_select_kernel<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set[dev] = true;
   }
-  const int C = select_cluster_size();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(n_grid * C));
@@ -859,7 +873,7 @@ static int launch_select_k(int n_grid, long long* header, const unsigned long lo
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return check_cuda(cudaLaunchKernelEx(&cfg, tally_select_kernel<K>, header, ukeys, ucnt, wbuf, ldw, H, lf, logV0,
-                                       n_total, top, stats),
+                                       n_total, top, stats, (int32_t)cache),
                     "tally_select launch");
 }
 
@@ -936,9 +950,10 @@ extern "C" int b200_tally_finalize(const b200_tally_plan* plan, void* workspace,
   tally_merge_kernel<<<sm_count() * 2, 256, 0, st>>>(P, L.header, L.concat, L.slot_of, L.keysB, L.countsB, L.posB,
                                                      L.capB, cat);
   B200_CUDA(cudaGetLastError());
-  tally_mark_kernel<<<(unsigned)L.nblk, 256, 0, st>>>(L.header, L.slot_of, L.posB, L.blockcnt);
+  const unsigned mgrid = (unsigned)std::min<int64_t>(L.nblk, (int64_t)sm_count() * 2);
+  tally_mark_kernel<<<mgrid, 256, 0, st>>>(L.header, L.slot_of, L.posB, L.blockcnt);
   B200_CUDA(cudaGetLastError());
-  tally_unique_kernel<<<(unsigned)L.nblk, 256, 0, st>>>(L.header, L.concat, L.slot_of, L.keysB, L.countsB, L.posB,
+  tally_unique_kernel<<<mgrid, 256, 0, st>>>(L.header, L.concat, L.slot_of, L.keysB, L.countsB, L.posB,
                                                         L.blockcnt, L.ukeys, L.ucnt, plan->bins_cap);
   return check_cuda(cudaGetLastError(), "tally_unique launch");
 }
