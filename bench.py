@@ -19,8 +19,10 @@ it - rlmd_b200.lev_exp.dice_fixed_final_lev(device, outcomes, ...) with
 `outcomes` an int64 [N,H] HOST tensor (pinned), stdout captured: chunked H2D of the
 int64 array, ingest kernel, statistics, the printed text - PCIe-bound at 8 bytes
 per roll.  The same call on uint8 / 2-bit host arrays is reported next to it.
-Steps run strictly one after the other (sweep, then its statistics); `pipelined`
-is the rate with the statistics of step i beside the sweep of step i+1.
+On one GPU steps run strictly one after the other (sweep, then its statistics);
+across GPUs the statistics of step i - mostly the exchange's latency - run beside
+the sweep of step i+1 (engine.FinalSweepPipeline's defaults; `other_depth` reports
+the other setting, `--pipeline` / `--no-pipeline` force one).
 With N GPUs (one process per GPU, torchrun) every rank owns its own 1e6
 investors (weak scaling); the only cross-GPU traffic is one exchange of the
 ranks' distinct-tuple lists per step over NVLink peer memory.
@@ -432,8 +434,10 @@ def run_gpu(args):
     row_bytes = (h + 3) // 4 if packed else h            # algorithmic bytes per investor row
     # depth 1: every sweep waits for the previous step's statistics, so a step is sweep -> statistics, one after
     # the other (--pipeline: the statistics of step i run beside the sweep of step i+1)
+    depth = 2 if args.pipeline else 1 if args.no_pipeline else None       # None: the engine's default
     pipe = engine.FinalSweepPipeline("discrete", table, V0, top_total, device=dev, group=group, n_total=n_total,
-                                     depth=2 if args.pipeline else 1, statistics=args.stats)
+                                     depth=depth, statistics=args.stats)
+    depth = pipe.depth
     pipe.timing = True
     stats_holder = {}
     ev = [None] * args.steps
@@ -466,14 +470,12 @@ def run_gpu(args):
              "max_rel_diff_moments": float(np.max(np.abs(stats[fin] - ref_stats[fin]) / np.abs(ref_stats[fin])))}
     # the pipelined rate and, for comparison, the other statistics path at depth 1
     extra_rates = {}
-    for name, p in (("pipelined", None), ("other_stats_path", other)):
+    for name, p in (("other_depth", None), ("other_stats_path", other)):
         if args.no_secondary:
             break
         if p is None:
-            if args.pipeline:
-                continue
             p = engine.FinalSweepPipeline("discrete", table, V0, top_total, device=dev, group=group,
-                                          n_total=n_total, depth=2, statistics=args.stats)
+                                          n_total=n_total, depth=3 - depth, statistics=args.stats)
         for _ in range(3):
             p.submit(outcomes)
         p.synchronize()
@@ -564,8 +566,11 @@ def run_gpu(args):
             "mode": {"tally": "log-domain count sweep -> tally of count tuples -> weighted exact statistics",
                      "rows": "log-domain final sweep -> data_T -> 4-pass row statistics"}[args.stats],
             "sharding": f"investors x{world}",
-            "pipeline": "the statistics of step i run beside the sweep of step i+1 (two streams)" if args.pipeline
-                        else "none: each sweep waits for the previous step's statistics",
+            "pipeline": ("depth 2: the statistics (and their cross-GPU exchange) of step i run beside the sweep of "
+                         "step i+1 on a second stream" if depth == 2 else
+                         "depth 1: each sweep waits for the previous step's statistics") +
+                        (" (engine default: 2 across GPUs, 1 on one GPU)" if not (args.pipeline or args.no_pipeline)
+                         else " (forced by flag)"),
             "statistics_exchange": "none (one GPU)" if world == 1 else
                                    ("one exchange per step: the ranks' distinct-tuple lists over NVLink peer memory"
                                     if args.stats == "tally" else "four per step (radix histograms), peer memory"),
@@ -574,7 +579,7 @@ def run_gpu(args):
         },
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
-        "path_steps_per_s": value * g, "pipelined": extra_rates.get("pipelined"),
+        "path_steps_per_s": value * g, "other_depth": extra_rates.get("other_depth"),
         "other_stats_path": extra_rates.get("other_stats_path"), "secondary": secondary,
         "check": {"median_wealth_lev0": float(stats[0, 9]), "mean_wealth_lev0": float(stats[0, 0]),
                   "tally_vs_rows": agree},
@@ -818,8 +823,10 @@ def main():
     ap.add_argument("--stats", default="tally", choices=["tally", "rows"],
                     help="statistics path: tally of count tuples (default) or data_T + row statistics")
     ap.add_argument("--pipeline", action="store_true",
-                    help="timed region: the statistics of step i beside the sweep of step i+1 (two streams); by default "
-                         "steps run strictly one after the other and the pipelined rate is reported as `pipelined`")
+                    help="force depth 2: the statistics of step i beside the sweep of step i+1 (two streams)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="force depth 1: steps strictly one after the other (default: the engine's choice - depth 2 "
+                         "across GPUs, depth 1 on one GPU; the other depth's rate is reported as `other_depth`)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-investors", type=int, default=250_000,
                     help="investors per GPU of the int64 end-to-end call (20 GB of pinned host memory per GPU)")
