@@ -723,31 +723,28 @@ def run_gpu_gbm(args):
     lev = np.asarray(lev_exp.param_range(*GBM_GRID), dtype=np.float32)
     g = len(lev)
     n_total, top_total = n * world, max(1, int(n * world * 1e-4))
-    data_T = torch.empty((g, n), dtype=torch.float32, device=dev)
+    depth = 2 if args.pipeline else 1 if args.no_pipeline else None       # None: the engine's default (2 for GBM)
+    pipe = engine.FinalSweepPipeline("gbm", lev, V0, top_total, device=dev, group=group, n_total=n_total, depth=depth)
+    pipe.timing = True
+    depth = pipe.depth
     holder = {}
     ev = [None] * args.steps
+    cur = torch.cuda.current_stream()
 
     def step(i):
-        a = torch.cuda.Event(enable_timing=True)
-        b = torch.cuda.Event(enable_timing=True)
-        a.record()
-        res = engine.lev_sweep("gbm", lev, V0, n_investors=n, horizon=h, seed=420, investor_offset=rank * n,
-                               log_mean=GBM_MEAN, sigma=GBM_SIGMA, mode="log", out_data_T=data_T, want_log_w=True,
-                               device=dev)
-        b.record()
-        holder["stats"] = engine.rowstats(data_T, top_total, n_total=n_total, group=group)
-        holder["growth"] = engine.growth_summary(res["log_w"], h, V0, data_T=data_T, quantiles=(0.05, 0.5),
-                                                 n_total=n_total, group=group)
+        holder["stats"], holder["growth"] = pipe.submit_philox(n, h, seed=420, investor_offset=rank * n,
+                                                               log_mean=GBM_MEAN, sigma=GBM_SIGMA)
         if i is not None:
-            ev[i] = (a, b)
+            ev[i] = pipe.last_sweep
 
-    elapsed, clocks, warm_done = timed_steps(torch, dist, world, local_rank, args, step, lambda: None)
+    def after():
+        cur.wait_stream(pipe.sweep_stream)
+        cur.wait_stream(pipe.stats_stream)
+
+    elapsed, clocks, warm_done = timed_steps(torch, dist, world, local_rank, args, step, after)
+    pipe.synchronize()
     sweep_s = sum(a.elapsed_time(b) for a, b in ev) * 1e-3 / args.steps
     elapsed, sweep_s = _max_over_ranks(torch, dist, dev, world, [elapsed, sweep_s])
-    if group is not None:
-        from rlmd_b200 import sharding
-
-        sharding.raise_if_peers_timed_out(group, dev)
     value = n_total * h * args.steps / elapsed
     stats = holder["stats"].cpu().numpy()
     growth = holder["growth"].cpu().numpy()
@@ -756,6 +753,7 @@ def run_gpu_gbm(args):
     # script contract (lev_scripts.gbm): statistics and growth summaries read back to the host every step
     def e2e_call():
         step(None)
+        after()
         return holder["stats"].cpu(), holder["growth"].cpu()
 
     e2e_call()
@@ -791,10 +789,12 @@ def run_gpu_gbm(args):
         "data": "synthetic (on-device Philox4x32-10 + Box-Muller, seed 420)",
         "config": {"workload": GBM_WORKLOAD, "investors_per_gpu": n, "horizon": h, "leverages": g, "top": top_total,
                    "mu_sigma": [0.05, GBM_SIGMA], "sharding": f"investors x{world}",
+                   "pipeline": f"depth {depth}: " + ("the statistics of step i (HBM-bound) run beside the sweep of step "
+                               "i+1 (issue-bound) on a second stream" if depth == 2 else "sweep, then its statistics"),
                    "statistics": "12 reference statistics per leverage (radix select over all shards) + growth-rate "
                                  "summaries (valid runs, mean, 5th percentile, median)",
-                   "l2": "no resident input (outcomes are generated in registers); data_T + log_w "
-                         f"({g * n * 12 / 1e9:.1f} GB per GPU) exceed the 126 MB L2"},
+                   "l2": "no resident input (outcomes are generated in registers); data_T + the state [3,N] "
+                         f"({(g * 4 + 24) * n / 1e9:.1f} GB per GPU) exceed the 126 MB L2"},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": args.steps * (1 + 9 + 14 + (0 if world == 1 else 8)), "clocks": clocks,
         "path_steps_per_s": value * g,

@@ -108,6 +108,12 @@ typedef struct b200_lev_desc {
  * time-ordered chain of gbm_smart_lev (:1048-1055: inf / 0 for good once the
  * running wealth left the range). */
 #define B200_LEV_FLAG_FINAL_ONLY 1
+/* GBM, LOG mode: `log_w` receives double [3,N] = (S, max_t S_t, min_t S_t), S_t the running
+ * sum of x - the leverage-INDEPENDENT state of an investor, from which every grid point's log
+ * wealth (log V0 + l S), its fp32 saturation and hence its growth rate follow - instead of the
+ * [G,N] log wealth: a tenth of the bytes at G = 10, and the growth-rate summaries of the whole
+ * grid need ONE selection over S (b200_gbm_valid + b200_growth_summary on the row S). */
+#define B200_LEV_FLAG_STATE_OUT 2
 
 /*
  * outcomes : STREAM: uint8 [N,ld] (discrete, codes < K; or packed 2-bit codes,
@@ -579,6 +585,24 @@ int b200_exchange_unpack(void* workspace, int64_t words_per_row, int64_t rows,
  * words named by b200_growth_exchange(phase) over ranks in between.
  * ------------------------------------------------------------------ */
 int64_t b200_growth_workspace_bytes(int64_t rows);
+
+/* GBM: per grid point, the runs that survive the reference's fp32 wealth - out double [G,2] =
+ * (count, sum of S over them) - from the sweep's state [3,N] (B200_LEV_FLAG_STATE_OUT) and its
+ * data_T [G, ld_T] (finite and > 0); data_T NULL: the wealth is re-formed from the state with
+ * the sweep's own saturation rule (one exp per run and grid point).  `out` is overwritten. */
+int b200_gbm_valid(const double* state, const float* data_T, int64_t n, int64_t ld_T,
+                   const float* lev_host, int32_t n_grid, double log_v0, double* out, void* stream);
+
+/* GBM: the growth-rate summaries of the whole grid, out double [G, 6 + n_q] in
+ * b200_growth_summary's layout, from base_row = the b200_growth_summary row of S (log_v0 = 0,
+ * horizon = 1; its quantile columns hold the quantiles the caller asked of S) and valid [G,2]
+ * (b200_gbm_valid, summed over ranks): g = l S / H, so every column scales with l / H, and a row
+ * with l < 0 takes S's mirrored quantile (type 8 is symmetric) and swaps min / max.
+ * pick_pos / pick_neg : device int32 [n_q]: which quantile column of base_row output column q
+ * reads for l >= 0 / l < 0. */
+int b200_gbm_growth_assemble(const double* base_row, const double* valid, const float* lev_host,
+                             int32_t n_grid, int32_t horizon, int32_t n_q, const int32_t* pick_pos,
+                             const int32_t* pick_neg, double* out, void* stream);
 int b200_growth_exchange(int32_t phase, int64_t out[5]);
 int b200_growth_summary(const double* log_w, const float* data_T, int64_t rows, int64_t n,
                         int64_t ld, int64_t ld_T, int64_t n_total, double log_v0,

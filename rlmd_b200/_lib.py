@@ -41,7 +41,7 @@ class LevDesc(C.Structure):
     ]
 
 
-LEV_FLAG_FINAL_ONLY = 1
+LEV_FLAG_FINAL_ONLY, LEV_FLAG_STATE_OUT = 1, 2
 MAX_PEERS = 8
 
 
@@ -224,6 +224,8 @@ _SIGNATURES = {
     "b200_bigbrain_chunk": (C.c_int, [C.POINTER(BigBrainDesc), _vp, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_double), _i32, _i32, _vp, _vp, _vp]),
     "b200_growth_workspace_bytes": (_i64, [_i64]),
+    "b200_gbm_valid": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(C.c_float), _i32, C.c_double, _vp, _vp]),
+    "b200_gbm_growth_assemble": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200_growth_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),
     "b200_growth_summary": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, C.c_double, _i32, C.POINTER(C.c_double),
                                       _i32, _vp, _vp, _i32, _vp]),

@@ -188,6 +188,32 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
   return r;
 }
 
+// hist[bin] += c for the lanes with `valid`; EVERY lane of the warp must call (converged).
+// Values of one row crowd into a few histogram bins when the bins are cut from the top bits
+// of a floating-point key (few binades in a row) or when most values are equal (wealth that
+// underflowed to 0): 32 lanes hitting one shared-memory word serialise.  Two rounds of "the
+// lanes that share the first pending lane's bin add up (REDUX) and issue ONE atomic" take out
+// the two biggest crowds; what is left goes as plain atomics.
+__device__ __forceinline__ void warp_hist_add(uint32_t* hist, uint32_t bin, uint32_t c, bool valid) {
+  constexpr unsigned FULL = 0xffffffffu;
+  unsigned rem = __ballot_sync(FULL, valid);
+  if (rem == 0u) return;
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    if (rem == 0u) return;
+    const int ld = __ffs(rem) - 1;
+    const uint32_t lb = __shfl_sync(FULL, bin, ld);
+    const bool same = valid && bin == lb;
+    const unsigned grp = __ballot_sync(FULL, same);
+    const uint32_t sum = __reduce_add_sync(FULL, same ? c : 0u);
+    if (lane == (unsigned)ld && sum != 0u) atomicAdd(hist + lb, sum);
+    rem &= ~grp;
+    valid = valid && !same;
+  }
+  if (valid && c != 0u) atomicAdd(hist + bin, c);
+}
+
 // Order-preserving map fp32 -> uint32 in torch.sort order (NaN greatest).
 __host__ __device__ __forceinline__ uint32_t float_key(float f) {
   uint32_t b;

@@ -95,15 +95,13 @@ growth_pass_kernel(const double* __restrict__ log_w, const float* __restrict__ d
 
   double a0 = 0, a1 = 0;
   long long c0 = 0;
-  const int64_t stride = (int64_t)gridDim.x * G_THREADS;
-  for (int64_t i = (int64_t)blockIdx.x * G_THREADS + threadIdx.x; i < n; i += stride) {
-    const double lw = v[i];
+  auto process = [&](double lw, float x, bool has_x) {
     const unsigned long long k = double_key(lw);
     if (LEVEL == 0) {
       const double g = (lw - p.log_v0) / p.h;
       a0 += g;
       bool ok;
-      if (w32) { const float x = w32[i]; ok = x > 0.0f && x < __int_as_float(0x7f800000); }
+      if (has_x) ok = x > 0.0f && x < __int_as_float(0x7f800000);
       else ok = fabs(lw) < __longlong_as_double(0x7ff0000000000000LL);
       if (ok) { a1 += g; ++c0; }
       atomicAdd(&g_hist[k >> shift], 1u);
@@ -115,6 +113,23 @@ growth_pass_kernel(const double* __restrict__ log_w, const float* __restrict__ d
       for (int j = 0; j < GT; ++j)
         if (hi == pfx[j]) atomicAdd(&g_hist[j * GBINS + lo], 1u);
     }
+  };
+  // four independent loads per thread are in flight before the first is used: with 64 KB of histograms a
+  // block the SM holds few warps, so the passes were bound by one memory round trip per element per thread
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * G_THREADS * U;
+  for (int64_t base = (int64_t)blockIdx.x * G_THREADS * U + threadIdx.x; base < n; base += stride) {
+    double lw[U];
+    float x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * G_THREADS;
+      lw[u] = i < n ? __ldcs(v + i) : 0.0;
+      x[u] = (LEVEL == 0 && w32 != nullptr && i < n) ? __ldcs(w32 + i) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (base + (int64_t)u * G_THREADS < n) process(lw[u], x[u], w32 != nullptr);
   }
   if (LEVEL == 0) {
     const double s0 = block_sum(a0, red_d), s1 = block_sum(a1, red_d);
@@ -139,45 +154,42 @@ growth_pass_kernel(const double* __restrict__ log_w, const float* __restrict__ d
 __global__ void __launch_bounds__(256)
 growth_resolve_kernel(GrowthWS* __restrict__ ws, int level, int64_t n_total, const __grid_constant__ GrowthParams p,
                       double* __restrict__ out, int out_ld) {
-  __shared__ long long part[256];
-  __shared__ int bin_s;
-  __shared__ long long rem_s;
   GrowthWS* w = ws + blockIdx.x;
   const int bins = level_bins(level), shift = level_shift(level);
-  const int per = bins / 256;  // 8 or 2
-  for (int j = 0; j < GT; ++j) {
+  // warp j resolves target j (eight warps, eight targets, all at once): every lane sums a contiguous
+  // run of bins, a shuffle scan names the lane whose run holds the rank, that lane walks its run
+  {
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long* h = level == 0 ? w->hist[0] : w->hist[j];
     const long long rank = level == 0 ? p.rank[j] : w->rank[j];
+    const int per = bins / 32;   // 64 or 16
     long long local = 0;
-    for (int i = 0; i < per; ++i) local += h[threadIdx.x * per + i];
-    part[threadIdx.x] = local;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      long long acc = 0;
-      int owner = 255;
-      for (int t = 0; t < 256; ++t) {
-        if (rank < acc + part[t]) { owner = t; break; }
-        acc += part[t];
-      }
-      long long r = rank - acc;
-      int b = owner * per;
+    for (int i = 0; i < per; ++i) local += h[lane * per + i];
+    long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const long long excl = incl - local;
+    const long long total = __shfl_sync(0xffffffffu, incl, 31);
+    const bool owner = (rank >= excl && rank < incl) || (lane == 31 && rank >= total);
+    if (owner) {
+      long long r = rank - excl;
+      int b = lane * per;
       for (int i = 0; i < per; ++i) {
-        const long long c = h[owner * per + i];
-        if (r < c || i == per - 1) { b = owner * per + i; break; }
+        const long long c = h[lane * per + i];
+        if (r < c || i == per - 1) { b = lane * per + i; break; }
         r -= c;
       }
-      bin_s = b;
-      rem_s = r;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned long long add = (unsigned long long)bin_s << shift;
+      const unsigned long long add = (unsigned long long)b << shift;
       w->prefix[j] = (level == 0 ? 0ull : w->prefix[j]) | add;
-      w->rank[j] = rem_s;
+      w->rank[j] = r;
       if (level == GLEVELS - 1) w->value[j] = (key_double(w->prefix[j]) - p.log_v0) / p.h;
     }
-    __syncthreads();
   }
+  __threadfence_block();
+  __syncthreads();
   // clear the histograms for the next level
   for (int i = threadIdx.x; i < GT * GBINS; i += 256) (&w->hist[0][0])[i] = 0;
   if (threadIdx.x == 0) {
@@ -276,7 +288,7 @@ extern "C" int b200_growth_summary(const double* log_w, const float* data_T, int
 
   cudaStream_t st = (cudaStream_t)stream;
   GrowthWS* ws = (GrowthWS*)workspace;
-  int64_t want = ((int64_t)sm_count() * 4 + rows - 1) / rows;
+  int64_t want = ((int64_t)sm_count() * 8 + rows - 1) / rows;
   int64_t max_slices = (n + G_THREADS * 8 - 1) / (G_THREADS * 8);
   int64_t slices = want < max_slices ? want : max_slices;
   if (slices < 1) slices = 1;

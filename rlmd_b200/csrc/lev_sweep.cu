@@ -359,9 +359,14 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
 __device__ __forceinline__ void gbm_finish(double S, double Smax, double Smin, int32_t G,
                                            const LevGrid& lv, double logV0, int64_t row, int64_t ldT,
                                            float* __restrict__ data_T, double* __restrict__ log_w,
-                                           bool saturate = true) {
+                                           bool saturate = true, int64_t state_n = 0) {
   const double LOG_FLT_MAX = 88.72283905206835;    // ln(3.4028234664e38)
   const double LOG_FLT_ZERO = -103.97207708399179; // ln(2^-150)
+  if (state_n > 0 && log_w != nullptr) {     // B200_LEV_FLAG_STATE_OUT: the leverage-independent state
+    log_w[row] = S; log_w[state_n + row] = Smax; log_w[2 * state_n + row] = Smin;
+    log_w = nullptr;
+  }
+  if (data_T == nullptr && log_w == nullptr) return;
   for (int g = 0; g < G; ++g) {
     const double l = (double)lv.lev[g];
     const double lw = logV0 + l * S;
@@ -387,6 +392,14 @@ struct GbmAcc {
     pmax = fmaxf(pmax, p);
     pmin = fminf(pmin, p);
   }
+  // two steps: the running extremes take both partial sums in ONE three-input min / max each
+  // (FMNMX3, sm_100) - 4 instructions per pair instead of 6, the same values bit for bit
+  __device__ __forceinline__ void step2(float x0, float x1) {
+    const float p1 = p + x0;
+    p = p1 + x1;
+    asm("max.f32 %0, %0, %1, %2;" : "+f"(pmax) : "f"(p1), "f"(p));
+    asm("min.f32 %0, %0, %1, %2;" : "+f"(pmin) : "f"(p1), "f"(p));
+  }
   __device__ __forceinline__ void fold() {
     Smax = fmax(Smax, S + (double)pmax);
     Smin = fmin(Smin, S + (double)pmin);
@@ -399,7 +412,8 @@ template <bool USE_TMA>
 __global__ void __launch_bounds__(TILE_ROWS)
 log_gbm_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ x, int64_t ld,
                       const __grid_constant__ LevGrid lv, int32_t H, int64_t N, int32_t G, double logV0,
-                      float* __restrict__ data_T, double* __restrict__ log_w, int64_t ldT, bool saturate) {
+                      float* __restrict__ data_T, double* __restrict__ log_w, int64_t ldT, bool saturate,
+                      int64_t state_n) {
   extern __shared__ __align__(1024) uint8_t tiles[];
   __shared__ __align__(8) uint64_t full[STAGES];
   constexpr int TILE_STEPS = TILE_BYTES / 4;  // 32 floats per row per tile
@@ -446,7 +460,7 @@ log_gbm_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float4 q = *reinterpret_cast<const float4*>(tile + swz(tid, c));
-        acc.step(q.x); acc.step(q.y); acc.step(q.z); acc.step(q.w);
+        acc.step2(q.x, q.y); acc.step2(q.z, q.w);
       }
     } else {
       for (int t = 0; t < steps; ++t)
@@ -462,7 +476,7 @@ log_gbm_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     }
   }
   const int64_t row = row0 + tid;
-  if (row < N) gbm_finish(acc.S, acc.Smax, acc.Smin, G, lv, logV0, row, ldT, data_T, log_w, saturate);
+  if (row < N) gbm_finish(acc.S, acc.Smax, acc.Smin, G, lv, logV0, row, ldT, data_T, log_w, saturate, state_n);
 }
 
 // x_t = log_mean + sigma * z_t; four steps per Philox block, two Box-Muller pairs;
@@ -491,7 +505,7 @@ __global__ void __launch_bounds__(128)
 log_gbm_philox_kernel(const __grid_constant__ LevGrid lv, const __grid_constant__ PhiloxKeys K,
                       int64_t investor_offset, float log_mean,
                       float sigma, int32_t H, int64_t N, int32_t G, double logV0, float* __restrict__ data_T,
-                      double* __restrict__ log_w, int64_t ldT, bool saturate) {
+                      double* __restrict__ log_w, int64_t ldT, bool saturate, int64_t state_n) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= N) return;
   const uint64_t id = (uint64_t)(row + investor_offset);
@@ -504,14 +518,14 @@ log_gbm_philox_kernel(const __grid_constant__ LevGrid lv, const __grid_constant_
     for (int u = 0; u < 8; ++u) {
       float x[4];
       gbm_draw4(c0, c1, (uint32_t)(j + u), K, log_mean, sigma, x);
-      acc.step(x[0]); acc.step(x[1]); acc.step(x[2]); acc.step(x[3]);
+      acc.step2(x[0], x[1]); acc.step2(x[2], x[3]);
     }
     acc.fold();
   }
   for (; j < nblk; ++j) {
     float x[4];
     gbm_draw4(c0, c1, (uint32_t)j, K, log_mean, sigma, x);
-    acc.step(x[0]); acc.step(x[1]); acc.step(x[2]); acc.step(x[3]);
+    acc.step2(x[0], x[1]); acc.step2(x[2], x[3]);
   }
   if (H & 3) {
     float x[4];
@@ -519,7 +533,7 @@ log_gbm_philox_kernel(const __grid_constant__ LevGrid lv, const __grid_constant_
     for (int t = 0; t < (H & 3); ++t) acc.step(x[t]);
   }
   acc.fold();
-  gbm_finish(acc.S, acc.Smax, acc.Smin, G, lv, logV0, row, ldT, data_T, log_w, saturate);
+  gbm_finish(acc.S, acc.Smax, acc.Smin, G, lv, logV0, row, ldT, data_T, log_w, saturate, state_n);
 }
 
 __global__ void __launch_bounds__(128)
@@ -761,10 +775,11 @@ static int run_log_gbm(const b200_lev_desc& d, const float* x, const float* lev_
   const double logV0 = log((double)d.value_0);
   const int64_t N = d.n_investors;
   const bool saturate = (d.flags & B200_LEV_FLAG_FINAL_ONLY) == 0;
+  const int64_t state_n = (d.flags & B200_LEV_FLAG_STATE_OUT) ? N : 0;
   if (d.source == B200_SRC_PHILOX) {
     const unsigned blocks = (unsigned)((N + 127) / 128);
     log_gbm_philox_kernel<<<blocks, 128, 0, st>>>(lv, philox_keys(d.seed), d.investor_offset, d.log_mean, d.sigma, d.horizon, N,
-                                                  d.n_grid, logV0, data_T, log_w, out_ld(d), saturate);
+                                                  d.n_grid, logV0, data_T, log_w, out_ld(d), saturate, state_n);
     return check_cuda(cudaGetLastError(), "log_gbm_philox launch");
   }
   const unsigned blocks = (unsigned)((N + TILE_ROWS - 1) / TILE_ROWS);
@@ -776,10 +791,10 @@ static int run_log_gbm(const b200_lev_desc& d, const float* x, const float* lev_
     auto kern = log_gbm_stream_kernel<true>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * TILE_SMEM));
     kern<<<blocks, TILE_ROWS, STAGES * TILE_SMEM, st>>>(map, x, d.ld_outcomes, lv, d.horizon, N, d.n_grid, logV0,
-                                                        data_T, log_w, out_ld(d), saturate);
+                                                        data_T, log_w, out_ld(d), saturate, state_n);
   } else {
     log_gbm_stream_kernel<false><<<blocks, TILE_ROWS, TILE_SMEM, st>>>(map, x, d.ld_outcomes, lv, d.horizon, N,
-                                                                       d.n_grid, logV0, data_T, log_w, out_ld(d), saturate);
+                                                                       d.n_grid, logV0, data_T, log_w, out_ld(d), saturate, state_n);
   }
   return check_cuda(cudaGetLastError(), "log_gbm_stream launch");
 }
@@ -990,4 +1005,114 @@ extern "C" int b200_lev_chunk(const b200_lev_desc* desc, const void* outcomes, c
                                                     d.investor_offset, d.log_mean, d.sigma, t_begin, t_end,
                                                     d.n_investors, d.n_grid, logV0, (double*)state, dump);
   return check_cuda(cudaGetLastError(), "gbm_chunk launch");
+}
+
+
+// ------------------------------------------------ GBM: valid runs per grid point from the state
+namespace b200 {
+constexpr int VALID_TILE = 16;     // grid points per sweep of the state
+
+__global__ void __launch_bounds__(256)
+gbm_valid_kernel(const double* __restrict__ state, const float* __restrict__ data_T, int64_t ldT, int64_t N,
+                 const __grid_constant__ LevGrid lv, int32_t G, double logV0, double* __restrict__ out) {
+  __shared__ double red_d[32];
+  __shared__ long long red_i[32];
+  const double LOG_FLT_MAX = 88.72283905206835, LOG_FLT_ZERO = -103.97207708399179;
+  for (int g0 = 0; g0 < G; g0 += VALID_TILE) {
+    double sum[VALID_TILE];
+    int cnt[VALID_TILE];            // a thread sees far fewer than 2^31 runs
+#pragma unroll
+    for (int q = 0; q < VALID_TILE; ++q) { sum[q] = 0.0; cnt[q] = 0; }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+      const double S = __ldcs(state + i);
+      if (data_T != nullptr) {          // the sweep's own fp32 wealth decides
+        float w[VALID_TILE];
+#pragma unroll
+        for (int q = 0; q < VALID_TILE; ++q)
+          w[q] = g0 + q < G ? __ldcs(data_T + (int64_t)(g0 + q) * ldT + i) : 0.0f;
+#pragma unroll
+        for (int q = 0; q < VALID_TILE; ++q)
+          if (w[q] > 0.0f && w[q] < __int_as_float(0x7f800000)) { sum[q] += S; ++cnt[q]; }
+        continue;
+      }
+      const double Smax = state[N + i], Smin = state[2 * N + i];
+#pragma unroll
+      for (int q = 0; q < VALID_TILE; ++q) {
+        if (g0 + q >= G) break;
+        const double l = (double)lv.lev[g0 + q];
+        const double hi = logV0 + (l >= 0 ? l * Smax : l * Smin);
+        const double lo = logV0 + (l >= 0 ? l * Smin : l * Smax);
+        bool ok = !(hi > LOG_FLT_MAX) && !(lo < LOG_FLT_ZERO);
+        if (ok) { const float x = (float)exp(logV0 + l * S); ok = x > 0.0f && x < __int_as_float(0x7f800000); }
+        if (ok) { sum[q] += S; ++cnt[q]; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < VALID_TILE; ++q) {
+      if (g0 + q >= G) break;
+      const double s = block_sum(sum[q], red_d);
+      const long long c = block_sum((long long)cnt[q], red_i);
+      if (threadIdx.x == 0) {
+        atomicAdd(out + 2 * (g0 + q), (double)c);      // counts < 2^53: exact in fp64
+        atomicAdd(out + 2 * (g0 + q) + 1, s);
+      }
+    }
+  }
+}
+
+// Growth-rate summaries of the whole grid from the statistics of S (one row) and the valid-run sums:
+// g = l S / H, so mean / std / extremes / quantiles scale with l / H (the q-quantile of a row with
+// l < 0 is l / H times S's (1-q)-quantile: Hyndman-Fan type 8 is symmetric).
+//   base  : the b200_growth_summary row of S with log_v0 = 0, H = 1: [valid, mean, std, mean_valid,
+//           min, max, then the quantiles `need[0..n_need)` of S]
+//   valid : [G,2] from b200_gbm_valid (all-reduced over ranks by the caller)
+//   out   : [G, 6 + n_q]
+__global__ void gbm_assemble_kernel(const double* __restrict__ base, const double* __restrict__ valid,
+                                    const __grid_constant__ LevGrid lv, int32_t G, double H, int32_t n_q,
+                                    const int32_t* __restrict__ pick_pos, const int32_t* __restrict__ pick_neg,
+                                    double* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const double l = (double)lv.lev[g] / H;
+  const bool pos = l >= 0;
+  double* o = out + (int64_t)g * (6 + n_q);
+  const double cnt = valid[2 * g], sv = valid[2 * g + 1];
+  o[0] = cnt;
+  o[1] = l * base[1];
+  o[2] = fabs(l) * base[2];
+  o[3] = cnt > 0 ? l * sv / cnt : __longlong_as_double(0x7ff8000000000000LL);
+  o[4] = pos ? l * base[4] : l * base[5];
+  o[5] = pos ? l * base[5] : l * base[4];
+  for (int q = 0; q < n_q; ++q) o[6 + q] = l * base[6 + (pos ? pick_pos[q] : pick_neg[q])];
+}
+}  // namespace b200
+
+extern "C" int b200_gbm_valid(const double* state, const float* data_T, int64_t n, int64_t ld_T, const float* lev_host,
+                              int32_t n_grid, double log_v0, double* out, void* stream) {
+  B200_REQUIRE(n >= 0 && n_grid >= 1 && n_grid <= B200_MAX_GRID, "gbm_valid: need n >= 0 and 1 <= n_grid <= %d", B200_MAX_GRID);
+  B200_REQUIRE(lev_host != nullptr && out != nullptr, "gbm_valid: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA(cudaMemsetAsync(out, 0, (size_t)n_grid * 2 * sizeof(double), st));
+  if (n == 0) return 0;
+  B200_REQUIRE(state != nullptr, "gbm_valid: state is NULL");
+  B200_REQUIRE(data_T == nullptr || ld_T >= n, "gbm_valid: ld_T < n");
+  LevGrid lv;
+  for (int g = 0; g < B200_MAX_GRID; ++g) lv.lev[g] = g < n_grid ? lev_host[g] : 0.f;
+  const int64_t want = (n + 255) / 256;
+  const unsigned blocks = (unsigned)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+  gbm_valid_kernel<<<blocks, 256, 0, st>>>(state, data_T, ld_T, n, lv, n_grid, log_v0, out);
+  return check_cuda(cudaGetLastError(), "gbm_valid launch");
+}
+
+extern "C" int b200_gbm_growth_assemble(const double* base_row, const double* valid, const float* lev_host,
+                                        int32_t n_grid, int32_t horizon, int32_t n_q, const int32_t* pick_pos,
+                                        const int32_t* pick_neg, double* out, void* stream) {
+  B200_REQUIRE(n_grid >= 1 && n_grid <= B200_MAX_GRID && horizon >= 1 && n_q >= 0, "gbm_growth_assemble: bad sizes");
+  B200_REQUIRE(base_row && valid && lev_host && out && (n_q == 0 || (pick_pos && pick_neg)),
+               "gbm_growth_assemble: NULL argument");
+  LevGrid lv;
+  for (int g = 0; g < B200_MAX_GRID; ++g) lv.lev[g] = g < n_grid ? lev_host[g] : 0.f;
+  gbm_assemble_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(base_row, valid, lv, n_grid, (double)horizon, n_q, pick_pos,
+                                                          pick_neg, out);
+  return check_cuda(cudaGetLastError(), "gbm_growth_assemble launch");
 }

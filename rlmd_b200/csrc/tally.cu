@@ -455,33 +455,7 @@ __device__ __forceinline__ void find_rank(const uint32_t* pre, int bins, long lo
   rem = rank - (lo > 0 ? (long long)pre[lo - 1] : 0);
 }
 
-// hist[bin] += c for the lanes with `valid`; every lane of the warp must call.
-// A wealth row spans few binades (a level-1 histogram sees most of its elements in
-// a handful of bins) and at high leverage most wealths underflow to the SAME value
-// (then every level sees one bin): 32 lanes hitting one shared-memory word would
-// serialise (measured: 50k cycles per pass).  Two rounds of "the lanes that share
-// the first pending lane's bin add up (REDUX) and issue ONE atomic" take out the
-// two most likely crowds; what is left goes as plain atomics.
-__device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t bin, uint32_t c, bool valid) {
-  constexpr unsigned FULL = 0xffffffffu;
-  unsigned rem = __ballot_sync(FULL, valid);
-  if (rem == 0u) return;
-  const unsigned lane = threadIdx.x & 31;
-#pragma unroll
-  for (int round = 0; round < 2; ++round) {
-    if (rem == 0u) return;
-    const int ld = __ffs(rem) - 1;
-    const uint32_t lb = __shfl_sync(FULL, bin, ld);
-    const bool same = valid && bin == lb;
-    const unsigned grp = __ballot_sync(FULL, same);
-    const uint32_t sum = __reduce_add_sync(FULL, same ? c : 0u);
-    if (lane == (unsigned)ld && sum != 0u) atomicAdd(hist + lb, sum);
-    rem &= ~grp;
-    valid = valid && !same;
-  }
-  if (valid && c != 0u) atomicAdd(hist + bin, c);
-}
-
+// (grouped shared-memory histogram adds: warp_hist_add, common.cuh)
 // The pass's histograms were filled in every CTA's OWN shared memory; the other CTAs now
 // add their non-empty bins to the leader's copy (few remote atomics instead of one per element).
 __device__ __forceinline__ void push_hist(uint32_t* mine, uint32_t* leaders, int bins, int rank) {
@@ -608,7 +582,7 @@ tally_select_kernel(long long* __restrict__ header, const unsigned long long* __
     sweep([&](float x, uint32_t c, bool in) {
       a0 += (double)c * (double)x;      // c = 0 where the lane holds nothing
       c0 += c;
-      hist_add(sh.hist, float_key(x) >> 21, c, in);
+      warp_hist_add(sh.hist, float_key(x) >> 21, c, in);
     });
     STAMP();
     push_hist(sh.hist, L->hist, SL1, r);
@@ -678,7 +652,7 @@ tally_select_kernel(long long* __restrict__ header, const unsigned long long* __
       const uint32_t b1 = k >> 21, b2 = (k >> 10) & (SL2 - 1);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (rep[j] == j) hist_add(sh.hist + j * SL2, b2, c, in && b1 == pre[j]);     // (rep is warp-uniform)
+        if (rep[j] == j) warp_hist_add(sh.hist + j * SL2, b2, c, in && b1 == pre[j]);     // (rep is warp-uniform)
     });
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -719,7 +693,7 @@ tally_select_kernel(long long* __restrict__ header, const unsigned long long* __
       else if (in && hi22 < thr22) v[1] += cx;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (rep[j] == j) hist_add(sh.hist + j * SL3, k & (SL3 - 1), c, in && hi22 == pre[j]);
+        if (rep[j] == j) warp_hist_add(sh.hist + j * SL3, k & (SL3 - 1), c, in && hi22 == pre[j]);
     });
 #pragma unroll
     for (int j = 0; j < 4; ++j)

@@ -197,6 +197,7 @@ def lev_sweep(
     out_data_T: Optional[torch.Tensor] = None,
     device=None,
     final_only: bool = False,
+    want_state: bool = False,
 ) -> dict:
     """
     One launch over the whole leverage grid (b200_lev_sweep).
@@ -208,6 +209,9 @@ def lev_sweep(
     mode      "chain" (exact fp32 product; discrete only) or "log"
     final_only  GBM: data_T without the running-extremes saturation, i.e. what gbm_fixed_final_lev's
               torch.prod holds (B200_LEV_FLAG_FINAL_ONLY); the default is gbm_smart_lev's chain
+    want_state  GBM: also return "state" = float64 [3,N] (S, running max, running min of the summed
+              log-returns): the leverage-independent state every row's log wealth log V0 + l S follows
+              from (B200_LEV_FLAG_STATE_OUT; excludes want_log_w) - see gbm_growth_summary
     returns   {"data_T": [G,N] f32, "log_w": [G,N] f64, "counts": [N,K] i32}
     """
     require_cuda()
@@ -216,6 +220,10 @@ def lev_sweep(
                                     probs, log_mean, sigma, variant, device)
     if final_only:
         d.flags |= _lib.LEV_FLAG_FINAL_ONLY
+    if want_state:
+        if kind != "gbm" or want_log_w:
+            raise ValueError("want_state is a GBM output and replaces log_w")
+        d.flags |= _lib.LEV_FLAG_STATE_OUT
 
     res = {}
     with torch.cuda.device(dev):
@@ -230,12 +238,17 @@ def lev_sweep(
                 raise ValueError("log_w and a strided out_data_T cannot be combined")
         if want_log_w:
             log_w = torch.empty((g, n), dtype=torch.float64, device=dev)
+        state = None
+        if want_state:
+            state = log_w = torch.empty((3, n), dtype=torch.float64, device=dev)
         if want_counts:
             counts = torch.empty((n, k), dtype=torch.int32, device=dev)
         oc = outcomes.data if isinstance(outcomes, PackedCodes) else outcomes
         check(lib.b200_lev_sweep(C.byref(d), ptr(oc), f.ctypes.data_as(C.POINTER(C.c_float)),
                                  ptr(data_T), ptr(log_w), ptr(counts), stream_ptr()))
-    res["data_T"], res["log_w"], res["counts"] = data_T, log_w, counts
+    res["data_T"], res["log_w"], res["counts"] = data_T, None if want_state else log_w, counts
+    if want_state:
+        res["state"] = state
     return res
 
 
@@ -640,7 +653,8 @@ class FinalSweepPipeline:
         # default: across GPUs the statistics chain is mostly exchange latency (flags, peer reads) - it runs beside
         # the next sweep; on one GPU there is nothing to hide and the two kernels only take SMs from each other
         # (measured: 0.474 ms per step at depth 2 against 0.461 at depth 1)
-        self.depth = max(1, int(depth)) if depth is not None else (2 if group is not None else 1)
+        # (the GBM Philox sweep is bound by instruction issue, its statistics by HBM: they overlap well anywhere)
+        self.depth = max(1, int(depth)) if depth is not None else (2 if (group is not None or kind == "gbm") else 1)
         self.statistics = statistics or ("tally" if kind == "discrete" else "rows")
         if self.statistics not in ("tally", "rows") or (self.statistics == "tally" and kind != "discrete"):
             raise ValueError("statistics must be 'tally' (discrete gambles) or 'rows'")
@@ -704,6 +718,55 @@ class FinalSweepPipeline:
                 self.free[b] = done
                 stats.record_stream(cur)
         return stats
+
+    def submit_philox(self, n_investors: int, horizon: int, *, seed: int, investor_offset: int = 0,
+                      log_mean: float, sigma: float, growth_quantiles: Optional[Sequence[float]] = (0.05, 0.5)):
+        """
+        GBM with outcomes drawn on the device (lev/gbm.py at sizes whose fp32 outcome array cannot exist):
+        Philox sweep -> data_T [G,N] + state [3,N] on the sweep stream; the 12 statistics per leverage and (when
+        `growth_quantiles` is not None) the growth-rate summaries on the statistics stream, beside the next
+        sweep.  Returns (stats [G,12], growth [G, 6 + len(q)] or None), float64 on the device.
+        """
+        if self.kind != "gbm":
+            raise ValueError("submit_philox is the GBM path")
+        lev = self.factors.reshape(-1)
+        g, n = lev.shape[0], int(n_investors)
+        b = self.count % self.depth
+        self.count += 1
+        with torch.cuda.device(self.dev):
+            cur = torch.cuda.current_stream()
+            self.sweep_stream.wait_stream(cur)
+            with torch.cuda.stream(self.sweep_stream):
+                if self.free[b] is not None:
+                    self.sweep_stream.wait_event(self.free[b])
+                if self.data_T[b] is None or tuple(self.data_T[b].shape) != (g, n):
+                    self.data_T[b] = torch.empty((g, n), dtype=torch.float32, device=self.dev)
+                    self.ws[b] = rowstats_workspace(g, self.dev)
+                if self.timing:
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t0.record(self.sweep_stream)
+                res = lev_sweep("gbm", lev, self.value_0, n_investors=n, horizon=int(horizon), seed=seed,
+                                investor_offset=investor_offset, log_mean=log_mean, sigma=sigma, mode="log",
+                                out_data_T=self.data_T[b], want_state=growth_quantiles is not None, device=self.dev)
+                swept = torch.cuda.Event(enable_timing=self.timing)
+                swept.record(self.sweep_stream)
+                if self.timing:
+                    self.last_sweep = (t0, swept)
+            n_total = self.n_total if self.n_total is not None else n
+            with torch.cuda.stream(self.stats_stream):
+                self.stats_stream.wait_event(swept)
+                stats = rowstats(self.data_T[b], self.top, n_total=n_total, group=self.group, workspace=self.ws[b])
+                growth = None
+                if growth_quantiles is not None:
+                    res["state"].record_stream(self.stats_stream)
+                    growth = gbm_growth_summary(res["state"], lev, int(horizon), self.value_0, data_T=self.data_T[b],
+                                                quantiles=growth_quantiles, n_total=n_total, group=self.group)
+                    growth.record_stream(cur)
+                done = torch.cuda.Event()
+                done.record(self.stats_stream)
+                self.free[b] = done
+                stats.record_stream(cur)
+        return stats, growth
 
     def synchronize(self) -> None:
         self.sweep_stream.synchronize()
@@ -858,6 +921,59 @@ def growth_summary(log_w: torch.Tensor, horizon: int, value_0: float, *, data_T:
 
             sharding.exchange_phases(run_phase, ws, group, what="growth", n_phases=7)
     return out
+
+
+def gbm_growth_summary(state: torch.Tensor, lev: np.ndarray, horizon: int, value_0: float, *,
+                       data_T: Optional[torch.Tensor] = None, quantiles: Sequence[float] = (0.05, 0.5),
+                       n_total: Optional[int] = None, group=None) -> torch.Tensor:
+    """
+    growth_summary for a GBM sweep from its leverage-independent state [3,N] (lev_sweep(..., want_state=True)):
+    log wealth is log V0 + l S, so g = l S / H and every row's mean / std / min / max / quantiles follow from
+    ONE set of statistics of S (the q-quantile of a row with l < 0 is l/H times S's (1-q)-quantile: type 8 is
+    symmetric) - one selection over N doubles instead of G selections over G x N.  The valid-run counts (finite
+    and positive fp32 wealth, per leverage) come from b200_gbm_valid: from the sweep's `data_T` when it is passed
+    (one 4-byte read per run and leverage), else re-formed from the state.  Same layout as growth_summary:
+    float64 [G, 6 + len(quantiles)].  With `group` the rows are investor shards.
+    """
+    require_cuda()
+    if state.dim() != 2 or state.shape[0] != 3 or state.dtype != torch.float64 or not state.is_cuda \
+            or not state.is_contiguous():
+        raise ValueError("state must be the contiguous float64 [3,N] CUDA tensor of lev_sweep(want_state=True)")
+    levf = np.ascontiguousarray(lev, dtype=np.float32).reshape(-1)
+    g = levf.shape[0]
+    n = state.shape[1]
+    q = [float(x) for x in quantiles]
+    need = sorted(set(q) | {1.0 - x for x in q})
+    dev = state.device
+    n_total = n if n_total is None else int(n_total)
+    with torch.cuda.device(dev):
+        valid = torch.empty((g, 2), dtype=torch.float64, device=dev)
+        ld_T = 0
+        if data_T is not None:
+            if tuple(data_T.shape) != (g, n) or data_T.dtype != torch.float32 or (n > 1 and data_T.stride(1) != 1):
+                raise ValueError("data_T must be the sweep's float32 [G,N] output")
+            ld_T = data_T.stride(0) if g > 1 else max(data_T.stride(0), n)
+        check(lib.b200_gbm_valid(ptr(state), ptr(data_T), n, ld_T, levf.ctypes.data_as(C.POINTER(C.c_float)), g,
+                                 math.log(float(value_0)), ptr(valid), stream_ptr()))
+        if group is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(valid, group=group)
+        if len(need) > 3:
+            raise ValueError("at most three distinct quantile levels of S per call (q and 1-q count)")
+        base = growth_summary(state[0:1], 1, 1.0, quantiles=need, n_total=n_total, group=group)   # the row S itself
+        key = (dev.index, tuple(q))
+        if key not in _gbm_picks:
+            _gbm_picks[key] = (torch.tensor([need.index(x) for x in q], dtype=torch.int32, device=dev),
+                               torch.tensor([need.index(1.0 - x) for x in q], dtype=torch.int32, device=dev))
+        pick_pos, pick_neg = _gbm_picks[key]
+        out = torch.empty((g, 6 + len(q)), dtype=torch.float64, device=dev)
+        check(lib.b200_gbm_growth_assemble(ptr(base), ptr(valid), levf.ctypes.data_as(C.POINTER(C.c_float)), g,
+                                           int(horizon), len(q), ptr(pick_pos), ptr(pick_neg), ptr(out), stream_ptr()))
+    return out
+
+
+_gbm_picks = {}
 
 
 # ---------------------------------------------------------------- big brain

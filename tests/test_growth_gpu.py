@@ -69,3 +69,30 @@ def test_sweep_to_growth_pipeline():
         want = lo.growth_summary(lw, np.exp(lw).astype(np.float32), 100.0, h)
     assert np.array_equal(got[:, 0], want[:, 0])
     np.testing.assert_allclose(got[:, 1:], want[:, 1:], rtol=1e-10, atol=1e-14)
+
+
+def test_gbm_state_summary_equals_row_summary():
+    """gbm_growth_summary (one selection over the leverage-independent state S) against growth_summary on the
+    [G,N] log-wealth rows of the same sweep: valid-run counts exact, everything else to fp64 rounding."""
+    import torch
+    from rlmd_b200 import engine, lev_exp
+    n, h = 200_003, 700
+    for grid, mu, sig in (((-1.0, 1.0, 0.2), 0.05, 0.2 ** 0.5), ((0.2, 2.0, 0.2), 0.0540025395205692, 0.1897916175617430)):
+        lev = np.asarray(lev_exp.param_range(*grid), dtype=np.float32)
+        kw = dict(n_investors=n, horizon=h, seed=3, log_mean=mu - sig * sig / 2, sigma=sig, mode="log")
+        a = engine.lev_sweep("gbm", lev, 100.0, want_log_w=True, **kw)
+        b = engine.lev_sweep("gbm", lev, 100.0, want_state=True, **kw)
+        assert torch.equal(a["data_T"], b["data_T"]) and b["log_w"] is None
+        want = engine.growth_summary(a["log_w"], h, 100.0, data_T=a["data_T"], quantiles=(0.05, 0.5)).cpu().numpy()
+        got = engine.gbm_growth_summary(b["state"], lev, h, 100.0, quantiles=(0.05, 0.5)).cpu().numpy()
+        got_T = engine.gbm_growth_summary(b["state"], lev, h, 100.0, data_T=b["data_T"], quantiles=(0.05, 0.5))
+        assert np.array_equal(got_T.cpu().numpy()[:, 0], got[:, 0])          # valid runs: from data_T or re-formed
+        np.testing.assert_allclose(got_T.cpu().numpy(), got, rtol=1e-13, equal_nan=True)
+        assert np.array_equal(got[:, 0], want[:, 0])              # valid runs per leverage
+        assert 0 < want[:, 0].min() or want[:, 0].max() > 0
+        ok = ~np.isnan(want)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_allclose(got[ok], want[ok], rtol=2e-12, atol=1e-16)
+        # log wealth rebuilt from the state is the sweep's log wealth
+        lw = np.log(100.0) + lev.astype(np.float64)[:, None] * b["state"][0].cpu().numpy()[None, :]
+        np.testing.assert_allclose(lw, a["log_w"].cpu().numpy(), rtol=1e-15, atol=1e-13)
