@@ -420,6 +420,18 @@ int b200_replay_sample(const b200_replay_desc* desc, const int64_t* idx, int64_t
                        float* out_action, float* out_reward, float* out_next_state,
                        uint8_t* out_done, int64_t* out_eff, void* stream);
 
+/* b200_replay_sample with nothing taken from the host at call time: the slots are always drawn on
+ * the device, `filled` comes from the device header and the draw index from `counter` (device
+ * int64 [2]: [0] the draw index, advanced by the call; [1] internal, zero-initialised).  The whole call can therefore be captured in a CUDA graph
+ * once and replayed - one sample_exp per training step for the cost of a graph launch instead of
+ * seven output allocations and a foreign-function call (tools/replay_torch.py:360-412 is called
+ * once per learner step, algos/algo_sac.py:238-298). */
+int b200_replay_sample_counted(const b200_replay_desc* desc, int64_t n_batches, int32_t batch,
+                               int32_t multi_steps, const float* gamma_pow_host, int32_t additive,
+                               uint64_t seed, int64_t* counter, int64_t* out_idx, float* out_state,
+                               float* out_action, float* out_reward, float* out_next_state,
+                               uint8_t* out_done, int64_t* out_eff, void* stream);
+
 /* ------------------------------------------------------------------ *
  * Fused collector and evaluation rollouts
  *

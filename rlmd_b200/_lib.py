@@ -211,6 +211,8 @@ _SIGNATURES = {
                                          C.c_double, C.POINTER(C.c_double), _i32, _i64, C.c_double, _vp]),
     "b200_replay_sample": (C.c_int, [C.POINTER(ReplayDesc), _vp, _i64, _i32, _i64, _i32, C.POINTER(C.c_float), _i32,
                                      C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_replay_sample_counted": (C.c_int, [C.POINTER(ReplayDesc), _i64, _i32, _i32, C.POINTER(C.c_float), _i32,
+                                             C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_exchange_pack": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "b200_exchange_unpack": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "b200_market_dims": (C.c_int, [C.POINTER(MarketDesc)] + [C.POINTER(_i32)] * 3),

@@ -32,7 +32,7 @@ int replay_sample_lanes(const b200_replay_desc* d, int64_t lanes, int64_t lane_l
                         const float* gamma_pow_host, int32_t additive, uint64_t seed, uint64_t draw_index,
                         const int64_t* draw_counter, int64_t* out_idx, float* out_state, float* out_action,
                         float* out_reward, float* out_next_state, uint8_t* out_done, int64_t* out_eff,
-                        void* stream);
+                        void* stream, int64_t* bump, int* bumped);
 
 __device__ __forceinline__ void reset_state(const b200_env_desc& d, double* __restrict__ s, int S) {
   s[0] = d.initial_value / d.max_value;
@@ -218,7 +218,8 @@ extern "C" int b200_collect_sample(const b200_collect_desc* c, const int64_t* id
   B200_REQUIRE(idx != nullptr || counter != nullptr, "collect_sample: counter is NULL while indices are drawn");
   int rc = replay_sample_lanes(&c->replay, c->n_envs, c->lane_len, idx, n_batches, batch, -1, multi_steps,
                                gamma_pow_host, additive, seed, 0, idx ? nullptr : counter + CTR_SAMPLE, out_idx,
-                               out_state, out_action, out_reward, out_next_state, out_done, out_eff, stream);
+                               out_state, out_action, out_reward, out_next_state, out_done, out_eff, stream, nullptr,
+                               nullptr);
   if (rc) return rc;
   if (idx == nullptr && n_batches * batch > 0) {
     counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, CTR_SAMPLE);

@@ -447,13 +447,19 @@ replay_draw_gather_kernel(const b200_replay_desc d, int64_t filled_arg, int32_t 
                           const __grid_constant__ GammaPow gp, float* __restrict__ out_state,
                           float* __restrict__ out_action, float* __restrict__ out_reward,
                           float* __restrict__ out_next_state, uint8_t* __restrict__ out_done,
-                          int64_t* __restrict__ out_eff) {
+                          int64_t* __restrict__ out_eff, int64_t* __restrict__ bump) {
   extern __shared__ unsigned long long table[];
   draw_block(d, filled_arg, B, seed, draw_index, draw_counter, lanes, lane_len, table_size, out_idx, table);
   __syncthreads();   // the block's own writes of out_idx
   for (int t = threadIdx.x; t < B; t += blockDim.x)
     gather_sample(d, out_idx, (int64_t)blockIdx.x * B + t, filled_arg, lanes, lane_len, n_steps, additive, gp,
                   out_state, out_action, out_reward, out_next_state, out_done, out_eff);
+  // bump = {draw counter, ticket}: the last block to get here advances the counter (every block has read
+  // it by then) - the counted call is this ONE launch, nothing to bump afterwards
+  if (bump != nullptr && threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(bump + 1), 1ull);
+    if (t == (unsigned long long)gridDim.x - 1) { bump[1] = 0; bump[0] += 1; }
+  }
 }
 
 static int check_desc(const b200_replay_desc* d) {
@@ -544,7 +550,8 @@ int replay_sample_lanes(const b200_replay_desc* d, int64_t lanes, int64_t lane_l
                         const float* gamma_pow_host, int32_t additive, uint64_t seed, uint64_t draw_index,
                         const int64_t* draw_counter, int64_t* out_idx, float* out_state, float* out_action,
                         float* out_reward, float* out_next_state, uint8_t* out_done, int64_t* out_eff,
-                        void* stream) {
+                        void* stream, int64_t* bump, int* bumped) {
+  if (bumped) *bumped = 0;
   if (int rc = require_device()) return rc;
   if (int rc = check_desc(d)) return rc;
   B200_REQUIRE(lanes >= 1 && lane_len >= 1 && lanes * lane_len <= d->mem_size, "replay_sample: lanes x lane_len exceeds mem_size");
@@ -583,8 +590,9 @@ int replay_sample_lanes(const b200_replay_desc* d, int64_t lanes, int64_t lane_l
     if (d->state_dim < 32 && n_batches <= 4) {
       replay_draw_gather_kernel<<<(unsigned)n_batches, threads, smem, st>>>(
           *d, filled, batch, seed, draw_index, draw_counter, lanes, lane_len, table, out_idx, multi_steps, additive,
-          gp, out_state, out_action, out_reward, out_next_state, out_done, out_eff);
+          gp, out_state, out_action, out_reward, out_next_state, out_done, out_eff, bump);
       B200_CUDA(cudaGetLastError());
+      if (bumped && bump) *bumped = 1;
       return 0;
     }
     replay_draw_kernel<<<(unsigned)n_batches, threads, smem, st>>>(*d, filled, batch, seed, draw_index, draw_counter,
@@ -617,5 +625,29 @@ extern "C" int b200_replay_sample(const b200_replay_desc* d, const int64_t* idx,
   if (d == nullptr) return set_error(B200_EINVAL, "replay: desc is NULL");
   return replay_sample_lanes(d, 1, d->mem_size, idx, n_batches, batch, filled, multi_steps, gamma_pow_host, additive,
                              seed, draw_index, nullptr, out_idx, out_state, out_action, out_reward, out_next_state,
-                             out_done, out_eff, stream);
+                             out_done, out_eff, stream, nullptr, nullptr);
+}
+
+
+namespace b200 {
+__global__ void replay_counter_bump_kernel(int64_t* __restrict__ counter) { counter[0] += 1; }
+}  // namespace b200
+
+extern "C" int b200_replay_sample_counted(const b200_replay_desc* d, int64_t n_batches, int32_t batch,
+                                          int32_t multi_steps, const float* gamma_pow_host, int32_t additive,
+                                          uint64_t seed, int64_t* counter, int64_t* out_idx, float* out_state,
+                                          float* out_action, float* out_reward, float* out_next_state,
+                                          uint8_t* out_done, int64_t* out_eff, void* stream) {
+  if (d == nullptr) return set_error(B200_EINVAL, "replay: desc is NULL");
+  B200_REQUIRE(counter != nullptr, "replay_sample_counted: counter is NULL");
+  int bumped = 0;
+  int rc = replay_sample_lanes(d, 1, d->mem_size, nullptr, n_batches, batch, -1, multi_steps, gamma_pow_host, additive,
+                               seed, 0, counter, out_idx, out_state, out_action, out_reward, out_next_state, out_done,
+                               out_eff, stream, counter, &bumped);
+  if (rc) return rc;
+  if (n_batches * batch > 0 && !bumped) {
+    replay_counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
+    return check_cuda(cudaGetLastError(), "replay_sample_counted counter");
+  }
+  return 0;
 }

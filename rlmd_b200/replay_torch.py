@@ -185,6 +185,57 @@ class ReplayBufferTorch:
         eff = e if self._n > 1 else self.eff_length[0]
         return s, a, r, s2, d, eff
 
+    def capture_sampler(self, k: int = 1):
+        """
+        `sample_exp` as a CUDA graph: records b200_replay_sample_counted (draw on the device, `filled` from
+        the device header, draw index from a device counter) ONCE into caller-owned static output tensors and
+        returns a callable; each call replays the graph - no allocation, no foreign-function call - and
+        returns the reference's 6-tuple (states, actions, rewards, next_states, dones, eff_length) as views
+        of the static tensors (overwritten by the next call; `self.last_batch` holds the drawn slots).
+        Transitions stored after the capture are seen (the header lives on the device).  Needs
+        mini_batch_size stored transitions, like the reference's multi-step sampler.  k > 1: k mini-batches
+        per replay, rows [k * batch_size, ...].
+        """
+        dev, b, n = self.device, self.batch_size, int(k) * self.batch_size
+        if min(self.mem_idx, self.mem_size) < b:
+            raise IndexError("fewer stored transitions than mini_batch_size")
+        with torch.cuda.device(dev):
+            out = dict(idx=torch.empty((n,), dtype=torch.int64, device=dev),
+                       s=torch.empty((n, self.input_dims), dtype=torch.float32, device=dev),
+                       a=torch.empty((n, self.num_actions), dtype=torch.float32, device=dev),
+                       r=torch.empty((n,), dtype=torch.float32, device=dev),
+                       s2=torch.empty((n, self.input_dims), dtype=torch.float32, device=dev),
+                       d=torch.empty((n,), dtype=torch.bool, device=dev),
+                       e=torch.empty((n,), dtype=torch.int64, device=dev))
+            # its own stream of draw indices, far from the ones sample_exp() uses
+            counter = torch.tensor([(1 << 40) + self._draws, 0], dtype=torch.int64, device=dev)
+
+            def launch():
+                check(lib.b200_replay_sample_counted(C.byref(self._desc), int(k), b, self._n, self._gamma_pow,
+                                                     int(self.dyna == "A"), self.seed, ptr(counter), ptr(out["idx"]),
+                                                     ptr(out["s"]), ptr(out["a"]), ptr(out["r"]), ptr(out["s2"]),
+                                                     ptr(out["d"]), ptr(out["e"]), stream_ptr()))
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                launch()                      # warm-up outside the capture (module loading, function attributes)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                launch()
+        eff = out["e"] if self._n > 1 else self.eff_length[0]
+        result = (out["s"], out["a"], out["r"], out["s2"], out["d"], eff)
+        self._sampler = (g, out, counter)
+
+        def replay():
+            g.replay()
+            self.last_batch = out["idx"]
+            return result
+
+        return replay
+
     def sample_many(self, k: int, batches=None):
         """k mini-batches in one launch: tensors with a leading [k, batch_size] shape (+ the slots)."""
         b = self.batch_size

@@ -183,3 +183,41 @@ def test_sample_exp_contract():
     s, a, r, s2, d, eff = one.sample_exp()     # young buffer: the batch is as long as the buffer (:382-383)
     assert s.shape == (10, 5) and eff.dim() == 0 and int(eff) == 1
     assert sorted(one.last_batch.cpu().tolist()) == list(range(10))
+
+
+def test_graph_captured_sampler_equals_indexed_sampling():
+    """capture_sampler(): every replay draws fresh distinct slots on the device (the oracle's draw for the
+    counter value), sees transitions stored after the capture, and returns exactly what sample_exp(batch=those
+    slots) returns - the multi-step targets included."""
+    case = golden_io.replay_case("n5_M")
+    st = golden_io.replay_stream(case)
+    buf = make(case, seed=77)
+    want = ro.ReplayOracle(golden_io.replay_inputs_dict(case))
+    for i in range(300):
+        args = (st["state"][i], st["action"][i], float(st["reward"][i]), st["next_state"][i], bool(st["done"][i]))
+        buf.store_exp(*args)
+        want.store_exp(*args)
+    run = buf.capture_sampler()
+    seen = []
+    for rep in range(4):
+        if rep == 2:                       # the buffer grows between replays
+            for i in range(300, 450):
+                args = (st["state"][i], st["action"][i], float(st["reward"][i]), st["next_state"][i], bool(st["done"][i]))
+                buf.store_exp(*args)
+                want.store_exp(*args)
+        out = run()
+        idx = buf.last_batch.cpu().numpy().copy()
+        filled = 300 if rep < 2 else 450
+        assert len(set(idx.tolist())) == case["batch"] and idx.min() >= 0 and idx.max() < filled
+        # the warm-up launch consumed counter value c0 (capturing launches nothing): replay r uses c0 + 1 + r
+        assert np.array_equal(idx, ro.draw_unique(buf.seed, (1 << 40) + 1 + rep, 0, filled, case["batch"]))
+        check_sample(tuple(t.clone() for t in out), want.sample_exp(idx), exact_reward=True)
+        seen.append(idx)
+    assert not np.array_equal(seen[0], seen[1])
+    # k mini-batches per replay
+    run3 = buf.capture_sampler(k=3)
+    s, a, r, s2, d, eff = run3()
+    assert s.shape == (3 * case["batch"], 5) and eff.shape == (3 * case["batch"],)
+    idx = buf.last_batch.cpu().numpy().reshape(3, -1)
+    for b in range(3):
+        assert len(set(idx[b].tolist())) == case["batch"]
