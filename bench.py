@@ -669,7 +669,16 @@ def measure_e2e(args, torch, dist, engine, lev_exp, np, dev, world, group, outco
             "printed_lines_per_call": len(lines) // (steps + 1),
             "note": "PCIe-bound: 8 bytes cross the bus per die roll in the reference's format",
         }
-        del host
+        # --- the platform's ceiling for this feed: the same pinned buffer copied H2D by every rank at once,
+        #     nothing else running (a bare cudaMemcpyAsync loop): what the PCIe links + host memory deliver
+        gib = min(host.numel() * 8, 4 << 30)
+        src_b = host.view(torch.uint8).reshape(-1)[:gib]
+        dst_b = torch.empty(gib, dtype=torch.uint8, device=dev)
+        dtc = timed(lambda: dst_b.copy_(src_b, non_blocking=True), 4)
+        out["h2d_ceiling"] = {"gbs_per_gpu": gib * 4 / dtc / 1e9, "gbs_all_gpus": world * gib * 4 / dtc / 1e9,
+                              "note": f"{gib >> 20} MiB pinned -> device, {world} rank(s) at the same time, 4 copies; "
+                                      "the e2e call above reaches h2d_gbs_per_gpu of it"}
+        del host, src_b, dst_b
         # --- the engine's host formats through the same statistics path
         for name, width, dtype in (("uint8_host_codes", h, torch.uint8),
                                    ("packed2_host_codes", -(-((h + 3) // 4) // 16) * 16, torch.uint8)):

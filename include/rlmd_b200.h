@@ -97,7 +97,9 @@ typedef struct b200_lev_desc {
                               stride ld_outcomes in BYTES (>= ceil(H/4)).  A
                               fair die carries 1.25 bits per roll: the packed
                               array is a quarter of the HBM traffic of the LOG
-                              sweep (the CHAIN kernels take uint8 codes)      */
+                              sweep (the CHAIN kernels take uint8 codes);
+                              1 = ONE bit per outcome (K = 2, the coin: step t in
+                              byte t>>3, bit t&7; stride in bytes >= ceil(H/8))  */
   int32_t flags;           /* B200_LEV_FLAG_*                                    */
 } b200_lev_desc;
 
@@ -171,6 +173,11 @@ int b200_lev_from_counts(const b200_lev_desc* desc, const int32_t* counts,
  * (ld_packed >= ceil(H/4); codes are taken modulo 4, pad bits are written 0). */
 int b200_lev_pack(const uint8_t* codes, int64_t n_investors, int32_t horizon,
                   int64_t ld_codes, uint8_t* packed, int64_t ld_packed, void* stream);
+/* ... with the packed width chosen: bits = 2 (above) or 1 (the coin; codes taken modulo 2,
+ * ld_packed >= ceil(H/8)). */
+int b200_lev_pack_bits(const uint8_t* codes, int64_t n_investors, int32_t horizon,
+                       int64_t ld_codes, uint8_t* packed, int64_t ld_packed, int32_t bits,
+                       void* stream);
 
 /* ------------------------------------------------------------------ *
  * Final-time statistics from outcome-count tuples ("tally")

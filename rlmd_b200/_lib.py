@@ -201,6 +201,7 @@ _SIGNATURES = {
     "b200_lev_draw": (C.c_int, [C.POINTER(LevDesc), _vp, _vp]),
     "b200_lev_from_counts": (C.c_int, [C.POINTER(LevDesc), _vp, C.POINTER(C.c_float), _vp, _vp, _vp]),
     "b200_lev_pack": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _vp]),
+    "b200_lev_pack_bits": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _i32, _vp]),
     "b200_lev_chunk": (C.c_int, [C.POINTER(LevDesc), _vp, C.POINTER(C.c_float), _i32, _i32, _vp, _vp, _vp]),
     "b200_menv_dims": (C.c_int, [C.POINTER(EnvDesc)] + [C.POINTER(_i32)] * 3),
     "b200_menv_reset": (C.c_int, [C.POINTER(EnvDesc), _i64, _vp, _vp, _vp, _vp, _vp]),

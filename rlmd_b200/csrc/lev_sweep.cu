@@ -77,6 +77,60 @@ draw_discrete_packed_kernel(const __grid_constant__ Thresholds th, uint64_t seed
   }
 }
 
+// One bit per flip (the coin: K = 2): step t in byte t >> 3, bit t & 7.  One thread per (investor, 32-bit
+// word = 32 steps = 8 Philox blocks): the same draws as draw_discrete_kernel<2>; steps >= H are written 0.
+__global__ void __launch_bounds__(128)
+draw_discrete_bits1_kernel(const __grid_constant__ Thresholds th, uint64_t seed, int64_t investor_offset, int32_t H,
+                           int64_t N, int64_t ldb, uint8_t* __restrict__ out) {
+  const int nwords = (H + 31) >> 5;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * nwords) return;
+  const int64_t row = idx / nwords;
+  const int w = (int)(idx - row * nwords);
+  const uint64_t id = (uint64_t)(row + investor_offset);
+  uint32_t word = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int j = w * 8 + q;
+    if (j * 4 >= H) break;
+    const Philox4 r = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)j, PHILOX_TAG_LEV,
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (j * 4 + b < H) word |= (uint32_t)draw_code<2>(u[b], th) << (q * 4 + b);
+  }
+  uint8_t* dst = out + row * ldb + (int64_t)w * 4;
+  if (w * 4 + 4 <= ldb && (((uintptr_t)dst) & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(dst) = word;
+  } else {
+    for (int b = 0; b < 4 && w * 4 + b < ldb; ++b) dst[b] = (uint8_t)(word >> (8 * b));
+  }
+}
+
+// uint8 codes -> one bit each: one thread per output word (32 codes)
+__global__ void __launch_bounds__(256)
+pack_bits1_kernel(const uint8_t* __restrict__ codes, int64_t ld, int32_t H, int64_t N, uint8_t* __restrict__ packed,
+                  int64_t ldb) {
+  const int nwords = (int)((ldb + 3) >> 2);
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * nwords) return;
+  const int64_t row = idx / nwords;
+  const int w = (int)(idx - row * nwords);
+  const uint8_t* __restrict__ src = codes + row * ld + (int64_t)w * 32;
+  uint32_t word = 0;
+  for (int i = 0; i < 32; ++i) {
+    const int t = w * 32 + i;
+    if (t < H) word |= (uint32_t)(src[i] & 1u) << i;
+  }
+  uint8_t* dst = packed + row * ldb + (int64_t)w * 4;
+  if (w * 4 + 4 <= ldb && (((uintptr_t)dst) & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(dst) = word;
+  } else {
+    for (int b = 0; b < 4 && w * 4 + b < ldb; ++b) dst[b] = (uint8_t)(word >> (8 * b));
+  }
+}
+
 // uint8 codes -> packed: one thread per output byte quad (16 codes)
 __global__ void __launch_bounds__(256)
 pack_codes_kernel(const uint8_t* __restrict__ codes, int64_t ld, int32_t H, int64_t N, uint8_t* __restrict__ packed,
@@ -198,8 +252,9 @@ log_discrete_stream_kernel(const uint8_t* __restrict__ outcomes, int64_t ld, int
 // masks of a code's low / high bit occupy the even bit positions only, so the
 // masks of TWO words share one popc: per 32 codes 2 shifts, 2 LOP3, 2 POPC and
 // 2 adds (POPC issues at 16 lanes/clk/SM: ~1/3 of its rate at the HBM rate).
-template <int K>
+template <int K, int BITS = 2>
 __device__ __forceinline__ void count_pair(uint32_t a, uint32_t b, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+  if (BITS == 1) { s1 += __popc(a) + __popc(b); return; }     // one bit per flip: the ones ARE the up moves
   constexpr uint32_t EVEN = 0x55555555u, ODD = 0xaaaaaaaau;
   s1 += __popc((a & EVEN) | ((b << 1) & ODD));
   if (K >= 3) s2 += __popc(((a >> 1) & EVEN) | (b & ODD));
@@ -213,13 +268,18 @@ __device__ __forceinline__ void count_pair(uint32_t a, uint32_t b, uint32_t& s1,
 // multiple of 16 there): the lane that holds it masks the codes of steps >= H.
 constexpr int PACKED_U = 6;
 
-__device__ __forceinline__ uint32_t word_mask(int valid) {   // low 2*valid bits, valid clamped to 0..16
-  const int v = min(max(valid, 0), 16);
-  return v >= 16 ? 0xffffffffu : ((1u << (2 * v)) - 1u);
+template <int BITS>
+__device__ __forceinline__ uint32_t word_mask(int valid) {   // low BITS*valid bits, valid clamped to 0..32/BITS
+  constexpr int PER = 32 / BITS;
+  const int v = min(max(valid, 0), PER);
+  return v >= PER ? 0xffffffffu : ((1u << (BITS * v)) - 1u);
 }
 // mask of a vector whose first `valid` codes are steps < H
+template <int BITS>
 __device__ __forceinline__ uint4 last_vector_mask(int valid) {
-  return make_uint4(word_mask(valid), word_mask(valid - 16), word_mask(valid - 32), word_mask(valid - 48));
+  constexpr int PER = 32 / BITS;
+  return make_uint4(word_mask<BITS>(valid), word_mask<BITS>(valid - PER), word_mask<BITS>(valid - 2 * PER),
+                    word_mask<BITS>(valid - 3 * PER));
 }
 
 // A warp takes 32 consecutive rows: it sweeps them one after the other (every
@@ -229,7 +289,8 @@ __device__ __forceinline__ uint4 last_vector_mask(int valid) {
 // reads and 128-byte coalesced stores of data_T / log_w.
 // TALLY: the row's count tuple goes to the tally (tally.cuh) and nothing else is written
 // but `counts` - the instantiation the final-time statistics run on.
-template <int K, bool TALLY>
+// BITS = 1: the coin's one-bit-per-flip format (K = 2), half the bytes again.
+template <int K, bool TALLY, int BITS = 2>
 __global__ void __launch_bounds__(COUNT_WARPS * 32, 4)   // 64 registers: 4 blocks per SM measured best (3: 0.86, 5: 0.83 of HBM)
 log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, int32_t H, int64_t N, int32_t G,
                            const __grid_constant__ LogFactorTable lf, double logV0, float* __restrict__ data_T,
@@ -238,8 +299,9 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * COUNT_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * COUNT_WARPS;
-  const int nbytes = (H + 3) >> 2;          // bytes that hold codes
-  const int full = H >> 2;                  // bytes whose four codes are all steps < H
+  constexpr int PER_BYTE = 8 / BITS;        // codes per byte
+  const int nbytes = (H + PER_BYTE - 1) / PER_BYTE;   // bytes that hold codes
+  const int full = H / PER_BYTE;            // bytes whose codes are all steps < H
   const int nvec = (nbytes + 15) >> 4;      // 16-byte vectors that hold codes
   const bool vec_rows = (ldb & 15) == 0 && ldb >= (int64_t)nvec * 16;
   // row-invariant shape of the vector walk (see the row loop)
@@ -249,10 +311,12 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
   const int tail_lanes = rem - (tail_slots - 1) * 32;            // lanes of its last slot, 1..32
   const bool in_tail = lane < tail_lanes;
   // this lane's mask for the last slot: only the row's very last vector holds pad codes
-  const uint4 wm = lane == tail_lanes - 1 ? last_vector_mask(H - 64 * (nvec - 1)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+  const uint4 wm = lane == tail_lanes - 1 ? last_vector_mask<BITS>(H - (128 / BITS) * (nvec - 1))
+                                          : make_uint4(~0u, ~0u, ~0u, ~0u);
   auto count_byte = [&](int t, uint32_t& s1, uint32_t& s2, uint32_t& s3, const uint8_t* __restrict__ p) {
     uint32_t c = p[t];
-    if (t >= full) c &= (1u << (2 * (H & 3))) - 1u;   // the last, partly filled byte
+    if (t >= full) c &= (1u << (BITS * (H % PER_BYTE))) - 1u;   // the last, partly filled byte
+    if (BITS == 1) { s1 += __popc(c); return; }
     s1 += __popc(c & 0x55u);
     if (K >= 3) s2 += __popc((c >> 1) & 0x55u);
     if (K >= 4) s3 += __popc(c & (c >> 1) & 0x55u);
@@ -276,8 +340,8 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
           for (int u = 0; u < PACKED_U; ++u) v[u] = __ldcs(q + u * 32);
 #pragma unroll
           for (int u = 0; u < PACKED_U; ++u) {
-            count_pair<K>(v[u].x, v[u].y, s1, s2, s3);
-            count_pair<K>(v[u].z, v[u].w, s1, s2, s3);
+            count_pair<K, BITS>(v[u].x, v[u].y, s1, s2, s3);
+            count_pair<K, BITS>(v[u].z, v[u].w, s1, s2, s3);
           }
         }
         // the row's last `rem` vectors: slots below tail_slots-1 are full, slot
@@ -290,13 +354,13 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
         for (int u = 0; u < PACKED_U - 1; ++u)
           if (u < tail_slots - 1) v[u] = __ldcs(q + u * 32);
         vl.x &= wm.x; vl.y &= wm.y; vl.z &= wm.z; vl.w &= wm.w;
-        count_pair<K>(vl.x, vl.y, s1, s2, s3);
-        count_pair<K>(vl.z, vl.w, s1, s2, s3);
+        count_pair<K, BITS>(vl.x, vl.y, s1, s2, s3);
+        count_pair<K, BITS>(vl.z, vl.w, s1, s2, s3);
 #pragma unroll
         for (int u = 0; u < PACKED_U - 1; ++u) {
           if (u < tail_slots - 1) {
-            count_pair<K>(v[u].x, v[u].y, s1, s2, s3);
-            count_pair<K>(v[u].z, v[u].w, s1, s2, s3);
+            count_pair<K, BITS>(v[u].x, v[u].y, s1, s2, s3);
+            count_pair<K, BITS>(v[u].z, v[u].w, s1, s2, s3);
           }
         }
       } else {
@@ -310,7 +374,7 @@ log_discrete_packed_kernel(const uint8_t* __restrict__ outcomes, int64_t ldb, in
         const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p + head);
         for (int i = lane; i < body; i += 32) {
           const uint4 a = __ldcs(q + i);
-          count_pair<K>(a.x, a.y, s1, s2, s3); count_pair<K>(a.z, a.w, s1, s2, s3);
+          count_pair<K, BITS>(a.x, a.y, s1, s2, s3); count_pair<K, BITS>(a.z, a.w, s1, s2, s3);
         }
         for (int t = tail0 + lane; t < nbytes; t += 32) count_byte(t, s1, s2, s3, p);
       }
@@ -730,16 +794,22 @@ static int run_log_discrete(const b200_lev_desc& d, const uint8_t* outcomes, con
   // (kernels on other streams get SM slots sooner) but a thinner epilogue.
   static const int task_rows = [] { const char* e = getenv("B200_PACKED_TASK_ROWS"); int v = e ? atoi(e) : 32;
                                     return v < 1 ? 1 : v > 32 ? 32 : v; }();
-  const int64_t warps = d.outcome_bits == 2 ? (N + task_rows - 1) / task_rows : N;
+  const bool packed = d.outcome_bits == 2 || d.outcome_bits == 1;
+  const int64_t warps = packed ? (N + task_rows - 1) / task_rows : N;
   int64_t blocks = (warps + COUNT_WARPS - 1) / COUNT_WARPS;
   // packed: one 32-row task per warp, handed out by the block scheduler (a capped
   // grid would give each warp 3.3 tasks at 1e6 rows: a fifth of the run spent in the tail)
-  const int64_t cap = d.outcome_bits == 2 ? (int64_t)0x7fffffff : (int64_t)sm_count() * 8;
+  const int64_t cap = packed ? (int64_t)0x7fffffff : (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
 #define B200_LOG_LAUNCH(KERNEL, ...)                                                                                     \
   KERNEL<__VA_ARGS__><<<(unsigned)blocks, COUNT_WARPS * 32, 0, st>>>(outcomes, d.ld_outcomes, d.horizon, N, d.n_grid, lf, \
                                                                      logV0, data_T, log_w, counts, out_ld(d), tally B200_EXTRA)
-  if (d.outcome_bits == 2) {
+  if (d.outcome_bits == 1) {
+#define B200_EXTRA , task_rows
+    if (tally.keys != nullptr) B200_LOG_LAUNCH(log_discrete_packed_kernel, 2, true, 1);
+    else B200_LOG_LAUNCH(log_discrete_packed_kernel, 2, false, 1);
+#undef B200_EXTRA
+  } else if (d.outcome_bits == 2) {
 #define B200_EXTRA , task_rows
     if (tally.keys != nullptr) {
       switch (d.n_outcomes) {
@@ -824,11 +894,14 @@ static int validate(const b200_lev_desc* d) {
       for (int k = 1; k < d->n_outcomes - 1; ++k)
         B200_REQUIRE(d->thresholds[k] >= d->thresholds[k - 1], "lev: thresholds must ascend");
   }
-  B200_REQUIRE(d->outcome_bits == 0 || d->outcome_bits == 8 || d->outcome_bits == 2,
-               "lev: outcome_bits must be 0/8 (uint8 codes) or 2 (packed)");
+  B200_REQUIRE(d->outcome_bits == 0 || d->outcome_bits == 8 || d->outcome_bits == 2 || d->outcome_bits == 1,
+               "lev: outcome_bits must be 0/8 (uint8 codes), 2 (packed) or 1 (packed coin)");
   if (d->outcome_bits == 2) {
     B200_REQUIRE(d->kind == B200_LEV_DISCRETE, "lev: packed outcomes are discrete codes");
     B200_REQUIRE(d->ld_outcomes >= ((int64_t)d->horizon + 3) / 4, "lev: packed ld_outcomes (bytes) < ceil(horizon/4)");
+  } else if (d->outcome_bits == 1) {
+    B200_REQUIRE(d->kind == B200_LEV_DISCRETE && d->n_outcomes == 2, "lev: one-bit outcomes are the coin's (K = 2)");
+    B200_REQUIRE(d->ld_outcomes >= ((int64_t)d->horizon + 7) / 8, "lev: packed ld_outcomes (bytes) < ceil(horizon/8)");
   } else if (d->source == B200_SRC_STREAM) {
     B200_REQUIRE(d->ld_outcomes >= d->horizon, "lev: ld_outcomes < horizon");
   }
@@ -856,7 +929,7 @@ extern "C" int b200_lev_sweep(const b200_lev_desc* desc, const void* outcomes, c
   if (d.kind == B200_LEV_DISCRETE) {
     if (d.mode == B200_MODE_CHAIN) {
       B200_REQUIRE(data_T != nullptr, "lev_sweep: CHAIN mode needs data_T");
-      B200_REQUIRE(d.outcome_bits != 2 || d.source == B200_SRC_PHILOX,
+      B200_REQUIRE((d.outcome_bits != 2 && d.outcome_bits != 1) || d.source == B200_SRC_PHILOX,
                    "lev_sweep: the CHAIN kernels take uint8 codes (packed outcomes feed the LOG sweep)");
       return run_chain_discrete(d, (const uint8_t*)outcomes, host_f, 0, d.horizon, nullptr, data_T, nullptr, out_ld(d), st);
     }
@@ -894,6 +967,15 @@ extern "C" int b200_lev_draw(const b200_lev_desc* desc, void* out, void* stream)
   cudaStream_t st = (cudaStream_t)stream;
   B200_REQUIRE(out != nullptr || d.n_investors == 0, "lev_draw: out is NULL");
   if (d.n_investors == 0) return 0;
+  if (d.outcome_bits == 1) {
+    const int64_t words = d.n_investors * (int64_t)((d.horizon + 31) >> 5);
+    const unsigned pb = (unsigned)((words + 127) / 128);
+    Thresholds th;
+    for (int k = 0; k < B200_MAX_OUTCOMES; ++k) th.t[k] = d.thresholds[k];
+    draw_discrete_bits1_kernel<<<pb, 128, 0, st>>>(th, d.seed, d.investor_offset, d.horizon, d.n_investors,
+                                                   d.ld_outcomes, (uint8_t*)out);
+    return check_cuda(cudaGetLastError(), "lev_draw (one bit) launch");
+  }
   if (d.outcome_bits == 2) {
     const int64_t words = d.n_investors * (int64_t)((d.horizon + 15) >> 4);
     const unsigned pb = (unsigned)((words + 127) / 128);
@@ -958,10 +1040,25 @@ extern "C" int b200_lev_from_counts(const b200_lev_desc* desc, const int32_t* co
 
 extern "C" int b200_lev_pack(const uint8_t* codes, int64_t n_investors, int32_t horizon, int64_t ld_codes,
                              uint8_t* packed, int64_t ld_packed, void* stream) {
+  return b200_lev_pack_bits(codes, n_investors, horizon, ld_codes, packed, ld_packed, 2, stream);
+}
+
+extern "C" int b200_lev_pack_bits(const uint8_t* codes, int64_t n_investors, int32_t horizon, int64_t ld_codes,
+                                  uint8_t* packed, int64_t ld_packed, int32_t bits, void* stream) {
   B200_REQUIRE(n_investors >= 0 && horizon >= 1, "lev_pack: need n_investors >= 0 and horizon >= 1");
+  B200_REQUIRE(bits == 1 || bits == 2, "lev_pack: bits must be 1 or 2");
   if (n_investors == 0) return 0;
   B200_REQUIRE(codes != nullptr && packed != nullptr, "lev_pack: NULL buffer");
   B200_REQUIRE(ld_codes >= horizon, "lev_pack: ld_codes < horizon");
+  if (bits == 1) {
+    B200_REQUIRE(ld_packed >= ((int64_t)horizon + 7) / 8, "lev_pack: ld_packed < ceil(horizon/8)");
+    const int64_t words = n_investors * ((ld_packed + 3) >> 2);
+    const int64_t blocks = (words + 255) / 256;
+    B200_REQUIRE(blocks <= 0x7fffffff, "lev_pack: too many rows for one launch");
+    pack_bits1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, ld_codes, horizon, n_investors, packed,
+                                                                           ld_packed);
+    return check_cuda(cudaGetLastError(), "lev_pack launch");
+  }
   B200_REQUIRE(ld_packed >= ((int64_t)horizon + 3) / 4, "lev_pack: ld_packed < ceil(horizon/4)");
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
@@ -986,7 +1083,8 @@ extern "C" int b200_lev_chunk(const b200_lev_desc* desc, const void* outcomes, c
   if (d.n_investors == 0) return 0;
   if (d.kind == B200_LEV_DISCRETE) {
     B200_REQUIRE(d.mode == B200_MODE_CHAIN, "lev_chunk: discrete chunks run in CHAIN mode");
-    B200_REQUIRE(d.outcome_bits != 2 || d.source == B200_SRC_PHILOX, "lev_chunk: the CHAIN kernels take uint8 codes");
+    B200_REQUIRE((d.outcome_bits != 2 && d.outcome_bits != 1) || d.source == B200_SRC_PHILOX,
+                 "lev_chunk: the CHAIN kernels take uint8 codes");
     B200_REQUIRE(d.source != B200_SRC_PHILOX || (t_begin & 3) == 0, "lev_chunk: Philox chunks start at a multiple of 4");
     float* stf = (float*)state;
     return run_chain_discrete(d, (const uint8_t*)outcomes, factors, t_begin, t_end, t_begin > 0 ? stf : nullptr, stf,

@@ -124,13 +124,27 @@ __global__ void __launch_bounds__(1024)
 replay_commit_kernel(const b200_replay_desc d, const uint8_t* __restrict__ done, int64_t count, int64_t position) {
   __shared__ long long s_cnt[32], s_first[32], s_last[32];
   long long cnt = 0, first = (1ll << 62), last = -1;
-  for (int64_t k = threadIdx.x; k < count; k += blockDim.x) {
-    if (done[k]) {
-      ++cnt;
-      first = min(first, (long long)k);
-      last = max(last, (long long)k);
-    }
+  // 16 flags per load (the flag array of a bulk append is a million bytes: byte loads made this one block
+  // 2.5x as long as the row-store kernel it follows); head / tail bytes around the aligned body
+  const uintptr_t addr = (uintptr_t)done;
+  int64_t head = (int64_t)((16 - (addr & 15)) & 15);
+  if (head > count) head = count;
+  const int64_t body = (count - head) >> 4;
+  auto flag = [&](int64_t k, uint32_t v) {
+    if (v) { ++cnt; first = min(first, (long long)k); last = max(last, (long long)k); }
+  };
+  for (int64_t k = threadIdx.x; k < head; k += blockDim.x) flag(k, done[k]);
+  const uint4* __restrict__ q = reinterpret_cast<const uint4*>(done + head);
+  for (int64_t i = threadIdx.x; i < body; i += blockDim.x) {
+    const uint4 v = q[i];
+    if ((v.x | v.y | v.z | v.w) == 0u) continue;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) flag(head + i * 16 + c * 4 + b, (w[c] >> (8 * b)) & 0xffu);
   }
+  for (int64_t k = head + body * 16 + threadIdx.x; k < count; k += blockDim.x) flag(k, done[k]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);

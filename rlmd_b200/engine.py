@@ -106,20 +106,24 @@ def encode_codes(outcomes, device=None, n_outcomes: int = 4, chunk_bytes: int = 
 
 class PackedCodes:
     """
-    Discrete outcomes at two bits each: `data` is uint8 [N, ld] (CUDA, or pinned
-    host memory for lev_final_host), four codes per byte - step t of a row in byte
+    Discrete outcomes at two bits each (`bits` = 2): `data` is uint8 [N, ld] (CUDA, or
+    pinned host memory for the host paths), four codes per byte - step t of a row in byte
     t >> 2, bits 2*(t&3)..+1 - with ld = ceil(H/4) rounded up to 16 bytes and zero
     pad bits.  A die roll carries 1.25 bits: the LOG sweep, which is bound by the
     read of the outcome array, moves a quarter of the bytes (the CHAIN kernels,
     bound by instruction issue, take uint8 codes).
+    `bits` = 1: the coin's format, ONE bit per flip (K = 2; step t in byte t >> 3, bit t & 7,
+    ld = ceil(H/8) rounded up to 16): half the bytes again.
     """
 
-    def __init__(self, data: torch.Tensor, horizon: int):
+    def __init__(self, data: torch.Tensor, horizon: int, bits: int = 2):
+        if bits not in (1, 2):
+            raise ValueError("bits must be 1 or 2")
         if data.dtype != torch.uint8 or data.dim() != 2 or (data.shape[0] > 1 and data.stride(1) != 1):
             raise ValueError("packed outcomes are a uint8 [N, ld] tensor with unit inner stride")
-        if data.shape[1] * 4 < horizon:
-            raise ValueError("packed outcomes: fewer than ceil(horizon/4) bytes per row")
-        self.data, self.horizon = data, int(horizon)
+        if data.shape[1] * (8 // bits) < horizon:
+            raise ValueError("packed outcomes: fewer than ceil(horizon * bits / 8) bytes per row")
+        self.data, self.horizon, self.bits = data, int(horizon), int(bits)
 
     @property
     def shape(self):
@@ -128,23 +132,24 @@ class PackedCodes:
     def unpack(self) -> torch.Tensor:
         """uint8 codes [N,H] (torch ops; for tests and one-off conversions)."""
         d = self.data
-        sh = torch.arange(0, 8, 2, device=d.device, dtype=torch.uint8)
-        codes = (d.unsqueeze(-1) >> sh) & 3
+        sh = torch.arange(0, 8, self.bits, device=d.device, dtype=torch.uint8)
+        codes = (d.unsqueeze(-1) >> sh) & ((1 << self.bits) - 1)
         return codes.reshape(d.shape[0], -1)[:, : self.horizon].contiguous()
 
 
-def pack_codes(codes: torch.Tensor) -> PackedCodes:
-    """uint8 codes [N,H] on the GPU (encode_codes / lev_draw) -> PackedCodes (b200_lev_pack)."""
+def pack_codes(codes: torch.Tensor, bits: int = 2) -> PackedCodes:
+    """uint8 codes [N,H] on the GPU (encode_codes / lev_draw) -> PackedCodes (b200_lev_pack_bits)."""
     require_cuda()
     if not codes.is_cuda or codes.dtype != torch.uint8 or codes.dim() != 2 or codes.stride(1) != 1:
         raise ValueError("codes must be a [N,H] uint8 CUDA tensor with unit inner stride")
     n, h = codes.shape
-    ldb = _round_up((h + 3) // 4, 16)
+    per = 8 // int(bits)
+    ldb = _round_up((h + per - 1) // per, 16)
     out = torch.empty((n, ldb), dtype=torch.uint8, device=codes.device)
     ld = codes.stride(0) if n > 1 else max(codes.stride(0), h)
     with torch.cuda.device(codes.device):
-        check(lib.b200_lev_pack(ptr(codes), n, h, ld, ptr(out), ldb, stream_ptr()))
-    return PackedCodes(out, h)
+        check(lib.b200_lev_pack_bits(ptr(codes), n, h, ld, ptr(out), ldb, int(bits), stream_ptr()))
+    return PackedCodes(out, h, int(bits))
 
 
 def encode_returns(x, device=None, chunk_bytes: int = 256 << 20) -> torch.Tensor:
@@ -294,8 +299,9 @@ def lev_grid_sweep(factors: np.ndarray, value_0: float, outcomes, *, want_log_w:
 
 
 def lev_draw(kind: str, n_investors: int, horizon: int, *, seed: int = 0, investor_offset: int = 0,
-             probs=None, log_mean: float = 0.0, sigma: float = 0.0, device="cuda", packed: bool = False):
-    """The outcome array a Philox sweep with the same arguments consumes (packed=True: PackedCodes)."""
+             probs=None, log_mean: float = 0.0, sigma: float = 0.0, device="cuda", packed: bool = False, bits: int = 2):
+    """The outcome array a Philox sweep with the same arguments consumes (packed=True: PackedCodes of `bits`
+    bits per outcome - 1 for a two-outcome gamble's one-bit format)."""
     require_cuda()
     d = LevDesc()
     d.n_investors, d.horizon = int(n_investors), int(horizon)
@@ -306,8 +312,11 @@ def lev_draw(kind: str, n_investors: int, horizon: int, *, seed: int = 0, invest
         for i, v in enumerate(philox_thresholds(probs)):
             d.thresholds[i] = v
         if packed:
-            ld = _round_up((horizon + 3) // 4, 16)
-            d.outcome_bits = 2
+            if bits == 1 and len(probs) != 2:
+                raise ValueError("one bit per outcome needs a two-outcome gamble")
+            per = 8 // int(bits)
+            ld = _round_up((horizon + per - 1) // per, 16)
+            d.outcome_bits = int(bits)
         else:
             ld = _round_up(horizon, 16)
         out = torch.zeros((n_investors, ld), dtype=torch.uint8, device=device)
@@ -321,7 +330,7 @@ def lev_draw(kind: str, n_investors: int, horizon: int, *, seed: int = 0, invest
     with torch.cuda.device(out.device):
         check(lib.b200_lev_draw(C.byref(d), ptr(out), stream_ptr()))
     if packed:
-        return PackedCodes(out, horizon)
+        return PackedCodes(out, horizon, int(bits))
     return out[:, :horizon]
 
 
@@ -350,7 +359,7 @@ def _fill_desc(kind, f, value_0, outcomes, n_investors, horizon, mode, seed, inv
         if not outcomes.data.is_cuda:
             raise ValueError("outcomes must live on the GPU")
         n, h = outcomes.shape
-        d.source, d.outcome_bits = _lib.SRC_STREAM, 2
+        d.source, d.outcome_bits = _lib.SRC_STREAM, outcomes.bits
         d.ld_outcomes = outcomes.data.stride(0) if n > 1 else outcomes.data.shape[1]
         dev = outcomes.data.device
     elif outcomes is not None:
@@ -521,7 +530,7 @@ def lev_final_host(kind: str, factors: np.ndarray, value_0: float, top: int, out
                 b[:rows, :w].copy_(host[r0:r0 + rows], non_blocking=True)
                 ready[i & 1].record(copy)
             comp.wait_event(ready[i & 1])
-            oc = PackedCodes(b[:rows], h) if packed else b[:rows, :h]
+            oc = PackedCodes(b[:rows], h, outcomes_host.bits) if packed else b[:rows, :h]
             lev_sweep(kind, f, value_0, outcomes=oc, mode=mode, variant=variant, out_data_T=data_T[:, r0:r0 + rows],
                       final_only=final_only)
             done[i & 1].record(comp)

@@ -94,20 +94,29 @@ def grid2d_factor_table(a, b, returns, sh_returns) -> np.ndarray:
 
 
 # -------------------------------------------------------------- plumbing
-def dice_sh_grid2d(device, outcomes, top, value_0, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r, a_grid, b_grid):
+def dice_sh_grid2d(device, outcomes, top, value_0, up_r, down_r, mid_r, sh_up_r, sh_down_r, sh_mid_r, a_grid, b_grid,
+                   want_data_T: bool = True):
     """
     Engine-only (BASELINE's 2-D grid of lev/dice_roll_sh.py): the final-time sweep of
     dice_sh_fixed_final_lev (lev/lev_exp.py:1121-1206) with the two coefficients of its factor
     `1 + l r_k + (1-l) sh_k` (:1160-1166) set free - m = (1 + a r_k) + b sh_k over a_grid x b_grid.
     One pass over the outcomes whatever the grid size (counts), then wealth and the reference's 12
     statistics per grid point.  Returns (stats [La,Lb,12] float64 CUDA, data_T [La,Lb,N] fp32 CUDA);
-    the reference's 1-D grid is the line b = 1 - a.
+    the reference's 1-D grid is the line b = 1 - a.  want_data_T=False: the statistics come from the
+    tally of count tuples (engine.lev_final_stats: no [G,N] array at all) and data_T is None.
     """
     a = np.asarray(a_grid, dtype=np.float32).reshape(-1)
     b = np.asarray(b_grid, dtype=np.float32).reshape(-1)
     # point (i, j) = (a_i, b_j), row-major
     table = grid2d_factor_table(np.repeat(a, len(b)), np.tile(b, len(a)), (up_r, down_r, mid_r),
                                 (sh_up_r, sh_down_r, sh_mid_r))
+    if not want_data_T:
+        n = outcomes.shape[0]
+        data = outcomes.data if isinstance(outcomes, engine.PackedCodes) else outcomes
+        dev = data.device if isinstance(data, T.Tensor) and data.is_cuda else engine._cuda_device(device)
+        stats = engine.lev_final_stats(table, _as_float(value_0), _as_int(top), outcomes, device=dev, group=_GROUP,
+                                       n_total=_n_total(n, dev))
+        return stats.view(len(a), len(b), 12), None
     codes = outcomes if isinstance(outcomes, engine.PackedCodes) else _codes(outcomes, 3, device)
     res = engine.lev_grid_sweep(table, _as_float(value_0), codes)
     data_T = res["data_T"]

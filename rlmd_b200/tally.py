@@ -159,7 +159,7 @@ class FinalTally:
                 d.kind, d.mode, d.source = _lib.LEV_DISCRETE, _lib.MODE_LOG, _lib.SRC_STREAM
                 d.n_investors, d.horizon, d.n_grid, d.n_outcomes = n, h, 1, k
                 d.value_0 = 1.0
-                d.outcome_bits = 2 if packed else 8
+                d.outcome_bits = outcomes.bits if packed else 8
                 d.ld_outcomes = data.stride(0) if n > 1 else data.shape[1]
                 check(lib.b200_lev_tally(C.byref(d), ptr(data), C.byref(self.plan), ptr(self.ws), ptr(counts),
                                          stream_ptr()))
@@ -222,7 +222,7 @@ class FinalTally:
                     b[:m].copy_(src[r0:r0 + m], non_blocking=True)
                     ready[i & 1].record(copy)
                 comp.wait_event(ready[i & 1])
-                self.add(PackedCodes(b[:m], h) if packed else b[:m], n_outcomes)
+                self.add(PackedCodes(b[:m], h, host.bits) if packed else b[:m], n_outcomes)
                 done[i & 1].record(comp)
             copy.wait_event(done[0])
             copy.wait_event(done[1])

@@ -172,7 +172,48 @@ def test_grid_of_any_size_from_one_pass_over_the_outcomes(eng):
     want_stats = np.stack([lo.summary_stats(res["data_T"][g].cpu().numpy(), top) for g in range(72)]).reshape(9, 8, 12)
     assert np.array_equal(stats.cpu().numpy()[..., 9:12], want_stats[..., 9:12])
     assert np.allclose(stats.cpu().numpy()[..., :9], want_stats[..., :9], rtol=1e-10)
+    # the same grid from the tally of count tuples (no data_T): identical order statistics, fp64 moments
+    for oc in (torch.as_tensor(c.astype(np.int64)), eng.pack_codes(codes)):
+        st2, none = lev_exp.dice_sh_grid2d("cuda", oc, top, 100.0, *r, *sh, a, b, want_data_T=False)
+        assert none is None and tuple(st2.shape) == (9, 8, 12)
+        assert torch.equal(st2[..., 9:12], stats[..., 9:12])
+        assert torch.allclose(st2, stats, rtol=1e-12, atol=0)
     # the reference's own 1-D dice_sh grid is the line b = 1 - a of this family
     lev = np.float32([0.73, 0.85, 1.0])
     line = lev_exp.grid2d_factor_table(lev, (np.float32(1) - lev).astype(np.float32), r, sh)
     assert np.array_equal(line, lev_exp.dice_sh_factor_table(lev, *r, *sh))
+
+
+def test_one_bit_coin_format(eng):
+    """The coin at one bit per flip: pack / draw / LOG sweep / tally agree with the uint8 route, ragged sizes."""
+    from rlmd_b200 import lev_exp
+
+    rs = np.random.RandomState(3)
+    lev = lo.lev_grid(0.1, 1.0, 0.1, 0.5, -0.4)
+    f = lo.coin_factors(lev, 0.5, -0.4)
+    for n, h in ((2001, 3000), (37, 41), (5, 8), (130, 1)):
+        c = (rs.random_sample((n, h)) < 0.5).astype(np.uint8)
+        codes = eng.encode_codes(c)
+        p1 = eng.pack_codes(codes, bits=1)
+        assert p1.bits == 1 and p1.data.shape[1] % 16 == 0 and p1.data.shape[1] * 8 >= h
+        assert np.array_equal(p1.unpack().cpu().numpy(), c)
+        # bit t & 7 of byte t >> 3
+        want = np.packbits(c, axis=1, bitorder="little")
+        assert np.array_equal(p1.data.cpu().numpy()[:, : want.shape[1]], want)
+        a = eng.lev_sweep("discrete", f, 100.0, outcomes=codes, mode="log", want_log_w=True, want_counts=True)
+        b = eng.lev_sweep("discrete", f, 100.0, outcomes=p1, mode="log", want_log_w=True, want_counts=True)
+        assert torch.equal(a["counts"], b["counts"]) and torch.equal(a["log_w"], b["log_w"])
+        assert torch.equal(a["data_T"].view(torch.int32), b["data_T"].view(torch.int32))
+        assert np.array_equal(b["counts"].cpu().numpy(), lo.counts_discrete(c, 2))
+        if n > 4:
+            s_a = eng.lev_final_stats(f, 100.0, 2, codes).cpu().numpy()
+            s_b = eng.lev_final_stats(f, 100.0, 2, p1).cpu().numpy()
+            assert np.array_equal(s_a[:, 9:12], s_b[:, 9:12]) and np.allclose(s_a, s_b, rtol=1e-13, equal_nan=True)
+    # the Philox draw in the one-bit format is the uint8 draw, packed
+    d8 = eng.lev_draw("discrete", 1000, 333, seed=9, probs=(0.4, 0.6))
+    d1 = eng.lev_draw("discrete", 1000, 333, seed=9, probs=(0.4, 0.6), packed=True, bits=1)
+    assert torch.equal(d1.unpack(), d8)
+    with pytest.raises(Exception):
+        eng.lev_draw("discrete", 10, 10, seed=1, probs=(1 / 6, 1 / 6, 2 / 3), packed=True, bits=1)
+    with pytest.raises(Exception):      # three outcomes do not fit one bit
+        eng.lev_sweep("discrete", lo.dice_factors(lev, 0.5, -0.5, 0.05), 100.0, outcomes=d1, mode="log")
