@@ -226,3 +226,39 @@ def test_replay_full_buffer_nstep_targets_recomputed_by_torch():
     assert torch.equal(s.reshape(-1, 5)[inner], buf.next_state_memory[first.clamp(0, mem - 1)][inner])
     assert torch.equal(s2.reshape(-1, 5), buf.next_state_memory[idx])
     assert torch.equal(d.reshape(-1), term[idx])
+
+
+def test_tally_path_at_full_size(c2):
+    """C2 through the route the drop-in functions take: count kernel with the tally sink -> distinct count
+    tuples -> cluster select.  Size-independent properties: the bins are exactly the distinct rows of the
+    count matrix and their weights add up to N; the order statistics are those of the sweep's data_T
+    (torch.sort), bit for bit; the moments agree with the row-statistics path to fp64 rounding; the uint8,
+    the packed and the int64 (reference dtype, ingest kernel) forms of the outcomes give the same answer."""
+    from rlmd_b200 import tally
+    eng = c2["engine"]
+    table, codes = c2["table"], c2["codes"]
+    t = tally.FinalTally(N)
+    t.add(codes, 3)
+    t.finalize()
+    st = t.stats(table, V0, H, n_total=N, top=TOP)
+    info = t.check()
+    counts = c2["log"]["counts"]
+    key = counts[:, 1].long() * (H + 1) + counts[:, 2].long()
+    assert info["bins"] == int(torch.unique(key).numel())
+    rows = eng.rowstats(c2["log"]["data_T"], TOP)
+    assert torch.equal(st[:, 9:12], rows[:, 9:12])
+    fin = torch.isfinite(rows)
+    assert torch.equal(torch.isnan(st), torch.isnan(rows))
+    assert float(((st[fin] - rows[fin]).abs() / rows[fin].abs().clamp_min(1e-300)).max()) <= 1e-12
+    srt = torch.sort(c2["log"]["data_T"][3])[0]
+    assert float(st[3, 9]) == float(srt[(N - 1) // 2]) and float(st[3, 10]) == float(srt[N - TOP + (TOP - 1) // 2])
+    packed = eng.pack_codes(codes)
+    st_p = eng.lev_final_stats(table, V0, TOP, packed)
+    assert torch.equal(st_p[:, 9:12], st[:, 9:12]) and torch.allclose(st_p, st, rtol=1e-12, atol=0, equal_nan=True)
+    # the reference's dtype for a slice of the investors (8 B per roll: 2e5 rows = 16 GB)
+    n_s = 200_000
+    wide = codes[:n_s].to(torch.int64)
+    a = eng.lev_final_stats(table, V0, 20, wide)
+    del wide
+    b = eng.lev_final_stats(table, V0, 20, codes[:n_s])
+    assert torch.equal(a[:, 9:12], b[:, 9:12]) and torch.allclose(a, b, rtol=1e-12, atol=0, equal_nan=True)

@@ -96,3 +96,26 @@ def test_gbm_state_summary_equals_row_summary():
         # log wealth rebuilt from the state is the sweep's log wealth
         lw = np.log(100.0) + lev.astype(np.float64)[:, None] * b["state"][0].cpu().numpy()[None, :]
         np.testing.assert_allclose(lw, a["log_w"].cpu().numpy(), rtol=1e-15, atol=1e-13)
+
+
+@pytest.mark.parametrize("depth", [1, 2])
+def test_gbm_philox_pipeline_equals_direct_calls(depth):
+    """FinalSweepPipeline.submit_philox (sweep on one stream, statistics + growth summaries on another) returns
+    what the direct calls return, step after step, at either depth."""
+    import torch
+    from rlmd_b200 import engine, lev_exp
+    n, h, top = 50_021, 300, 5
+    lev = np.asarray(lev_exp.param_range(-1.0, 1.0, 0.2), dtype=np.float32)
+    pipe = engine.FinalSweepPipeline("gbm", lev, 100.0, top, depth=depth)
+    assert pipe.depth == depth
+    got = [pipe.submit_philox(n, h, seed=40 + i, log_mean=-0.05, sigma=0.447) for i in range(4)]
+    pipe.synchronize()
+    for i, (st, gr) in enumerate(got):
+        res = engine.lev_sweep("gbm", lev, 100.0, n_investors=n, horizon=h, seed=40 + i, log_mean=-0.05, sigma=0.447,
+                               mode="log", want_state=True)
+        want_st = engine.rowstats(res["data_T"], top)
+        want_gr = engine.gbm_growth_summary(res["state"], lev, h, 100.0, data_T=res["data_T"])
+        assert torch.equal(st[:, 9:12], want_st[:, 9:12]) and torch.allclose(st, want_st, rtol=1e-12, atol=0, equal_nan=True)
+        assert torch.equal(gr[:, 0], want_gr[:, 0]) and torch.allclose(gr, want_gr, rtol=1e-12, atol=0, equal_nan=True)
+    assert engine.FinalSweepPipeline("gbm", lev, 100.0, top).depth == 2       # the GBM default
+    assert engine.FinalSweepPipeline("discrete", np.ones((2, 2), np.float32), 100.0, top).depth == 1
