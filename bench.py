@@ -306,11 +306,13 @@ def run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world, hbm_peak, 
         rb.store_batch(st, st[:, :1], 1 + 0.01 * st[:, 0], st, torch.as_tensor(done, device=dev))
         t1 = _event_time(torch, lambda: rb.sample_exp(), 5, 50)
         tk = _event_time(torch, lambda: rb.sample_many(1024), 2, 10)
+        idx_k = rb.sample_many(1024)[0].reshape(-1).clone()        # the same launch with the slots supplied:
+        tgat = _event_time(torch, lambda: rb.sample_many(1024, batches=idx_k), 2, 10)   # the gather kernel alone
         tg = None
         if hasattr(rb, "capture_sampler"):
             run = rb.capture_sampler()
             tg = _event_time(torch, run, 5, 200)
-        times += [t1, tk, tg if tg is not None else 0.0]
+        times += [t1, tk, tg if tg is not None else 0.0, tgat]
         del rb, st
     env = envs.Coin_InvA(1, n_envs=1, seed=1, device=dev)
     col = collector.Collector(env, 100_000, {"mini_batch_size": batch, "discount": 0.99, "multi_steps": 5,
@@ -330,19 +332,26 @@ def run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world, hbm_peak, 
         }
     ns = (1, 5, 10)
     bytes_per_sample = {1: 106, 5: 114 + 4 * 4, 10: 114 + 4 * 9}
-    bulk = {n: 1024 * batch / times[base + 3 * i + 1] for i, n in enumerate(ns)}
+    bulk = {n: 1024 * batch / times[base + 4 * i + 1] for i, n in enumerate(ns)}
+    gath = {n: 1024 * batch / times[base + 4 * i + 3] for i, n in enumerate(ns)}
     out["replay_nstep_sampling"] = {
         "unit": "samples/s", "buffer": mem, "batch": batch, "per_gpu": True,
-        "per_call": {str(n): batch / times[base + 3 * i] for i, n in enumerate(ns)},
-        "per_call_us": {str(n): times[base + 3 * i] * 1e6 for i, n in enumerate(ns)},
-        "graph_replay_us": {str(n): times[base + 3 * i + 2] * 1e6 for i, n in enumerate(ns)
-                            if times[base + 3 * i + 2] > 0},
+        "per_call": {str(n): batch / times[base + 4 * i] for i, n in enumerate(ns)},
+        "per_call_us": {str(n): times[base + 4 * i] * 1e6 for i, n in enumerate(ns)},
+        "graph_replay_us": {str(n): times[base + 4 * i + 2] * 1e6 for i, n in enumerate(ns)
+                            if times[base + 4 * i + 2] > 0},
         "1024_batches_per_launch": {str(n): bulk[n] for n in ns},
+        "1024_batches_gather_only": {str(n): gath[n] for n in ns},
         "roofline": {str(n): {"bound": "hbm", "kernel": "replay_draw_kernel + replay_gather_thread_kernel",
                               "achieved": bulk[n] * bytes_per_sample[n] / 1e9, "peak": hbm_peak, "unit": "GB/s",
                               "frac": bulk[n] * bytes_per_sample[n] / 1e9 / hbm_peak, "traffic": None,
                               "algorithmic_bytes_per_sample": bytes_per_sample[n],
-                              "note": "random 20-byte rows of a 52 MB buffer: L2-resident, sector-amplified"}
+                              "gather_only": {"achieved": gath[n] * bytes_per_sample[n] / 1e9,
+                                              "frac": gath[n] * bytes_per_sample[n] / 1e9 / hbm_peak},
+                              "note": "draw + gather of 1024 x 256 samples per launch (the distinct-slot draw - Philox + "
+                                      "a shared-memory hash set per mini-batch - is the larger part); gather_only: the "
+                                      "same launch with the slots supplied.  Random 20-byte rows of a 52 MB buffer: "
+                                      "L2-resident, sector-amplified"}
                      for n in ns},
     }
     out["collector_graph_coin_invA"] = {

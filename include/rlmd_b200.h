@@ -552,27 +552,37 @@ int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealt
  * ------------------------------------------------------------------ */
 /* The same exchange WITHOUT a collective library, for the GPUs of one node: the
  * ranks' workspaces (and small flag blocks) live in memory every process has
- * mapped (CUDA IPC / torch symmetric memory).  A rank flags each finished pass
- * in its peers' flag blocks; a gather kernel then waits for the world's flags and
- * sums the peers' partial histograms straight out of their memory over NVLink
- * (system-scope vector loads, every rank in the same order) into local scratch
- * that the resolve kernel walks.
+ * mapped (CUDA IPC / torch symmetric memory).  Rows are owned round-robin
+ * (row % world).  After each pass a rank pushes every row's partial sums into the
+ * staging area of the row's owner (posted stores over NVLink) and flags its peers;
+ * the owner waits for the world's flags, sums its rows' partials (ranks in the same
+ * order) into shared memory, resolves them there and stores the few resolved words
+ * - finally the 12 statistics - into every rank's workspace: a histogram crosses
+ * NVLink once, and all ranks end with bit-identical statistics.
+ *   stage[r]     : rank r's staging area, b200_rowstats_stage_bytes(rows, world) bytes:
+ *                  [source rank][stage_rows][words]; alternates with the workspaces
  *   workspace[r] : rank r's rowstats workspace as mapped HERE (>= workspace_bytes(rows))
- *   flags[r]     : rank r's flag block, uint32 [B200_MAX_PEERS * 4 + 1], zeroed once;
- *                  word B200_MAX_PEERS*4 of the own block is set when a peer's flag
- *                  did not arrive within ~60 s (the statistics are then NaN)
+ *   flags[r]     : rank r's flag block, uint32 [B200_PEER_FLAG_WORDS], zeroed once;
+ *                  word B200_PEER_FLAG_ERROR_WORD of the own block is set when a peer's
+ *                  flag did not arrive within ~60 s (the statistics are then NaN)
+ *   sums         : unused (kept for layout compatibility)
  *   epoch        : 1, 2, 3, ... - one more per call, the same on every rank; successive
  *                  calls must alternate between two workspaces (a peer may still be
  *                  reading the previous call's sums)
  * Runs the whole statistic block (all passes) on `stream`. */
+#define B200_PEER_FLAG_ERROR_WORD (B200_MAX_PEERS * 8)
+#define B200_PEER_FLAG_WORDS 128
 typedef struct b200_peer_set {
   void* workspace[B200_MAX_PEERS];
   uint32_t* flags[B200_MAX_PEERS];
-  void* sums;   /* LOCAL scratch of workspace_bytes(rows): the cross-GPU sums of the step being resolved */
+  void* sums;   /* unused */
+  void* stage[B200_MAX_PEERS];   /* rank r's staging area as mapped HERE (b200_rowstats_stage_bytes) */
+  int64_t stage_rows;            /* owned rows a staging area holds per source rank: >= ceil(rows / world) */
   int32_t world, rank;
   uint32_t epoch;
   uint32_t reserved;
 } b200_peer_set;
+int64_t b200_rowstats_stage_bytes(int64_t rows, int32_t world);
 int b200_rowstats_p2p(const float* values, int64_t rows, int64_t n, int64_t ld,
                       int64_t n_total, int64_t top, const b200_peer_set* peers,
                       double* stats, void* stream);

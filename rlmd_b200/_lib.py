@@ -50,6 +50,8 @@ class PeerSet(C.Structure):
         ("workspace", C.c_void_p * MAX_PEERS),
         ("flags", C.c_void_p * MAX_PEERS),
         ("sums", C.c_void_p),
+        ("stage", C.c_void_p * MAX_PEERS),
+        ("stage_rows", C.c_int64),
         ("world", C.c_int32),
         ("rank", C.c_int32),
         ("epoch", C.c_uint32),
@@ -241,6 +243,7 @@ _SIGNATURES = {
     "b200_tally_stats": (C.c_int, [C.POINTER(TallyPlan), _vp, C.POINTER(LevDesc), C.POINTER(C.c_float), _i64, _i64,
                                    _vp, _vp]),
     "b200_rowstats_workspace_bytes": (_i64, [_i64]),
+    "b200_rowstats_stage_bytes": (_i64, [_i64, _i32]),
     "b200_rowstats": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "b200_rowstats_exchange": (C.c_int, [_i32, C.POINTER(_i64)]),
     "b200_rowstats_p2p": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, C.POINTER(PeerSet), _vp, _vp]),

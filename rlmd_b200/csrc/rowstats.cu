@@ -28,6 +28,8 @@
 // 8-byte words so that a multi-GPU caller can all-reduce it between passes.
 #include <algorithm>
 #include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -67,6 +69,7 @@ struct RowWS {
   long long has_nan[3];     // all / top / adj group holds a NaN (torch.median -> nan)
   long long key_mode;       // KEY_FULL / KEY_NO_NAN / KEY_POSITIVE for passes 1..3 (from hist1)
   long long pad_r[2];
+  double stats_out[12];     // multi-GPU: the row's statistics as its owner rank resolved them (step 3)
 };
 static_assert(sizeof(RowWS) % 16 == 0, "8-byte words, rows 16-byte aligned (the peer gather loads word pairs)");
 static_assert(offsetof(RowWS, hist1) == 16 * 8 && offsetof(RowWS, cnt_gt) == (16 + L1_BINS + NT * L2_BINS) * 8 &&
@@ -292,112 +295,6 @@ rowstats_pass_kernel(const float* __restrict__ values, int64_t n, int64_t ld, Ro
   else rowstats_pass_body<PASS, KEY_FULL>(v, n, w, smem_hist);
 }
 
-// ----------------------------------------------------------------------------
-// Multi-GPU without a collective library: every rank's workspace is mapped into
-// every process (CUDA IPC / symmetric memory), a rank raises a flag in each
-// peer's flag block when one of its passes is complete, and the resolve kernel
-// that follows waits for the world's flags and then SUMS the peers' partial
-// histograms and sums straight out of their memory over NVLink - the all-reduce
-// is fused into the kernel that consumes it.  Every rank adds the ranks in the
-// same order, so all of them resolve bit-identical thresholds and means.
-struct PeerSet {
-  RowWS* ws[B200_MAX_PEERS];            // [rank] is this rank's own workspace
-  uint32_t* flags[B200_MAX_PEERS];      // flag blocks: uint32 [B200_MAX_PEERS][4] + 1 error word
-  int32_t world, rank;
-  uint32_t epoch;
-};
-constexpr int FLAG_ERROR_WORD = B200_MAX_PEERS * 4;
-
-__device__ __forceinline__ long long ld_sys(const long long* p) {
-  long long v;
-  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double ld_sys(const double* p) {
-  return __longlong_as_double(ld_sys(reinterpret_cast<const long long*>(p)));
-}
-
-// One warp: tells every peer that this rank's pass `phase` of call `epoch` is in memory.
-__global__ void rowstats_signal_kernel(const __grid_constant__ PeerSet P, int phase) {
-  const int r = threadIdx.x;
-  if (r >= P.world || r == P.rank) return;
-  __threadfence_system();
-  uint32_t* f = P.flags[r] + P.rank * 4 + phase;
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(P.epoch) : "memory");
-}
-
-// Block-wide wait for the peers' flags of `phase`; false after ~60 s (a peer died):
-// the caller then writes NaN statistics instead of hanging the device.
-__device__ bool wait_peers(const PeerSet& P, int phase) {
-  __shared__ int ok_s;
-  if (threadIdx.x == 0) {
-    int ok = 1;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (int r = 0; r < P.world && ok; ++r) {
-      if (r == P.rank) continue;
-      const uint32_t* f = P.flags[P.rank] + r * 4 + phase;
-      for (;;) {
-        uint32_t v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        if ((int32_t)(v - P.epoch) >= 0) break;
-        __nanosleep(200);
-        unsigned long long t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 60000000000ull) { ok = 0; break; }
-      }
-    }
-    if (!ok) P.flags[P.rank][FLAG_ERROR_WORD] = 1u;
-    ok_s = ok;
-  }
-  __syncthreads();
-  return ok_s != 0;
-}
-
-// vector load of two 8-byte words, system scope
-__device__ __forceinline__ void ld_sys_v2(const long long* p, long long& a, long long& b) {
-  asm volatile("ld.relaxed.sys.global.v2.s64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-}
-
-// The cross-GPU sum of one step's exchange region (the words b200_rowstats_exchange
-// names), written to this rank's `gsum` workspace for the resolve kernel that
-// follows.  grid = (slices, rows), 256 threads, two words per thread: all of a
-// thread's loads - one 16-byte vector per rank - are in flight together, so a row's
-// region costs about one NVLink round trip.  Integer words are added, double
-// words are added in rank order (the same order on every rank).
-template <int STEP>
-__global__ void __launch_bounds__(256)
-rowstats_gather_kernel(const __grid_constant__ PeerSet P, RowWS* __restrict__ gsum) {
-  constexpr int64_t IOFF = STEP == 0 ? OFF_H1 : STEP == 1 ? OFF_H2 : OFF_CNT;
-  constexpr int ICNT = STEP == 0 ? L1_BINS : STEP == 1 ? NT * L2_BINS : STEP == 2 ? 8 + NT * L3_BINS : 0;
-  constexpr int DOFF = STEP == 0 ? 0 : STEP == 1 ? 0 : STEP == 2 ? 1 : 3;
-  constexpr int DCNT = STEP == 0 ? 1 : STEP == 1 ? 0 : STEP == 2 ? 2 : 6;
-  const int64_t row = blockIdx.y;
-  if (!wait_peers(P, STEP)) return;   // the error word is set: the final resolve writes NaN
-  long long* dst = reinterpret_cast<long long*>(gsum + row);
-  const int i = (blockIdx.x * 256 + threadIdx.x) * 2;
-  if (i < ICNT) {
-    long long a[B200_MAX_PEERS], b[B200_MAX_PEERS];
-#pragma unroll
-    for (int r = 0; r < B200_MAX_PEERS; ++r)
-      if (r < P.world) ld_sys_v2(reinterpret_cast<const long long*>(P.ws[r] + row) + IOFF + i, a[r], b[r]);
-    long long sa = 0, sb = 0;
-#pragma unroll
-    for (int r = 0; r < B200_MAX_PEERS; ++r)
-      if (r < P.world) { sa += a[r]; sb += b[r]; }
-    dst[IOFF + i] = sa;
-    dst[IOFF + i + 1] = sb;
-  }
-  if (blockIdx.x == 0 && threadIdx.x < DCNT) {
-    double acc = 0.0;
-    for (int r = 0; r < P.world; ++r) {
-      const double v = ld_sys(reinterpret_cast<const double*>(P.ws[r] + row) + DOFF + threadIdx.x);
-      acc = r == 0 ? v : acc + v;
-    }
-    reinterpret_cast<double*>(dst)[DOFF + threadIdx.x] = acc;
-  }
-}
-
 // One block per row: walk a histogram to find the bin that holds `rank`.
 // blockDim.x == 256: each thread sums a contiguous run of bins, a block-wide
 // inclusive scan of the 256 partials (warp shuffles + 8 warp totals) names the
@@ -461,35 +358,21 @@ __device__ __forceinline__ void copy_hist(long long* __restrict__ dst, const lon
 }
 
 // STEP 0: after pass 0   STEP 1: after pass 1   STEP 2: after pass 2 (order
-// statistics, top / adj split and means)   STEP 3: after pass 3 (writes stats)
-// The step's histograms are first summed over the world into shared memory
-// (world == 1: a copy), then walked there.
+// statistics, top / adj split and means)   STEP 3: after pass 3 (writes the 12 statistics)
+// One block (256 threads) per row.  `hs`: the step's histogram(s), summed over the
+// world, in shared memory (STEP 0: hist1, STEP 1: hist2[NT], STEP 2: hist3[NT]);
+// `sd`: the row's 16 leading doubles, summed over the world; `cnt_gt_sum`: cnt_gt
+// likewise (STEP 2).  The resolved prefixes / ranks / means go to `w`.
 template <int STEP>
-__global__ void __launch_bounds__(256)
-rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own, const uint32_t* __restrict__ error_word,
-                        int64_t n_total, int64_t top, double* __restrict__ stats) {
-  extern __shared__ long long hs[];   // STEP 0: hist1, STEP 1: hist2[NT], STEP 2: hist3[NT]
+__device__ void resolve_row(const long long* __restrict__ hs, const double* __restrict__ sd, long long cnt_gt_sum,
+                            RowWS* __restrict__ w, long long n, long long K, double* __restrict__ stats_row) {
   __shared__ long long scratch[256];
   __shared__ double red_d[32];
   __shared__ long long red_i[32];
   __shared__ int bin_s;
   __shared__ long long rem_s;
-  // `sums`: where the pass kernels' sums and histograms are - this rank's own
-  // workspace (one GPU, or all-reduced in place by the caller) or the cross-GPU
-  // sums of rowstats_gather_kernel; `own`: where the resolved prefixes / means go.
-  const int64_t row = blockIdx.x;
-  RowWS* w = own + row;
-  const long long* si = reinterpret_cast<const long long*>(sums + row);
-  const double* sd = reinterpret_cast<const double*>(sums + row);
-  const long long n = n_total, K = top;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-  if (STEP == 3 && error_word != nullptr && *error_word) {   // a peer's flag never arrived
-    if (threadIdx.x < 12) stats[row * 12 + threadIdx.x] = qnan;
-    return;
-  }
-
   if (STEP == 0) {
-    copy_hist<L1_BINS>(hs, si + OFF_H1);
     const long long ranks[NT] = {(n - 1) / 2, n - K, n - K + (K - 1) / 2, (n - K - 1) / 2};
     for (int j = 0; j < NT; ++j) {
       find_bin(hs, L1_BINS, ranks[j], &bin_s, &rem_s, scratch);
@@ -517,7 +400,6 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
       w->has_nan[2] = nan > K;
     }
   } else if (STEP == 1) {
-    copy_hist<NT * L2_BINS>(hs, si + OFF_H2);
     for (int j = 0; j < NT; ++j) {
       find_bin(hs + j * L2_BINS, L2_BINS, w->rank[j], &bin_s, &rem_s, scratch);
       if (threadIdx.x == 0) {
@@ -527,7 +409,6 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
       __syncthreads();
     }
   } else if (STEP == 2) {
-    copy_hist<NT * L3_BINS>(hs, si + OFF_H3);
     for (int j = 0; j < NT; ++j) {
       find_bin(hs + j * L3_BINS, L3_BINS, w->rank[j], &bin_s, &rem_s, scratch);
       if (threadIdx.x == 0) {
@@ -554,7 +435,7 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
     c_gt = block_sum(c_gt, red_i); c_lt = block_sum(c_lt, red_i); c_all = block_sum(c_all, red_i);
     if (threadIdx.x == 0) {
       const double thr = w->value[1];
-      const long long cnt_gt = si[OFF_CNT];
+      const long long cnt_gt = cnt_gt_sum;
       const double coarse_gt = sd[1], coarse_lt = sd[2];
       // below thr's prefix = everything that is neither above it nor inside it
       const long long n_gt = cnt_gt + c_gt, n_lt = (n - cnt_gt - c_all) + c_lt;
@@ -579,7 +460,7 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
       const double sq_top = sqdev_gt + (tt > 0 ? tt * dt * dt : 0.0);
       const double abs_adj = absdev_lt + (ta > 0 ? ta * fabs(da) : 0.0);
       const double sq_adj = sqdev_lt + (ta > 0 ? ta * da * da : 0.0);
-      double* s = stats + row * 12;
+      double* s = stats_row;
       s[0] = w->mean_all; s[1] = w->mean_top; s[2] = w->mean_adj;
       s[3] = absdev_all / (double)n; s[4] = abs_top / (double)K; s[5] = abs_adj / (double)(n - K);
       s[6] = sqrt(sqdev_all / (double)n); s[7] = sqrt(sq_top / (double)K);
@@ -597,6 +478,274 @@ rowstats_resolve_kernel(const RowWS* __restrict__ sums, RowWS* __restrict__ own,
       }
     }
   }
+}
+
+// One GPU (or partial sums all-reduced in place by the caller): grid = rows.
+template <int STEP>
+__global__ void __launch_bounds__(256)
+rowstats_resolve_kernel(RowWS* __restrict__ ws, int64_t n_total, int64_t top, double* __restrict__ stats) {
+  extern __shared__ long long hs[];
+  const int64_t row = blockIdx.x;
+  RowWS* w = ws + row;
+  const long long* si = reinterpret_cast<const long long*>(w);
+  if (STEP == 0) copy_hist<L1_BINS>(hs, si + OFF_H1);
+  if (STEP == 1) copy_hist<NT * L2_BINS>(hs, si + OFF_H2);
+  if (STEP == 2) copy_hist<NT * L3_BINS>(hs, si + OFF_H3);
+  resolve_row<STEP>(hs, reinterpret_cast<const double*>(w), si[OFF_CNT], w, n_total, top, stats + row * 12);
+}
+
+// ----------------------------------------------------------------------------
+// Multi-GPU without a collective library: every rank's workspace is mapped into
+// every process (CUDA IPC / symmetric memory).  Rows are OWNED round-robin
+// (row % world).  After each pass a rank PUSHES the partial sums of every row to
+// the staging area of the row's owner (posted stores: NVLink at line rate, where
+// loads out of a peer's memory were bound by their round trips - 0.25 TB/s
+// measured) and its last block raises a flag at every peer; the owner then sums
+// its rows' partials out of its own memory into shared memory, resolves them there
+// and stores the few resolved words (prefixes, ranks, means, finally the 12
+// statistics) into every rank's workspace.  So a histogram crosses NVLink once (to
+// its owner) instead of once per rank, the resolve work is split over the ranks,
+// and every rank continues from the same resolved words: bit-identical statistics
+// everywhere.  Doubles are added in rank order.
+struct PeerSet {
+  RowWS* ws[B200_MAX_PEERS];            // [rank] is this rank's own workspace
+  uint32_t* flags[B200_MAX_PEERS];      // flag blocks (B200_PEER_FLAG_WORDS uint32 each)
+  long long* stage[B200_MAX_PEERS];     // staging of every rank: [source rank][owned row][STAGE_WORDS]
+  int64_t stage_rows;                   // owned rows the staging holds per source rank
+  int32_t world, rank;
+  uint32_t epoch;
+};
+// A staged row (8-byte words): the 16 leading doubles of the source's RowWS (word 15 carries cnt_gt), then the
+// step's histogram(s) as 32-bit counts.
+constexpr int64_t STAGE_HEAD = 16, STAGE_CNT = 15, STAGE_WORDS = STAGE_HEAD + (int64_t)NT * L2_BINS / 2;
+// Flag block of a rank: for every peer r, words [r][0..3] "r's partial sums of pass p
+// are in memory" and [r][4..7] "the rows r owns are resolved after pass p and stored
+// here"; then the error word, then one block ticket per pass.
+constexpr int FLAG_STRIDE = 8, FLAG_RESOLVED = 4;
+constexpr int FLAG_ERROR_WORD = B200_PEER_FLAG_ERROR_WORD, FLAG_TICKET = FLAG_ERROR_WORD + 1;
+static_assert(FLAG_ERROR_WORD == B200_MAX_PEERS * FLAG_STRIDE && FLAG_TICKET + 4 <= B200_PEER_FLAG_WORDS, "flag block layout");
+
+__device__ __forceinline__ long long ld_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_sys(const double* p) {
+  return __longlong_as_double(ld_sys(reinterpret_cast<const long long*>(p)));
+}
+// vector load of two 8-byte words, system scope
+__device__ __forceinline__ void ld_sys_v2(const long long* p, long long& a, long long& b) {
+  asm volatile("ld.relaxed.sys.global.v2.s64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
+
+// Warp 0 of a block (all 32 lanes call): raises flag `word` of this rank at every peer.
+__device__ __forceinline__ void signal_peers(const PeerSet& P, int word) {
+  const int r = threadIdx.x;
+  if (r < P.world && r != P.rank) {
+    __threadfence_system();
+    uint32_t* f = P.flags[r] + P.rank * FLAG_STRIDE + word;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(P.epoch) : "memory");
+  }
+}
+
+// Block-wide wait for flag `word` of every peer, one lane per peer; false after
+// ~60 s (a peer died) or when an earlier wait already gave up: the error word is
+// set and the call's statistics become NaN instead of the device hanging.
+__device__ bool wait_peers(const PeerSet& P, int word) {
+  __shared__ int ok_s;
+  if (threadIdx.x < 32) {
+    int ok = 1;
+    const int r = threadIdx.x;
+    volatile uint32_t* err = P.flags[P.rank] + FLAG_ERROR_WORD;
+    if (r < P.world && r != P.rank) {
+      const uint32_t* f = P.flags[P.rank] + r * FLAG_STRIDE + word;
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int32_t)(v - P.epoch) >= 0) break;
+        if (*err) { ok = 0; break; }
+        __nanosleep(100);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 60000000000ull) { ok = 0; break; }
+      }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x == 0) {
+      if (!ok) *err = 1u;
+      ok_s = ok;
+    }
+  }
+  __syncthreads();
+  return ok_s != 0;
+}
+
+// Where rank r's partial sums of owned row `row` are on THIS (the owner's) GPU: the own
+// workspace row, or the staged copy the source pushed.  `head`: the doubles; + hist: the histogram words.
+struct RowSource {
+  const long long* head;
+  const long long* hist;
+};
+template <int STEP>
+__device__ __forceinline__ RowSource row_source(const PeerSet& P, int r, int64_t row) {
+  constexpr int64_t IOFF = STEP == 0 ? OFF_H1 : STEP == 1 ? OFF_H2 : OFF_H3;
+  RowSource s;
+  if (r == P.rank) {
+    s.head = reinterpret_cast<const long long*>(P.ws[P.rank] + row);
+    s.hist = s.head + IOFF;
+  } else {
+    s.head = P.stage[P.rank] + ((int64_t)r * P.stage_rows + row / P.world) * STAGE_WORDS;
+    s.hist = s.head + STAGE_HEAD;
+  }
+  return s;
+}
+
+// After pass STEP, before the owners resolve: every row's partial sums to the row's
+// owner.  Blocks stride over the rows; the last block to finish raises this rank's
+// flag at every peer (one system-scope fence per block).
+template <int STEP>
+__global__ void __launch_bounds__(256)
+rowstats_push_kernel(const __grid_constant__ PeerSet P, int64_t rows) {
+  constexpr int64_t IOFF = STEP == 0 ? OFF_H1 : STEP == 1 ? OFF_H2 : OFF_H3;
+  constexpr int ICNT = STEP == 0 ? L1_BINS : STEP == 1 ? NT * L2_BINS : STEP == 2 ? NT * L3_BINS : 0;
+  constexpr int DOFF = STEP == 0 ? 0 : STEP == 2 ? 1 : 3;
+  constexpr int DCNT = STEP == 0 ? 1 : STEP == 1 ? 0 : STEP == 2 ? 2 : 6;
+  constexpr int PER4 = ICNT / 1024;    // groups of four counts per thread and row
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int owner = (int)(row % P.world);
+    if (owner == P.rank) continue;
+    const long long* src = reinterpret_cast<const long long*>(P.ws[P.rank] + row);
+    long long* dst = P.stage[owner] + ((int64_t)P.rank * P.stage_rows + row / P.world) * STAGE_WORDS;
+    if (PER4 > 0) {   // the counts travel as 32-bit words (a rank holds fewer than 2^32 elements): half the NVLink bytes
+      const longlong2* s2 = reinterpret_cast<const longlong2*>(src + IOFF);
+      uint4* d4 = reinterpret_cast<uint4*>(dst + STAGE_HEAD);
+      constexpr int CH = PER4 > 4 ? 4 : (PER4 > 0 ? PER4 : 1);
+#pragma unroll 1
+      for (int u0 = 0; u0 < PER4; u0 += CH) {
+        longlong2 v[CH][2];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          v[c][0] = __ldcg(s2 + 2 * ((u0 + c) * 256 + threadIdx.x));
+          v[c][1] = __ldcg(s2 + 2 * ((u0 + c) * 256 + threadIdx.x) + 1);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          d4[(u0 + c) * 256 + threadIdx.x] = make_uint4((uint32_t)v[c][0].x, (uint32_t)v[c][0].y, (uint32_t)v[c][1].x,
+                                                        (uint32_t)v[c][1].y);
+      }
+    }
+    if ((int)threadIdx.x < DCNT) dst[DOFF + threadIdx.x] = src[DOFF + threadIdx.x];
+    if (STEP == 2 && threadIdx.x == 32) dst[STAGE_CNT] = src[OFF_CNT];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int last = 0;
+    if (threadIdx.x == 0) {
+      unsigned int* ticket = P.flags[P.rank] + FLAG_TICKET + STEP;
+      __threadfence_system();
+      last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+      if (last) *ticket = 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) signal_peers(P, STEP);
+  }
+}
+
+// COUNT 8-byte words of the step's histogram(s) of owned row `row`, summed over the
+// world (own workspace + the staged copies, all in this GPU's memory), into shared memory.
+template <int STEP, int COUNT>
+__device__ __forceinline__ void gather_hist(long long* __restrict__ hs, const PeerSet& P, int64_t row) {
+  static_assert(COUNT % 1024 == 0, "256 threads x four counts");
+  constexpr int PER4 = COUNT / 1024;
+  const uint4* staged[B200_MAX_PEERS];    // the peers' counts: 32-bit words ([rank]: unused)
+#pragma unroll
+  for (int r = 0; r < B200_MAX_PEERS; ++r)
+    staged[r] = reinterpret_cast<const uint4*>(row_source<STEP>(P, r < P.world && r != P.rank ? r : (P.rank + 1) % P.world, row).hist);
+  const longlong2* own = reinterpret_cast<const longlong2*>(row_source<STEP>(P, P.rank, row).hist);
+#pragma unroll 1
+  for (int u = 0; u < PER4; ++u) {
+    const int i = u * 256 + threadIdx.x;
+    uint4 v[B200_MAX_PEERS];
+    const longlong2 o0 = __ldcg(own + 2 * i), o1 = __ldcg(own + 2 * i + 1);
+#pragma unroll
+    for (int r = 0; r < B200_MAX_PEERS; ++r) v[r] = __ldcg(staged[r] + i);   // absent ranks: a cached re-read, not added
+    long long a = o0.x, b = o0.y, c = o1.x, d = o1.y;
+#pragma unroll
+    for (int r = 0; r < B200_MAX_PEERS; ++r)
+      if (r < P.world && r != P.rank) { a += v[r].x; b += v[r].y; c += v[r].z; d += v[r].w; }
+    reinterpret_cast<longlong2*>(hs)[2 * i] = make_longlong2(a, b);
+    reinterpret_cast<longlong2*>(hs)[2 * i + 1] = make_longlong2(c, d);
+  }
+}
+
+// After the push of step STEP: grid = the rows this rank owns (at least one block:
+// a rank without rows still tells its peers it is done), 256 threads.
+template <int STEP>
+__global__ void __launch_bounds__(256)
+rowstats_owner_kernel(const __grid_constant__ PeerSet P, int64_t rows, int64_t n_total, int64_t top) {
+  extern __shared__ long long hs[];
+  __shared__ double sd_s[16];
+  __shared__ long long cnt_s;
+  constexpr int DOFF = STEP == 0 ? 0 : STEP == 2 ? 1 : 3;
+  constexpr int DCNT = STEP == 0 ? 1 : STEP == 1 ? 0 : STEP == 2 ? 2 : 6;
+  const bool ok = wait_peers(P, STEP);
+  const int64_t row = P.rank + (int64_t)blockIdx.x * P.world;
+  if (ok && row < rows) {
+    if (STEP == 0) gather_hist<0, L1_BINS>(hs, P, row);
+    if (STEP == 1) gather_hist<1, NT * L2_BINS>(hs, P, row);
+    if (STEP == 2) gather_hist<2, NT * L3_BINS>(hs, P, row);
+    if ((int)threadIdx.x < DCNT) {
+      double acc = 0.0;
+      for (int r = 0; r < P.world; ++r) {
+        const double v = __longlong_as_double(__ldcg(row_source<STEP>(P, r, row).head + DOFF + threadIdx.x));
+        acc = r == 0 ? v : acc + v;
+      }
+      sd_s[DOFF + threadIdx.x] = acc;
+    }
+    if (STEP == 2 && threadIdx.x == 32) {
+      long long c = 0;
+      for (int r = 0; r < P.world; ++r)
+        c += __ldcg(row_source<STEP>(P, r, row).head + (r == P.rank ? OFF_CNT : STAGE_CNT));
+      cnt_s = c;
+    }
+    __syncthreads();
+    RowWS* w = P.ws[P.rank] + row;
+    resolve_row<STEP>(hs, sd_s, cnt_s, w, n_total, top, w->stats_out);
+    __syncthreads();
+    // the resolved words of this row into every peer's workspace
+    if (threadIdx.x < ROW_WORDS - OFF_RES) {
+      const long long v = reinterpret_cast<const long long*>(w)[OFF_RES + threadIdx.x];
+      for (int r = 0; r < P.world; ++r)
+        if (r != P.rank) reinterpret_cast<long long*>(P.ws[r] + row)[OFF_RES + threadIdx.x] = v;
+    }
+  }
+  // the last block to get here tells the peers that this rank's rows are resolved
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int last = 0;
+    if (threadIdx.x == 0) {
+      unsigned int* ticket = P.flags[P.rank] + FLAG_TICKET + STEP;
+      __threadfence_system();
+      last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+      if (last) *ticket = 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last && ok) signal_peers(P, FLAG_RESOLVED + STEP);
+  }
+}
+
+// One warp, before the next pass reads the resolved words: every owner has stored them here.
+__global__ void rowstats_wait_kernel(const __grid_constant__ PeerSet P, int word) { wait_peers(P, word); }
+
+// The statistics of all rows (resolved by their owners after pass 3) out of the workspace.
+__global__ void __launch_bounds__(256)
+rowstats_collect_kernel(const __grid_constant__ PeerSet P, int64_t rows, double* __restrict__ stats) {
+  const bool ok = wait_peers(P, FLAG_RESOLVED + 3) && P.flags[P.rank][FLAG_ERROR_WORD] == 0u;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < rows * 12)
+    stats[i] = ok ? P.ws[P.rank][i / 12].stats_out[i % 12] : __longlong_as_double(0x7ff8000000000000LL);
 }
 
 static int launch_pass(int pass, const float* values, int64_t rows, int64_t n, int64_t ld, RowWS* ws,
@@ -624,41 +773,68 @@ static int launch_pass(int pass, const float* values, int64_t rows, int64_t n, i
   return check_cuda(cudaGetLastError(), "rowstats pass launch");
 }
 
-static int launch_resolve(int step, int64_t rows, int64_t n_total, int64_t top, const RowWS* sums, RowWS* own,
-                          const uint32_t* error_word, double* stats, cudaStream_t st) {
+static int launch_resolve(int step, int64_t rows, int64_t n_total, int64_t top, RowWS* ws, double* stats,
+                          cudaStream_t st) {
   static bool attr_set[64] = {false};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {   // step 1 walks four 2048-bin histograms of 8-byte counts: 64 KB
     B200_CUDA(cudaFuncSetAttribute(rowstats_resolve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    NT * L2_BINS * 8));
+    B200_CUDA(cudaFuncSetAttribute(rowstats_owner_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   NT * L2_BINS * 8));
     attr_set[dev] = true;
   }
   const unsigned g = (unsigned)rows;
   switch (step) {
-    case 0: rowstats_resolve_kernel<0><<<g, 256, L1_BINS * 8, st>>>(sums, own, error_word, n_total, top, stats); break;
-    case 1: rowstats_resolve_kernel<1><<<g, 256, NT * L2_BINS * 8, st>>>(sums, own, error_word, n_total, top, stats); break;
-    case 2: rowstats_resolve_kernel<2><<<g, 256, NT * L3_BINS * 8, st>>>(sums, own, error_word, n_total, top, stats); break;
-    case 3: rowstats_resolve_kernel<3><<<g, 256, 0, st>>>(sums, own, error_word, n_total, top, stats); break;
+    case 0: rowstats_resolve_kernel<0><<<g, 256, L1_BINS * 8, st>>>(ws, n_total, top, stats); break;
+    case 1: rowstats_resolve_kernel<1><<<g, 256, NT * L2_BINS * 8, st>>>(ws, n_total, top, stats); break;
+    case 2: rowstats_resolve_kernel<2><<<g, 256, NT * L3_BINS * 8, st>>>(ws, n_total, top, stats); break;
+    case 3: rowstats_resolve_kernel<3><<<g, 256, 0, st>>>(ws, n_total, top, stats); break;
   }
   return check_cuda(cudaGetLastError(), "rowstats resolve launch");
 }
 
-static int launch_gather(int step, int64_t rows, const PeerSet& P, RowWS* gsum, cudaStream_t st) {
-  const int icnt[4] = {L1_BINS, NT * L2_BINS, 8 + NT * L3_BINS, 0};
-  dim3 grid((unsigned)std::max(1, (icnt[step] + 511) / 512), (unsigned)rows);
+static int launch_push(int step, int64_t rows, const PeerSet& P, cudaStream_t st) {
+  const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)sm_count() * 4));
   switch (step) {
-    case 0: rowstats_gather_kernel<0><<<grid, 256, 0, st>>>(P, gsum); break;
-    case 1: rowstats_gather_kernel<1><<<grid, 256, 0, st>>>(P, gsum); break;
-    case 2: rowstats_gather_kernel<2><<<grid, 256, 0, st>>>(P, gsum); break;
-    case 3: rowstats_gather_kernel<3><<<grid, 256, 0, st>>>(P, gsum); break;
+    case 0: rowstats_push_kernel<0><<<g, 256, 0, st>>>(P, rows); break;
+    case 1: rowstats_push_kernel<1><<<g, 256, 0, st>>>(P, rows); break;
+    case 2: rowstats_push_kernel<2><<<g, 256, 0, st>>>(P, rows); break;
+    case 3: rowstats_push_kernel<3><<<g, 256, 0, st>>>(P, rows); break;
   }
-  return check_cuda(cudaGetLastError(), "rowstats gather launch");
+  return check_cuda(cudaGetLastError(), "rowstats push launch");
+}
+
+static int launch_owner(int step, int64_t rows, int64_t n_total, int64_t top, const PeerSet& P, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    B200_CUDA(cudaFuncSetAttribute(rowstats_owner_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   NT * L2_BINS * 8));
+    attr_set[dev] = true;
+  }
+  const int64_t owned = rows > P.rank ? (rows - P.rank + P.world - 1) / P.world : 0;
+  const unsigned g = (unsigned)std::max<int64_t>(owned, 1);
+  switch (step) {
+    case 0: rowstats_owner_kernel<0><<<g, 256, L1_BINS * 8, st>>>(P, rows, n_total, top); break;
+    case 1: rowstats_owner_kernel<1><<<g, 256, NT * L2_BINS * 8, st>>>(P, rows, n_total, top); break;
+    case 2: rowstats_owner_kernel<2><<<g, 256, NT * L3_BINS * 8, st>>>(P, rows, n_total, top); break;
+    case 3: rowstats_owner_kernel<3><<<g, 256, 0, st>>>(P, rows, n_total, top); break;
+  }
+  return check_cuda(cudaGetLastError(), "rowstats owner launch");
 }
 
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int64_t b200_rowstats_stage_bytes(int64_t rows, int32_t world) {
+  if (rows < 0 || world < 1) return 0;
+  const int64_t owned = (rows + world - 1) / world;
+  return (int64_t)world * owned * STAGE_WORDS * 8;
+}
 
 extern "C" int64_t b200_rowstats_workspace_bytes(int64_t rows) {
   return rows < 0 ? 0 : rows * (int64_t)sizeof(RowWS);
@@ -694,7 +870,7 @@ extern "C" int b200_rowstats(const float* values, int64_t rows, int64_t n, int64
     if (p == 0) {
       B200_CUDA(cudaMemsetAsync(ws, 0, (size_t)rows * sizeof(RowWS), st));
     } else {
-      rc = launch_resolve(p - 1, rows, n_total, top, ws, ws, nullptr, stats, st);
+      rc = launch_resolve(p - 1, rows, n_total, top, ws, stats, st);
       if (rc) return rc;
     }
     if (p <= 3) {
@@ -737,6 +913,7 @@ extern "C" int b200_rowstats_p2p(const float* values, int64_t rows, int64_t n, i
   B200_REQUIRE(n_total >= 2 && n <= n_total, "rowstats_p2p: need n_total >= 2 and n <= n_total");
   B200_REQUIRE(top >= 1 && top < n_total, "rowstats_p2p: need 1 <= top < n_total (top=%lld)", (long long)top);
   B200_REQUIRE(ld >= n, "rowstats_p2p: ld < n");
+  B200_REQUIRE(n < (1ll << 32), "rowstats_p2p: a rank's partial counts travel as 32-bit words (n < 2^32 per rank)");
   PeerSet P;
   memset(&P, 0, sizeof(P));
   P.world = peers->world; P.rank = peers->rank; P.epoch = peers->epoch;
@@ -745,21 +922,56 @@ extern "C" int b200_rowstats_p2p(const float* values, int64_t rows, int64_t n, i
                  "rowstats_p2p: workspace / flags of rank %d is NULL", r);
     P.ws[r] = (RowWS*)peers->workspace[r];
     P.flags[r] = peers->flags[r];
+    P.stage[r] = (long long*)peers->stage[r];
+    B200_REQUIRE(peers->world == 1 || P.stage[r] != nullptr, "rowstats_p2p: staging of rank %d is NULL", r);
   }
+  P.stage_rows = peers->stage_rows;
+  B200_REQUIRE(P.world == 1 || P.stage_rows * P.world >= rows,
+               "rowstats_p2p: the staging holds %lld owned rows per rank, %lld rows need %lld", (long long)P.stage_rows,
+               (long long)rows, (long long)((rows + P.world - 1) / P.world));
   RowWS* ws = P.ws[P.rank];
-  RowWS* gsum = (RowWS*)peers->sums;
-  B200_REQUIRE(P.world == 1 || gsum != nullptr, "rowstats_p2p: sums workspace is NULL");
+#ifdef B200_P2P_DEBUG   // per-kernel times of one call (tools/bench_series_n.py --debug): -DB200_P2P_DEBUG builds only
+  cudaEvent_t ev[24];
+  int nev = 0;
+  for (auto& e : ev) cudaEventCreate(&e);
+#define P2P_STAMP() cudaEventRecord(ev[nev++], st)
+#else
+#define P2P_STAMP()
+#endif
+  P2P_STAMP();
   B200_CUDA(cudaMemsetAsync(ws, 0, (size_t)rows * sizeof(RowWS), st));
   for (int p = 0; p < 4; ++p) {
+    P2P_STAMP();
     if (int rc = launch_pass(p, values, rows, n, ld, ws, st)) return rc;
+    P2P_STAMP();
     if (P.world == 1) {
-      if (int rc = launch_resolve(p, rows, n_total, top, ws, ws, nullptr, stats, st)) return rc;
+      if (int rc = launch_resolve(p, rows, n_total, top, ws, stats, st)) return rc;
       continue;
     }
-    rowstats_signal_kernel<<<1, 32, 0, st>>>(P, p);
+    if (int rc = launch_push(p, rows, P, st)) return rc;
+    P2P_STAMP();
+    if (int rc = launch_owner(p, rows, n_total, top, P, st)) return rc;
+    P2P_STAMP();
+    if (p < 3) {
+      rowstats_wait_kernel<<<1, 32, 0, st>>>(P, FLAG_RESOLVED + p);
+    } else {
+      rowstats_collect_kernel<<<(unsigned)((rows * 12 + 255) / 256), 256, 0, st>>>(P, rows, stats);
+    }
     B200_CUDA(cudaGetLastError());
-    if (int rc = launch_gather(p, rows, P, gsum, st)) return rc;
-    if (int rc = launch_resolve(p, rows, n_total, top, gsum, ws, P.flags[P.rank] + FLAG_ERROR_WORD, stats, st)) return rc;
   }
+  P2P_STAMP();
+#ifdef B200_P2P_DEBUG
+  cudaStreamSynchronize(st);
+  if (getenv("B200_P2P_PRINT")) {
+    fprintf(stderr, "[p2p rank %d rows %lld]", P.rank, (long long)rows);
+    for (int i = 1; i < nev; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, " %.1f", ms * 1e3f);
+    }
+    fprintf(stderr, " us\n");
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+#endif
   return 0;
 }

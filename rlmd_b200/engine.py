@@ -403,7 +403,7 @@ def lev_series(
     sigma: float = 0.0,
     variant: int = 0,
     chunk_steps: Optional[int] = None,
-    chunk_bytes: int = 2 << 30,
+    chunk_bytes: int = 8 << 30,
     n_total: Optional[int] = None,
     group=None,
     device=None,
@@ -417,6 +417,8 @@ def lev_series(
     step of the chunk to a [G*steps, N] buffer, b200_rowstats reduces every row,
     and the statistics are scattered into `data` (step t -> column t-1).
     With `group`, the rows are investor shards and the statistics are global.
+    A chunk is up to `chunk_bytes` (8 GB of the 180) and 2048 rows: the statistics'
+    launch and cross-GPU latencies (4 exchange steps per chunk) are paid once per chunk.
     """
     require_cuda()
     f = np.ascontiguousarray(factors, dtype=np.float32)
@@ -571,6 +573,11 @@ def final_tally(rows: int, device, group=None):
             return t
     elif t is not None and t.plan.rows_cap >= need:
         return t
+    if group is not None:
+        from . import sharding
+
+        if not sharding.peer_memory_available(group, dev):      # decided by all ranks together
+            raise _tally.TallyUnavailable("no peer-mapped memory between the ranks of this group")
     if t is not None:
         torch.cuda.synchronize(dev)          # peers may still read the old exchange buffer
         if group is not None:
@@ -667,6 +674,11 @@ class FinalSweepPipeline:
         self.statistics = statistics or ("tally" if kind == "discrete" else "rows")
         if self.statistics not in ("tally", "rows") or (self.statistics == "tally" and kind != "discrete"):
             raise ValueError("statistics must be 'tally' (discrete gambles) or 'rows'")
+        if self.statistics == "tally" and group is not None:
+            from . import sharding
+
+            if not sharding.peer_memory_available(group, self.dev):     # collective; all ranks decide alike
+                self.statistics = "rows"       # the general path, whose exchange can run over NCCL
         with torch.cuda.device(self.dev):
             # the statistics' short, dependent kernels go first whenever they are ready
             self.sweep_stream = torch.cuda.Stream()

@@ -54,13 +54,16 @@ class PeerWorkspace:
     mapped into every process through torch's symmetric memory (CUDA IPC over
     NVLink), for b200_rowstats_p2p: two workspaces per rank (successive calls
     alternate: a peer may still be summing the previous call's histograms) and one
-    flag block.  Construction and `peer_set` are collective: every rank must make
+    flag block, plus two alternating staging areas.  Rows are owned round-robin: every rank
+    pushes a row's partial sums into its owner's staging area, the owner sums and resolves
+    the rows it owns and stores the resolved words into every workspace (rowstats.cu).  Construction and `peer_set` are collective: every rank must make
     the same calls in the same order, and the calls of one workspace must execute
     one after the other on the GPU - engine.rowstats chains them with an event
     (`last_call`), whatever streams they are issued on.
     """
 
-    FLAG_WORDS = 64   # uint32 [8 ranks][4 phases] + error word, in 8-byte slots
+    FLAG_WORDS = 64   # B200_PEER_FLAG_WORDS uint32 ([8 ranks][8 flags], error word, tickets) in 8-byte slots
+    ERROR_WORD = 64   # B200_PEER_FLAG_ERROR_WORD
 
     def __init__(self, rows: int, group, device):
         import torch.distributed as dist
@@ -73,7 +76,10 @@ class PeerWorkspace:
             raise ValueError(f"the peer-memory exchange spans at most {MAX_PEERS} GPUs of one node")
         self.rows = int(rows)
         self.row_words = int(lib.b200_rowstats_workspace_bytes(1)) // 8
-        words = 3 * self.rows * self.row_words + self.FLAG_WORDS    # two alternating workspaces, the sums, the flags
+        self.stage_rows = (self.rows + self.world - 1) // self.world       # owned rows per source rank
+        self.stage_words = int(lib.b200_rowstats_stage_bytes(self.rows, self.world)) // 8
+        # two alternating workspaces, the flags, two alternating staging areas
+        words = 2 * self.rows * self.row_words + self.FLAG_WORDS + 2 * self.stage_words
         self.buf = symm.empty(words, dtype=torch.int64, device=device)
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, group)
@@ -93,16 +99,18 @@ class PeerWorkspace:
         ps.world, ps.rank, ps.epoch = self.world, self.rank, self.epoch
         for r in range(self.world):
             ps.workspace[r] = self.ptrs[r] + 8 * parity * self.rows * self.row_words
-            ps.flags[r] = self.ptrs[r] + 8 * 3 * self.rows * self.row_words
-        ps.sums = self.ptrs[self.rank] + 8 * 2 * self.rows * self.row_words
+            ps.flags[r] = self.ptrs[r] + 8 * 2 * self.rows * self.row_words
+            ps.stage[r] = self.ptrs[r] + 8 * (2 * self.rows * self.row_words + self.FLAG_WORDS + parity * self.stage_words)
+        ps.sums = None
+        ps.stage_rows = self.stage_rows
         return ps
 
     def timed_out(self, clear: bool = False) -> bool:
         """True when a resolve kernel gave up waiting for a peer (its statistics are NaN)."""
-        flags = self.buf[3 * self.rows * self.row_words:].view(torch.int32)
-        hit = bool(flags[32].item())
+        flags = self.buf[2 * self.rows * self.row_words:2 * self.rows * self.row_words + self.FLAG_WORDS].view(torch.int32)
+        hit = bool(flags[self.ERROR_WORD].item())
         if hit and clear:
-            flags[32] = 0
+            flags[self.ERROR_WORD] = 0
         return hit
 
 

@@ -43,6 +43,11 @@ class TallyOverflow(RuntimeError):
     """More distinct count tuples than the plan's bins_cap: use lev_sweep + rowstats for this input."""
 
 
+class TallyUnavailable(TallyOverflow):
+    """The ranks of the group cannot map each other's memory (no peer access): the tally's exchange cannot be
+    set up; callers take the general path (lev_sweep + rowstats with the NCCL exchange), like on overflow."""
+
+
 class TallyExchange:
     """
     One rank's peer-mapped exchange buffer (torch symmetric memory: CUDA IPC over

@@ -75,11 +75,13 @@ def _worker(rank, world, port, out_dir):
         # back-to-back calls alternate between the two peer workspaces; rows of every key
         # mode, a different row count, a rank with far fewer investors than the other
         pw = sharding.peer_workspace(1, dist.group.WORLD, local.device)
-        for it in range(5):
+        for it in range(6):
             rsi = np.random.RandomState(100 + it)
             vi = np.exp(rsi.standard_normal((3 + it, 20_011)) * 2).astype(np.float32)
             vi[0] = rsi.standard_normal(20_011).astype(np.float32)           # sign bit set
             vi[1, 5] = np.float32(np.nan)
+            if it == 5:
+                vi = vi[2:3]             # one row: a rank that owns no row still takes part in the exchange
             cut = 17 if it % 2 else 12_000
             loc = torch.as_tensor(vi[:, :cut] if rank == 0 else vi[:, cut:], device="cuda")
             sti = engine.rowstats(loc, 7, n_total=vi.shape[1], group=dist.group.WORLD)
@@ -167,11 +169,13 @@ def test_two_ranks_equal_one(tmp_path):
             np.testing.assert_allclose(got, want, rtol=1e-12)
     # the peer-memory exchange sums the ranks in one order everywhere: identical bits on both ranks
     assert np.array_equal(np.load(tmp_path / "stats0.npy"), np.load(tmp_path / "stats1.npy"))
-    for it in range(5):
+    for it in range(6):
         rsi = np.random.RandomState(100 + it)
         vi = np.exp(rsi.standard_normal((3 + it, 20_011)) * 2).astype(np.float32)
         vi[0] = rsi.standard_normal(20_011).astype(np.float32)
         vi[1, 5] = np.float32(np.nan)
+        if it == 5:
+            vi = vi[2:3]
         wi = engine.rowstats(torch.as_tensor(vi, device="cuda"), 7).cpu().numpy()
         for r in range(world):
             gi = np.load(tmp_path / f"loop{it}_{r}.npy")
