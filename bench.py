@@ -276,7 +276,7 @@ def run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world, hbm_peak, 
     * C4: GBM leverage sweep kernel alone, on-device Philox draws, 1.25e7 investors x 1e4 steps
       per GPU (the whole step with statistics is `--workload gbm`);
     * C5: n-step replay sampling, batch 256 from a full 1e6 buffer (per call, graph replay,
-      and 1024 mini-batches per launch), and the fused collector (env step + append + sample).
+      and 16384 mini-batches per launch), and the fused collector (env step + append + sample).
     """
     from rlmd_b200 import collector, envs
     from rlmd_b200.replay_torch import ReplayBufferTorch
@@ -298,6 +298,7 @@ def run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world, hbm_peak, 
     done = np.zeros(mem, dtype=bool)
     done[ends[ends < mem] - 1] = True
     base = len(times)
+    BULK = 16384
     for nstep in (1, 5, 10):
         inputs = {"gpu": str(dev), "input_dims": (5,), "num_actions": 1, "mini_batch_size": batch, "discount": 0.99,
                   "multi_steps": nstep, "r_abs_zero": None, "dynamics": "M", "buffer": mem, "n_cumsteps": mem}
@@ -305,9 +306,13 @@ def run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world, hbm_peak, 
         st = torch.randn((mem, 5), dtype=torch.float64, device=dev)
         rb.store_batch(st, st[:, :1], 1 + 0.01 * st[:, 0], st, torch.as_tensor(done, device=dev))
         t1 = _event_time(torch, lambda: rb.sample_exp(), 5, 50)
-        tk = _event_time(torch, lambda: rb.sample_many(1024), 2, 10)
-        idx_k = rb.sample_many(1024)[0].reshape(-1).clone()        # the same launch with the slots supplied:
-        tgat = _event_time(torch, lambda: rb.sample_many(1024, batches=idx_k), 2, 10)   # the gather kernel alone
+        # bulk: BULK mini-batches per launch (one kernel: the block that draws a mini-batch gathers it); a launch of
+        # 1024 x 256 samples takes less GPU time than the eager call's ~33 us of host work, so it says nothing
+        # about the kernels
+        tk = _event_time(torch, lambda: rb.sample_many(BULK), 2, 10)
+        idx_k = rb.sample_many(BULK)[0].reshape(-1).clone()        # the same samples with the slots supplied:
+        tgat = _event_time(torch, lambda: rb.sample_many(BULK, batches=idx_k), 2, 10)   # the gather kernel alone
+        del idx_k
         tg = None
         if hasattr(rb, "capture_sampler"):
             run = rb.capture_sampler()
@@ -332,25 +337,26 @@ def run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world, hbm_peak, 
         }
     ns = (1, 5, 10)
     bytes_per_sample = {1: 106, 5: 114 + 4 * 4, 10: 114 + 4 * 9}
-    bulk = {n: 1024 * batch / times[base + 4 * i + 1] for i, n in enumerate(ns)}
-    gath = {n: 1024 * batch / times[base + 4 * i + 3] for i, n in enumerate(ns)}
+    bulk = {n: BULK * batch / times[base + 4 * i + 1] for i, n in enumerate(ns)}
+    gath = {n: BULK * batch / times[base + 4 * i + 3] for i, n in enumerate(ns)}
     out["replay_nstep_sampling"] = {
         "unit": "samples/s", "buffer": mem, "batch": batch, "per_gpu": True,
         "per_call": {str(n): batch / times[base + 4 * i] for i, n in enumerate(ns)},
         "per_call_us": {str(n): times[base + 4 * i] * 1e6 for i, n in enumerate(ns)},
         "graph_replay_us": {str(n): times[base + 4 * i + 2] * 1e6 for i, n in enumerate(ns)
                             if times[base + 4 * i + 2] > 0},
-        "1024_batches_per_launch": {str(n): bulk[n] for n in ns},
-        "1024_batches_gather_only": {str(n): gath[n] for n in ns},
-        "roofline": {str(n): {"bound": "hbm", "kernel": "replay_draw_kernel + replay_gather_thread_kernel",
+        "bulk_batches_per_launch": BULK,
+        "bulk_draw_and_gather": {str(n): bulk[n] for n in ns},
+        "bulk_gather_only": {str(n): gath[n] for n in ns},
+        "roofline": {str(n): {"bound": "hbm", "kernel": "replay_draw_gather_kernel (gather_only: replay_gather_bulk_kernel)",
                               "achieved": bulk[n] * bytes_per_sample[n] / 1e9, "peak": hbm_peak, "unit": "GB/s",
                               "frac": bulk[n] * bytes_per_sample[n] / 1e9 / hbm_peak, "traffic": None,
                               "algorithmic_bytes_per_sample": bytes_per_sample[n],
                               "gather_only": {"achieved": gath[n] * bytes_per_sample[n] / 1e9,
                                               "frac": gath[n] * bytes_per_sample[n] / 1e9 / hbm_peak},
-                              "note": "draw + gather of 1024 x 256 samples per launch (the distinct-slot draw - Philox + "
-                                      "a shared-memory hash set per mini-batch - is the larger part); gather_only: the "
-                                      "same launch with the slots supplied.  Random 20-byte rows of a 52 MB buffer: "
+                              "note": "draw + gather of 16384 x 256 samples in one launch (distinct slots per mini-batch: "
+                                      "Philox + a shared-memory hash set; the drawing block gathers); gather_only: the "
+                                      "same samples with the slots supplied.  Random 20-byte rows of a 52 MB buffer: "
                                       "L2-resident, sector-amplified"}
                      for n in ns},
     }

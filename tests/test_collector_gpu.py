@@ -90,6 +90,21 @@ def test_collector_memory_and_samples_match_the_lane_oracles(family, investor, n
             assert np.array_equal(got[5][sel], want[5]), (e, "eff")
 
 
+@pytest.mark.parametrize("n_steps,dyn", [(1, "M"), (5, "M"), (10, "A")])
+def test_bulk_gather_over_lanes_equals_the_per_call_gather(n_steps, dyn):
+    """>= 4096 samples per launch take the warp-cooperative gather: slot-major lanes, the same bits."""
+    E, T = 6, 90
+    col, _ = _drive("coin", "B", 2, E, T, n_steps, dyn)
+    B = col.batch_size
+    k = -(-4100 // B)
+    slots = np.random.RandomState(3).randint(0, E * T, size=(k, B)).astype(np.int64)
+    big = [x.clone() for x in col.sample(k, batch=slots)]
+    for j in range(k):
+        small = col.sample(1, batch=slots[j:j + 1])
+        for g_, w_ in zip(big, small):
+            assert torch.equal(g_[j * B:(j + 1) * B], w_), j
+
+
 def test_single_lane_is_the_reference_stream():
     """n_envs = 1: the collector's memory equals ReplayBufferTorch fed by the env, transition by transition."""
     from rlmd_b200.replay_torch import ReplayBufferTorch

@@ -221,3 +221,47 @@ def test_graph_captured_sampler_equals_indexed_sampling():
     idx = buf.last_batch.cpu().numpy().reshape(3, -1)
     for b in range(3):
         assert len(set(idx[b].tolist())) == case["batch"]
+
+
+@pytest.mark.parametrize("s_dim,n,dyna", [(1, 1, "M"), (5, 1, "M"), (5, 10, "M"), (5, 5, "A"), (6, 3, "M"), (12, 10, "A"),
+                                          (13, 2, "M")])
+def test_bulk_gather_equals_the_per_call_gather(s_dim, n, dyna):
+    """
+    >= 4096 samples per launch take the warp-cooperative gather (aligned 16-byte windows through shared
+    memory); fewer take the per-thread one.  Same slots -> the same bits, including slots beyond the
+    filled part (zeros), the first episode, episode ends and a tail group of fewer than 32 samples.
+    """
+    mem, fill, b = 40_000, 30_011, 256
+    case = dict(name="bulk", mem=mem, s=s_dim, a=1, n=n, gamma=0.97, dyna=dyna, batch=b, r0=None, lens=[10], fill=fill,
+                events=[], seed=5)
+    buf = make(case, seed=77)
+    dev = buf.device
+    rs = np.random.RandomState(s_dim * 100 + n)
+    ends = np.cumsum(rs.randint(1, 40, size=fill // 10))
+    done = np.zeros(fill, dtype=bool)
+    done[ends[ends < fill - 5] - 1] = True
+    st = torch.as_tensor(rs.standard_normal((fill, s_dim)), device=dev)
+    buf.store_batch(st, st[:, :1] * 2, torch.as_tensor(1 + 0.05 * rs.standard_normal(fill), device=dev), st + 1,
+                    torch.as_tensor(done, device=dev))
+    k = 17
+    slots = rs.randint(0, mem, size=(k, b)).astype(np.int64)            # a quarter lies beyond the filled part
+    slots[0, :40] = np.arange(40)                                       # the first episode
+    slots[1, :64] = np.concatenate([ends[:32] - 1, ends[:32]])          # episode ends and starts
+    slots[2, :8] = fill - 1 - np.arange(8)                              # the unfinished run at the end
+    slots_t = torch.as_tensor(slots, device=dev)
+    big = buf.sample_many(k, batches=slots_t)                           # 4352 samples: bulk
+    for j in range(k):
+        small = buf.sample_many(1, batches=slots_t[j:j + 1].contiguous())
+        for name, g_, w_ in zip("i s a r s2 d e".split(), big, small):
+            assert torch.equal(g_[j], w_[0]), (name, j)
+    # a tail group: 4100 samples = 128 full warps + 4 samples
+    flat = slots_t.reshape(-1)[:4100].contiguous()
+    i2, s2_, a2, r2, n2, d2, e2 = buf._sample(1, 4100, flat)
+    assert torch.equal(s2_, big[1].reshape(-1, s_dim)[:4100]) and torch.equal(r2, big[3].reshape(-1)[:4100])
+    assert torch.equal(n2, big[4].reshape(-1, s_dim)[:4100]) and torch.equal(e2, big[6].reshape(-1)[:4100])
+    # drawn on the device (one fused launch at this size) == the same slots supplied
+    drawn = buf.sample_many(k)
+    assert np.array_equal(drawn[0][3].cpu().numpy(), ro.draw_unique(buf.seed, buf._draws, 3, fill, b))
+    again = buf.sample_many(k, batches=drawn[0])
+    for name, g_, w_ in zip("i s a r s2 d e".split(), drawn, again):
+        assert torch.equal(g_, w_), name
