@@ -520,10 +520,10 @@ struct PeerSet {
 constexpr int64_t STAGE_HEAD = 16, STAGE_CNT = 15, STAGE_WORDS = STAGE_HEAD + (int64_t)NT * L2_BINS / 2;
 // Flag block of a rank: for every peer r, words [r][0..3] "r's partial sums of pass p
 // are in memory" and [r][4..7] "the rows r owns are resolved after pass p and stored
-// here"; then the error word, then one block ticket per pass.
+// here"; then the error word, then one block ticket per pass for the push kernels and one for the owner kernels.
 constexpr int FLAG_STRIDE = 8, FLAG_RESOLVED = 4;
 constexpr int FLAG_ERROR_WORD = B200_PEER_FLAG_ERROR_WORD, FLAG_TICKET = FLAG_ERROR_WORD + 1;
-static_assert(FLAG_ERROR_WORD == B200_MAX_PEERS * FLAG_STRIDE && FLAG_TICKET + 4 <= B200_PEER_FLAG_WORDS, "flag block layout");
+static_assert(FLAG_ERROR_WORD == B200_MAX_PEERS * FLAG_STRIDE && FLAG_TICKET + 8 <= B200_PEER_FLAG_WORDS, "flag block layout");
 
 __device__ __forceinline__ long long ld_sys(const long long* p) {
   long long v;
@@ -726,7 +726,7 @@ rowstats_owner_kernel(const __grid_constant__ PeerSet P, int64_t rows, int64_t n
   if (threadIdx.x < 32) {
     int last = 0;
     if (threadIdx.x == 0) {
-      unsigned int* ticket = P.flags[P.rank] + FLAG_TICKET + STEP;
+      unsigned int* ticket = P.flags[P.rank] + FLAG_TICKET + 4 + STEP;
       __threadfence_system();
       last = atomicAdd(ticket, 1u) == gridDim.x - 1;
       if (last) *ticket = 0u;
