@@ -99,7 +99,8 @@ def main():
             st = torch.randn((mem, 5), dtype=torch.float64, device="cuda")
             buf.store_batch(st, st[:, :1], 1 + 0.01 * st[:, 0], st, torch.as_tensor(done, device="cuda"))
             buf.sample_exp()
-            buf.sample_many(1024)
+            idx = buf.sample_many(16384)[0]                  # one launch: draw + gather
+            buf.sample_many(16384, batches=idx)              # the warp-cooperative gather alone
     if on("collect"):
         from rlmd_b200 import collector, envs
         e = 1_048_576
