@@ -565,7 +565,6 @@ int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealt
  *   flags[r]     : rank r's flag block, uint32 [B200_PEER_FLAG_WORDS], zeroed once;
  *                  word B200_PEER_FLAG_ERROR_WORD of the own block is set when a peer's
  *                  flag did not arrive within ~60 s (the statistics are then NaN)
- *   sums         : unused (kept for layout compatibility)
  *   epoch        : 1, 2, 3, ... - one more per call, the same on every rank; successive
  *                  calls must alternate between two workspaces (a peer may still be
  *                  reading the previous call's sums)
@@ -575,7 +574,6 @@ int b200_market_step(const b200_market_desc* desc, int64_t n_envs, double* wealt
 typedef struct b200_peer_set {
   void* workspace[B200_MAX_PEERS];
   uint32_t* flags[B200_MAX_PEERS];
-  void* sums;   /* unused */
   void* stage[B200_MAX_PEERS];   /* rank r's staging area as mapped HERE (b200_rowstats_stage_bytes) */
   int64_t stage_rows;            /* owned rows a staging area holds per source rank: >= ceil(rows / world) */
   int32_t world, rank;

@@ -49,7 +49,6 @@ class PeerSet(C.Structure):
     _fields_ = [
         ("workspace", C.c_void_p * MAX_PEERS),
         ("flags", C.c_void_p * MAX_PEERS),
-        ("sums", C.c_void_p),
         ("stage", C.c_void_p * MAX_PEERS),
         ("stage_rows", C.c_int64),
         ("world", C.c_int32),

@@ -101,7 +101,6 @@ class PeerWorkspace:
             ps.workspace[r] = self.ptrs[r] + 8 * parity * self.rows * self.row_words
             ps.flags[r] = self.ptrs[r] + 8 * 2 * self.rows * self.row_words
             ps.stage[r] = self.ptrs[r] + 8 * (2 * self.rows * self.row_words + self.FLAG_WORDS + parity * self.stage_words)
-        ps.sums = None
         ps.stage_rows = self.stage_rows
         return ps
 
