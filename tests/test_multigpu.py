@@ -132,6 +132,19 @@ def _worker(rank, world, port, out_dir):
         lev_exp.set_process_group(None)
         np.save(os.path.join(out_dir, f"data{rank}.npy"), data.cpu().numpy())
         np.save(os.path.join(out_dir, f"dataT{rank}.npy"), data_T.cpu().numpy())
+        # (2a) the big-brain sweep (state-dependent leverage) on sharded rows of the reference's fixture
+        bcase = golden_io.bigbrain_case("coin_grid_top4")
+        boc = golden_io.draw_outcomes(bcase)
+        off, cnt = sharding.shard_range(bcase["n"], world, rank)
+        lev_exp.set_process_group(dist.group.WORLD)
+        with contextlib.redirect_stdout(io.StringIO()):
+            bdata = lev_exp.coin_big_brain_lev(
+                "cuda", torch.tensor(boc[off:off + cnt].astype(np.float32)), torch.tensor(cnt, dtype=torch.int32),
+                torch.tensor(bcase["h"], dtype=torch.int32), bcase["top"], torch.tensor(bcase["v0"]), bcase["up_r"],
+                bcase["down_r"], torch.tensor(golden_io.bigbrain_lev_factor(bcase), dtype=torch.float64),
+                *bcase["stop"], *bcase["roll"])
+        lev_exp.set_process_group(None)
+        np.save(os.path.join(out_dir, f"bigbrain{rank}.npy"), bdata.cpu().numpy())
         # (2b) C4's shape: a GBM sweep on investor shards (on-device Philox, global investor ids) and the
         #      growth-rate summaries of the WHOLE population from the shards
         levg = np.asarray(lev_exp.param_range(-1.0, 1.0, 0.2), dtype=np.float32)
@@ -198,6 +211,11 @@ def test_two_ranks_equal_one(tmp_path):
     ref_text = json.load(open(os.path.join(golden_io.GOLDEN_DIR, "final_text.json")))["dice_top5"]
     for r in range(world):
         assert open(tmp_path / f"text{r}.txt").read().rstrip("\n") == ref_text
+    from test_oracle_bigbrain import assert_bigbrain_close
+    bgold = golden_io.load("bigbrain_coin_grid_top4")
+    b0, b1 = np.load(tmp_path / "bigbrain0.npy"), np.load(tmp_path / "bigbrain1.npy")
+    assert np.array_equal(b0.view(np.uint32), b1.view(np.uint32))           # both ranks: identical bits
+    assert_bigbrain_close(b0[:, :, :, bgold["cols"]], bgold["data"])        # = the reference on the whole population
     levg = np.asarray(lev_exp.param_range(-1.0, 1.0, 0.2), dtype=np.float32)
     full = engine.lev_sweep("gbm", levg, 100.0, n_investors=60_000, horizon=500, seed=7, log_mean=0.05 - 0.1,
                             sigma=0.2 ** 0.5, mode="log", want_log_w=True)
