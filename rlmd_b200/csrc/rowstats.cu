@@ -525,19 +525,6 @@ constexpr int FLAG_STRIDE = 8, FLAG_RESOLVED = 4;
 constexpr int FLAG_ERROR_WORD = B200_PEER_FLAG_ERROR_WORD, FLAG_TICKET = FLAG_ERROR_WORD + 1;
 static_assert(FLAG_ERROR_WORD == B200_MAX_PEERS * FLAG_STRIDE && FLAG_TICKET + 8 <= B200_PEER_FLAG_WORDS, "flag block layout");
 
-__device__ __forceinline__ long long ld_sys(const long long* p) {
-  long long v;
-  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double ld_sys(const double* p) {
-  return __longlong_as_double(ld_sys(reinterpret_cast<const long long*>(p)));
-}
-// vector load of two 8-byte words, system scope
-__device__ __forceinline__ void ld_sys_v2(const long long* p, long long& a, long long& b) {
-  asm volatile("ld.relaxed.sys.global.v2.s64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-}
-
 // Warp 0 of a block (all 32 lanes call): raises flag `word` of this rank at every peer.
 __device__ __forceinline__ void signal_peers(const PeerSet& P, int word) {
   const int r = threadIdx.x;
