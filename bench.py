@@ -292,6 +292,18 @@ def run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world, hbm_peak, 
             sigma=GBM_SIGMA, mode="log", out_data_T=buf, device=dev), 1, 3)
         del buf
         times.append(t)
+    # C1: the coin of lev/coin_flip.py (1e6 investors x 3e3 flips, 20 leverages) at ONE bit per flip, every rank
+    # its own replica (no exchange): count kernel -> tally -> statistics, like the headline
+    n_c, h_c = 1_000_000, 3_000
+    levc = np.asarray(lev_exp.param_range(0.05, 1.0, 0.05), np.float32)
+    coin = engine.lev_draw("discrete", n_c, h_c, seed=421, investor_offset=rank * n_c, probs=(0.5, 0.5), packed=True,
+                           bits=1, device=dev)
+    cpipe = engine.FinalSweepPipeline("discrete", lev_exp.coin_factor_table(levc, 0.5, -0.4), V0, max(1, n_c // 10_000),
+                                      device=dev, depth=1)
+    coin_idx = len(times)
+    times.append(_event_time(torch, lambda: cpipe.submit(coin), 5, 200))
+    cpipe.synchronize()
+    del coin, cpipe
     mem, batch = 1_000_000, 256
     rs = np.random.RandomState(0)
     ends = np.cumsum(rs.randint(5, 61, size=mem // 5))
@@ -335,6 +347,17 @@ def run_secondary(torch, dist, engine, lev_exp, np, dev, rank, world, hbm_peak, 
                         "device, 1.25e7 investors x 1e4 steps per GPU, 10 leverages",
             "roofline": gbm_roofline(n_g * h / t, t * 1e3),
         }
+    tcoin = times[coin_idx]
+    out["coin_final_sweep_c1"] = {
+        "value": n_c * h_c / tcoin, "unit": UNIT, "per_gpu": True, "ms_per_step": tcoin * 1e3,
+        "workload": "lev/coin_flip.py coin_fixed_final_lev's sweep: 1e6 investors x 3e3 flips, 20 leverages, outcomes "
+                    "resident as 1-bit codes (375 MB), count kernel -> tally of count tuples -> 12 statistics per leverage",
+        "roofline": {"bound": "hbm", "kernel": "log_discrete_packed_kernel<2, tally sink, 1 bit> + statistics",
+                     "achieved": n_c * h_c / 8 / tcoin / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": n_c * h_c / 8 / tcoin / 1e9 / hbm_peak, "traffic": None,
+                     "note": "whole step: ~58 us to read 375 MB of codes at the HBM peak + the statistics of the <= 3001 "
+                             "count tuples (compaction + cluster select, latency-bound)"},
+    }
     ns = (1, 5, 10)
     bytes_per_sample = {1: 106, 5: 114 + 4 * 4, 10: 114 + 4 * 9}
     bulk = {n: BULK * batch / times[base + 4 * i + 1] for i, n in enumerate(ns)}
