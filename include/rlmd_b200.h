@@ -375,7 +375,8 @@ typedef struct b200_replay_desc {
   uint8_t* terminal_memory;   /* [mem_size] 0/1                                  */
   int32_t* episode_start;     /* [mem_size] first slot of the slot's episode     */
   int64_t* header;            /* [8]: mem_idx, finished episodes, first / last
-                                 terminal slot, first slot of the running episode */
+                                 terminal slot, first slot of the running episode;
+                                 words 5..7: scratch of b200_replay_store (zero between calls) */
 } b200_replay_desc;
 
 /* zeroes the header, the terminal flags and episode_start (the reference's

@@ -265,3 +265,39 @@ def test_bulk_gather_equals_the_per_call_gather(s_dim, n, dyna):
     again = buf.sample_many(k, batches=drawn[0])
     for name, g_, w_ in zip("i s a r s2 d e".split(), drawn, again):
         assert torch.equal(g_, w_), name
+
+
+def test_bulk_append_bookkeeping_over_several_blocks():
+    """
+    The header update of a large append is a multi-block scan of the done flags (partial results meet in the
+    spare header words): two appends of > 65536 transitions, the second from an UNALIGNED uint8 flag array,
+    against NumPy; the scratch words are zero again afterwards.
+    """
+    mem = 700_000
+    case = dict(name="commit", mem=mem, s=2, a=1, n=3, gamma=0.99, dyna="M", batch=64, r0=None, lens=[10], fill=mem,
+                events=[], seed=1)
+    buf = make(case)
+    dev = buf.device
+    rs = np.random.RandomState(11)
+    counts = [300_000, 333_337]
+    done = rs.rand(sum(counts) + 3) < 0.01
+    done[:170_000] = False                          # the first flag sits in the third block's part
+    flags = torch.as_tensor(done.astype(np.uint8), device=dev)
+    pos = 0
+    for i, c in enumerate(counts):
+        z = torch.zeros((c, 2), dtype=torch.float32, device=dev)
+        off = 0 if i == 0 else 3                    # a view that starts 3 bytes into the allocation
+        dn = flags[off + pos: off + pos + c]
+        buf.store_batch(z, z[:, :1], torch.ones(c, dtype=torch.float32, device=dev), z, dn)
+        pos += c
+    want = np.concatenate([done[:counts[0]], done[3 + counts[0]: 3 + counts[0] + counts[1]]])
+    ends = np.flatnonzero(want)
+    hdr = buf.header.cpu().numpy()
+    assert hdr[0] == pos and hdr[1] == len(ends) and hdr[2] == ends[0] and hdr[3] == ends[-1] and hdr[4] == ends[-1] + 1
+    assert not hdr[5:].any()
+    assert np.array_equal(buf.terminal_memory[:pos].cpu().numpy().astype(bool), want)
+    start = np.zeros(pos, dtype=np.int64)
+    for e0, e1 in zip(ends[:-1], ends[1:]):
+        start[e0 + 1:e1 + 1] = e0 + 1
+    start[ends[-1] + 1:] = ends[-1] + 1
+    assert np.array_equal(buf.episode_start[:pos].cpu().numpy(), start)
