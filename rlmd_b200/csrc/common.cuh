@@ -191,25 +191,32 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
 // hist[bin] += c for the lanes with `valid`; EVERY lane of the warp must call (converged).
 // Values of one row crowd into a few histogram bins when the bins are cut from the top bits
 // of a floating-point key (few binades in a row) or when most values are equal (wealth that
-// underflowed to 0): 32 lanes hitting one shared-memory word serialise.  Two rounds of "the
-// lanes that share the first pending lane's bin add up (REDUX) and issue ONE atomic" take out
-// the two biggest crowds; what is left goes as plain atomics.
+// underflowed to 0).  B200_HIST_ROUNDS rounds of "the lanes that share the first pending lane's
+// bin add up (REDUX) and issue ONE atomic" take out the biggest crowds before the plain atomics.
+// Default 0: measured in tally_select_kernel (clock stamps, C2's 45 561 tuples), the shared-memory
+// atomic unit copes with the crowds better than the ballots / shuffles / REDUX of a round cost -
+// pass 0 of the leverage with the most ties: 8.1k cycles plain, 6.7k with one round, 9.3k with
+// two; of a leverage without: 4.2k / 6.8k / 9.2k.
+#ifndef B200_HIST_ROUNDS
+#define B200_HIST_ROUNDS 0
+#endif
 __device__ __forceinline__ void warp_hist_add(uint32_t* hist, uint32_t bin, uint32_t c, bool valid) {
   constexpr unsigned FULL = 0xffffffffu;
-  unsigned rem = __ballot_sync(FULL, valid);
-  if (rem == 0u) return;
-  const unsigned lane = threadIdx.x & 31;
+  if (B200_HIST_ROUNDS > 0) {
+    unsigned rem = __ballot_sync(FULL, valid);
+    const unsigned lane = threadIdx.x & 31;
 #pragma unroll
-  for (int round = 0; round < 2; ++round) {
-    if (rem == 0u) return;
-    const int ld = __ffs(rem) - 1;
-    const uint32_t lb = __shfl_sync(FULL, bin, ld);
-    const bool same = valid && bin == lb;
-    const unsigned grp = __ballot_sync(FULL, same);
-    const uint32_t sum = __reduce_add_sync(FULL, same ? c : 0u);
-    if (lane == (unsigned)ld && sum != 0u) atomicAdd(hist + lb, sum);
-    rem &= ~grp;
-    valid = valid && !same;
+    for (int round = 0; round < B200_HIST_ROUNDS; ++round) {
+      if (rem == 0u) return;
+      const int ld = __ffs(rem) - 1;
+      const uint32_t lb = __shfl_sync(FULL, bin, ld);
+      const bool same = valid && bin == lb;
+      const unsigned grp = __ballot_sync(FULL, same);
+      const uint32_t sum = __reduce_add_sync(FULL, same ? c : 0u);
+      if (lane == (unsigned)ld && sum != 0u) atomicAdd(hist + lb, sum);
+      rem &= ~grp;
+      valid = valid && !same;
+    }
   }
   if (valid && c != 0u) atomicAdd(hist + bin, c);
 }
