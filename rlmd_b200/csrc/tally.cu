@@ -654,6 +654,7 @@ tally_select_kernel(long long* __restrict__ header, const unsigned long long* __
       for (int j = 0; j < 4; ++j)
         if (rep[j] == j) warp_hist_add(sh.hist + j * SL2, b2, c, in && b1 == pre[j]);     // (rep is warp-uniform)
     });
+    STAMP();
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (rep[j] == j) push_hist(sh.hist + j * SL2, L->hist + j * SL2, SL2, r);
@@ -695,6 +696,7 @@ tally_select_kernel(long long* __restrict__ header, const unsigned long long* __
       for (int j = 0; j < 4; ++j)
         if (rep[j] == j) warp_hist_add(sh.hist + j * SL3, k & (SL3 - 1), c, in && hi22 == pre[j]);
     });
+    STAMP();
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (rep[j] == j) push_hist(sh.hist + j * SL3, L->hist + j * SL3, SL3, r);

@@ -12,7 +12,7 @@ for it in range(3):
     t.add(oc, 3); t.finalize(); st = t.stats(f, 100.0, h, n_total=n, top=100)
 torch.cuda.synchronize()
 w = t.ws[16:64].cpu().numpy()
-names = ["start", "zero+sync", "pass0 loop", "sums+sync", "resolve0+read", "pass1 loop", "sync", "resolve1..p2 start", "pass2 loop", "sums,resolve2,read", "pass3 loop", "block sums", "sync"]
+names = ["start", "wealth+zero+sync", "pass0 loop", "push+sums+sync", "resolve0+read", "pass1 loop", "pass1 push", "sync", "resolve1..p2 start", "pass2 loop", "pass2 push", "sums,resolve2,read", "pass3 loop", "block sums", "sync"]
 for off, tag in ((0, "g=0"), (24, "g=last")):
     s = w[off:off + 24]; s = s[s != 0]
     d = np.diff(s)
