@@ -548,11 +548,12 @@ def run_gpu(args):
         torch.cuda.synchronize()
     alone_s, = _max_over_ranks(torch, dist, dev, world, [alone_s])
     if args.stats == "tally":
-        # count kernel, compaction, [merge, mark, unique,] wealth, select
-        launches_per_step = 4 if world == 1 else 7
+        # count kernel, compaction, [merge, mark, unique,] select (profiles/r02_launches_final.csv)
+        launches_per_step = 3 if world == 1 else 6
     else:
         exchange = os.environ.get("RLMD_B200_EXCHANGE", "p2p") if world > 1 else None
-        launches_per_step = 1 + 8 + (0 if world == 1 else 4 if exchange == "p2p" else 8)
+        # sweep + 4 x (pass, resolve); across GPUs over peer memory 4 x (pass, push, owner) + 3 waits + collect
+        launches_per_step = 1 + 8 + (0 if world == 1 else 8)
 
     # ---- end to end through the reference's entry point
     e2e = None if args.no_e2e else measure_e2e(args, torch, dist, engine, lev_exp, np, dev, world, group, outcomes,
