@@ -116,6 +116,10 @@ typedef struct b200_lev_desc {
  * [G,N] log wealth: a tenth of the bytes at G = 10, and the growth-rate summaries of the whole
  * grid need ONE selection over S (b200_gbm_valid + b200_growth_summary on the row S). */
 #define B200_LEV_FLAG_STATE_OUT 2
+/* b200_tally_stats: the statistics run BESIDE another kernel (the next sweep, on another stream): the
+ * select kernel then takes two CTAs per leverage instead of six - slower alone (more bins per CTA), but it
+ * leaves the sweep its SMs (measured at 2 GPUs, statistics beside the next sweep: 0.448 against 0.469 ms per step). */
+#define B200_LEV_FLAG_BESIDE_SWEEP 4
 
 /*
  * outcomes : STREAM: uint8 [N,ld] (discrete, codes < K; or packed 2-bit codes,

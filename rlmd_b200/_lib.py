@@ -41,7 +41,7 @@ class LevDesc(C.Structure):
     ]
 
 
-LEV_FLAG_FINAL_ONLY, LEV_FLAG_STATE_OUT = 1, 2
+LEV_FLAG_FINAL_ONLY, LEV_FLAG_STATE_OUT, LEV_FLAG_BESIDE_SWEEP = 1, 2, 4
 MAX_PEERS = 8
 
 

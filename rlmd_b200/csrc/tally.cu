@@ -823,12 +823,14 @@ static void select_shape(int& cluster, int& cache) {
 template <int K>
 static int launch_select_k(int n_grid, long long* header, const unsigned long long* ukeys, const uint32_t* ucnt,
                            float* wbuf, int64_t ldw, int32_t H, const LogTable& lf, double logV0, int64_t n_total,
-                           int64_t top, double* stats, cudaStream_t st) {
+                           int64_t top, double* stats, bool beside_sweep, cudaStream_t st) {
   static bool attr_set[64] = {false};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   int C = 1, cache = 0;
   select_shape(C, cache);
+  static const bool forced = getenv("B200_SELECT_CLUSTER") != nullptr;
+  if (beside_sweep && !forced) C = 2;     // a small footprint beside a running sweep (B200_LEV_FLAG_BESIDE_SWEEP)
   const size_t dyn = (size_t)cache * 8;
   if (dev < 64 && !attr_set[dev]) {
     B200_CUDA(cudaFuncSetAttribute(tally_select_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -958,9 +960,10 @@ extern "C" int b200_tally_stats(const b200_tally_plan* plan, void* workspace, co
       lf.lm[k][g] = v;
     }
   const double logV0 = log((double)desc->value_0);
+  const bool beside = (desc->flags & B200_LEV_FLAG_BESIDE_SWEEP) != 0;
   switch (desc->n_outcomes) {
-    case 2: return launch_select_k<2>(desc->n_grid, L.header, L.ukeys, L.ucnt, L.wbuf, L.ldw, desc->horizon, lf, logV0, n_total, top, stats, st);
-    case 3: return launch_select_k<3>(desc->n_grid, L.header, L.ukeys, L.ucnt, L.wbuf, L.ldw, desc->horizon, lf, logV0, n_total, top, stats, st);
-    default: return launch_select_k<4>(desc->n_grid, L.header, L.ukeys, L.ucnt, L.wbuf, L.ldw, desc->horizon, lf, logV0, n_total, top, stats, st);
+    case 2: return launch_select_k<2>(desc->n_grid, L.header, L.ukeys, L.ucnt, L.wbuf, L.ldw, desc->horizon, lf, logV0, n_total, top, stats, beside, st);
+    case 3: return launch_select_k<3>(desc->n_grid, L.header, L.ukeys, L.ucnt, L.wbuf, L.ldw, desc->horizon, lf, logV0, n_total, top, stats, beside, st);
+    default: return launch_select_k<4>(desc->n_grid, L.header, L.ukeys, L.ucnt, L.wbuf, L.ldw, desc->horizon, lf, logV0, n_total, top, stats, beside, st);
   }
 }

@@ -730,7 +730,8 @@ class FinalSweepPipeline:
                 self.stats_stream.wait_event(swept)
                 if tally:
                     self.tallies[b].finalize()
-                    stats = self.tallies[b].stats(f, self.value_0, h, n_total=n_total, top=self.top)
+                    stats = self.tallies[b].stats(f, self.value_0, h, n_total=n_total, top=self.top,
+                                                  beside_sweep=self.depth > 1)
                 else:
                     stats = rowstats(self.data_T[b], self.top, n_total=self.n_total, group=self.group,
                                      workspace=self.ws[b])

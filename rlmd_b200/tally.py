@@ -241,8 +241,10 @@ class FinalTally:
                                           stream_ptr()))
         self.rows = 0
 
-    def stats(self, factors: np.ndarray, value_0: float, horizon: int, *, n_total: int, top: int) -> torch.Tensor:
-        """The 12 statistics (engine.STAT_NAMES order) of every grid point: float64 [G,12] on the GPU."""
+    def stats(self, factors: np.ndarray, value_0: float, horizon: int, *, n_total: int, top: int,
+              beside_sweep: bool = False) -> torch.Tensor:
+        """The 12 statistics (engine.STAT_NAMES order) of every grid point: float64 [G,12] on the GPU.
+        beside_sweep: the call runs beside another kernel (B200_LEV_FLAG_BESIDE_SWEEP: a smaller footprint)."""
         f = np.ascontiguousarray(factors, dtype=np.float32)
         if f.ndim != 2:
             raise ValueError("factors must be [G,K]")
@@ -251,6 +253,7 @@ class FinalTally:
         d = LevDesc()
         d.kind, d.mode, d.source = _lib.LEV_DISCRETE, _lib.MODE_LOG, _lib.SRC_STREAM
         d.horizon, d.n_outcomes, d.value_0 = int(horizon), k, float(value_0)
+        d.flags = _lib.LEV_FLAG_BESIDE_SWEEP if beside_sweep else 0
         with torch.cuda.device(self.dev):
             for g0 in range(0, g, self.plan.grid_cap):
                 tile = np.ascontiguousarray(f[g0:g0 + self.plan.grid_cap])

@@ -329,3 +329,21 @@ def test_merge_of_rank_tallies_on_one_gpu(world):
         assert_same_stats(got[0], ref, rtol=1e-13)
     distinct = len({tuple(c) for c in lo.counts_discrete(oc, 3)})
     assert ranks[0].info()["bins"] == distinct
+
+
+def test_pipeline_depths_agree():
+    """Statistics beside the next sweep (depth 2: two tallies, two streams, the select kernel in its two-CTA
+    shape, B200_LEV_FLAG_BESIDE_SWEEP) equal the strictly sequential pipeline and the one-shot call."""
+    from rlmd_b200 import engine
+    rs = np.random.RandomState(12)
+    n, h, top = 60_000, 500, 6
+    f = np.float32([[1.25, 0.75, 1.025], [1.5, 0.5, 1.05], [1.9, 0.1, 1.09]])
+    arrays = [engine.pack_codes(engine.encode_codes(rs.choice(3, size=(n, h), p=[1 / 6, 1 / 6, 2 / 3]).astype(np.uint8)))
+              for _ in range(5)]
+    want = [engine.lev_final_stats(f, 100.0, top, a) for a in arrays]
+    for depth in (1, 2):
+        pipe = engine.FinalSweepPipeline("discrete", f, 100.0, top, depth=depth)
+        got = [pipe.submit(a) for a in arrays]
+        pipe.synchronize()
+        for g_, w_ in zip(got, want):
+            assert T.equal(g_[:, 9:12], w_[:, 9:12]) and T.allclose(g_, w_, rtol=1e-12, atol=0), depth
