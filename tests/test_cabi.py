@@ -143,3 +143,34 @@ def test_tally_plan_sizes():
     assert b"rows_cap" in _lib.lib.b200_last_error()
     assert _lib.lib.b200_tally_workspace_bytes(C.byref(plan(10, 10, grid=65))) < 0
     assert _lib.lib.b200_tally_workspace_bytes(C.byref(plan(10, 10, world=9))) < 0
+
+
+def test_constants_match_the_header(tmp_path):
+    """The Python mirror of the header's constants (flags, limits, enums) is what a C compiler sees."""
+    import subprocess
+
+    from rlmd_b200 import _lib, sharding
+
+    pairs = {
+        "B200_MAX_PEERS": _lib.MAX_PEERS, "B200_MAX_GRID": _lib.MAX_GRID, "B200_MAX_OUTCOMES": _lib.MAX_OUTCOMES,
+        "B200_LEV_DISCRETE": _lib.LEV_DISCRETE, "B200_LEV_GBM": _lib.LEV_GBM, "B200_SRC_STREAM": _lib.SRC_STREAM,
+        "B200_SRC_PHILOX": _lib.SRC_PHILOX, "B200_MODE_CHAIN": _lib.MODE_CHAIN, "B200_MODE_LOG": _lib.MODE_LOG,
+        "B200_LEV_FLAG_FINAL_ONLY": _lib.LEV_FLAG_FINAL_ONLY, "B200_LEV_FLAG_STATE_OUT": _lib.LEV_FLAG_STATE_OUT,
+        "B200_LEV_FLAG_BESIDE_SWEEP": _lib.LEV_FLAG_BESIDE_SWEEP, "B200_TALLY_INFO_WORDS": _lib.TALLY_INFO_WORDS,
+        "B200_DT_U8": _lib.DT_U8, "B200_DT_I32": _lib.DT_I32, "B200_DT_I64": _lib.DT_I64, "B200_DT_F32": _lib.DT_F32,
+        "B200_DT_F64": _lib.DT_F64, "B200_ENV_MAX_GAMBLES": _lib.ENV_MAX_GAMBLES,
+        "B200_REPLAY_MAX_STEPS": _lib.REPLAY_MAX_STEPS, "B200_MARKET_MAX_ASSETS": _lib.MARKET_MAX_ASSETS,
+        "B200_BB_MAX_POINTS": _lib.BB_MAX_POINTS,
+        "B200_PEER_FLAG_ERROR_WORD": sharding.PeerWorkspace.ERROR_WORD,
+        "B200_PEER_FLAG_WORDS": 2 * sharding.PeerWorkspace.FLAG_WORDS,      # uint32 words in 8-byte slots
+    }
+    lines = ['#include <stdio.h>', f'#include "{HEADER}"', "int main(void){"]
+    lines += [f'printf("{name} %lld\\n", (long long)({name}));' for name in pairs]
+    lines.append("return 0;}")
+    src = tmp_path / "consts.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "consts"
+    subprocess.check_call(["gcc", "-std=c99", "-o", str(exe), str(src)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
+    for name, want in pairs.items():
+        assert int(out[name]) == int(want), (name, out[name], want)
